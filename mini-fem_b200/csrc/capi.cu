@@ -1,0 +1,812 @@
+// C ABI of the B200 assembly path (include/minifem_b200.h): host-side layout builders,
+// mesh files, and the GPU context that runs the four stages of FEM_loop
+// (src/FEM.cc:177-257).  No CPU fallback: every mfb_ctx_* call needs a CUDA device.
+#include "../../include/minifem_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../host/mesh_data.h"
+#include "../host/mesh_topology.h"
+#include "../host/tile_plan.h"
+#include "kernels.cuh"
+
+using namespace mfb;
+
+// ------------------------------------------------------------------------ errors
+
+static thread_local std::string g_lastError;
+
+static int fail (int code, const std::string &msg)
+{
+    g_lastError = msg;
+    return code;
+}
+
+#define MFB_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            return fail (MFB_ERR_CUDA, std::string (#call) + ": " + cudaGetErrorString (e_)); \
+        }                                                                                \
+    } while (0)
+
+extern "C" const char *mfb_last_error (void) { return g_lastError.c_str (); }
+extern "C" const char *mfb_version (void) { return "minifem_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------ host builders
+
+extern "C" int mfb_node_to_elem (const int *elemToNode, int nbElem, int nbNodes, int *index, int *value)
+{
+    if (!elemToNode || !index || !value || nbElem < 0 || nbNodes < 0) return fail (MFB_ERR_ARG, "mfb_node_to_elem: bad argument");
+    node_to_elem (elemToNode, nbElem, nbNodes, index, value);
+    return MFB_OK;
+}
+
+extern "C" int64_t mfb_count_edges (const int *elemToNode, int nbElem, int nbNodes)
+{
+    if ((!elemToNode && nbElem > 0) || nbElem < 0 || nbNodes < 0) return fail (MFB_ERR_ARG, "mfb_count_edges: bad argument");
+    return count_csr_entries (elemToNode, nbElem, nbNodes);
+}
+
+extern "C" int mfb_create_nodeToNode (const int *elemToNode, int nbElem, int nbNodes,
+                                      int *nodeToNodeRow, int *nodeToNodeColumn, int *nbEdgesOut)
+{
+    if (!nodeToNodeRow || (!nodeToNodeColumn && nbElem > 0) || nbElem < 0 || nbNodes < 0) {
+        return fail (MFB_ERR_ARG, "mfb_create_nodeToNode: bad argument");
+    }
+    int64_t n = build_csr (elemToNode, nbElem, nbNodes, nodeToNodeRow, nodeToNodeColumn);
+    if (n > INT32_MAX) return fail (MFB_ERR_ARG, "mfb_create_nodeToNode: more than 2^31 entries");
+    if (nbEdgesOut) *nbEdgesOut = (int)n;
+    return MFB_OK;
+}
+
+extern "C" int mfb_create_elemToEdge (const int *nodeToNodeRow, const int *nodeToNodeColumn,
+                                      const int *elemToNode, int *elemToEdge, int nbElem)
+{
+    if (!nodeToNodeRow || !nodeToNodeColumn || !elemToNode || !elemToEdge || nbElem < 0) {
+        return fail (MFB_ERR_ARG, "mfb_create_elemToEdge: bad argument");
+    }
+    if (build_elem_to_edge (nodeToNodeRow, nodeToNodeColumn, elemToNode, elemToEdge, nbElem) != 0) {
+        return fail (MFB_ERR_ARG, "mfb_create_elemToEdge: a node pair is missing from the CSR");
+    }
+    return MFB_OK;
+}
+
+extern "C" int mfb_coloring_creation (const int *elemToNode, int nbElem, int nbNodes, int *colorPart,
+                                      int *colorToElem, int *colorPerm, int *nbTotalColors)
+{
+    if (!elemToNode || !colorPart || !colorToElem || !colorPerm || !nbTotalColors || nbElem < 0) {
+        return fail (MFB_ERR_ARG, "mfb_coloring_creation: bad argument");
+    }
+    int n = color_elements (elemToNode, nbElem, nbNodes, colorPart, colorToElem, colorPerm);
+    if (n < 0) return fail (MFB_ERR_COLORS, "Error: Not enough colors.");
+    *nbTotalColors = n;
+    return MFB_OK;
+}
+
+extern "C" int mfb_permute_int_2d (int *tab, const int *perm, int nbItem, int dimItem)
+{
+    if (!tab || !perm || nbItem < 0 || dimItem < 1) return fail (MFB_ERR_ARG, "mfb_permute_int_2d: bad argument");
+    permute_rows (tab, perm, nbItem, dimItem);
+    return MFB_OK;
+}
+
+extern "C" int mfb_boundary_mask (const int *boundNodesCode, int nbNodes, int *checkBounds, int *nbBoundNodes)
+{
+    if (!boundNodesCode || !checkBounds || nbNodes < 0) return fail (MFB_ERR_ARG, "mfb_boundary_mask: bad argument");
+    int n = boundary_mask (boundNodesCode, nbNodes, checkBounds);
+    if (nbBoundNodes) *nbBoundNodes = n;
+    return MFB_OK;
+}
+
+extern "C" double mfb_double_norm (const double *tab, int64_t size) { return double_norm (tab, size); }
+
+// ------------------------------------------------------------------------ meshes
+
+struct mfb_mesh { SubMesh m; };
+
+extern "C" int mfb_mesh_generate (int nx, int ny, int nz, int px, int py, int pz, int rank,
+                                  uint64_t seed, mfb_mesh **out)
+{
+    if (!out) return fail (MFB_ERR_ARG, "mfb_mesh_generate: out is NULL");
+    mfb_mesh *mesh = new mfb_mesh ();
+    if (generate_block (nx, ny, nz, px, py, pz, rank, seed, mesh->m) != 0) {
+        delete mesh;
+        return fail (MFB_ERR_ARG, "mfb_mesh_generate: invalid grid / partition (or counts exceed 32-bit indices)");
+    }
+    *out = mesh;
+    return MFB_OK;
+}
+
+extern "C" int mfb_mesh_read (const char *file, mfb_mesh **out)
+{
+    if (!file || !out) return fail (MFB_ERR_ARG, "mfb_mesh_read: bad argument");
+    mfb_mesh *mesh = new mfb_mesh ();
+    if (read_input (file, mesh->m) != 0) {
+        delete mesh;
+        return fail (MFB_ERR_IO, std::string ("Error: cannot read input data: ") + file);
+    }
+    *out = mesh;
+    return MFB_OK;
+}
+
+extern "C" int mfb_mesh_write (const mfb_mesh *mesh, const char *file)
+{
+    if (!mesh || !file) return fail (MFB_ERR_ARG, "mfb_mesh_write: bad argument");
+    if (write_input (file, mesh->m) != 0) return fail (MFB_ERR_IO, std::string ("Error: cannot store input data: ") + file);
+    return MFB_OK;
+}
+
+extern "C" int mfb_mesh_get (const mfb_mesh *mesh, mfb_mesh_view *v)
+{
+    if (!mesh || !v) return fail (MFB_ERR_ARG, "mfb_mesh_get: bad argument");
+    SubMesh &m = const_cast<SubMesh&> (mesh->m);
+    v->nbElem = m.nbElem; v->nbNodes = m.nbNodes; v->nbEdges = m.nbEdges; v->nbIntf = m.nbIntf;
+    v->nbIntfNodes = m.nbIntfNodes; v->nbBoundNodes = m.nbBoundNodes;
+    v->coord = m.coord.data (); v->elemToNode = m.elemToNode.data ();
+    v->neighborsList = m.neighborsList.data (); v->intfIndex = m.intfIndex.data ();
+    v->intfNodes = m.intfNodes.data (); v->boundNodesCode = m.boundNodesCode.data ();
+    v->globalNode = m.globalNode.empty () ? nullptr : m.globalNode.data ();
+    return MFB_OK;
+}
+
+extern "C" void mfb_mesh_free (mfb_mesh *mesh) { delete mesh; }
+
+extern "C" void mfb_choose_blocks (int nx, int ny, int nz, int maxRanks, int *px, int *py, int *pz)
+{
+    int a = 1, b = 1, c = 1;
+    choose_blocks (nx, ny, nz, std::max (maxRanks, 1), a, b, c);
+    if (px) *px = a;
+    if (py) *py = b;
+    if (pz) *pz = c;
+}
+
+extern "C" int mfb_checking_write (const char *file, double matrixNorm, double precNorm)
+{
+    if (!file || write_checking (file, matrixNorm, precNorm) != 0) return fail (MFB_ERR_IO, "Error: cannot store reference checking.");
+    return MFB_OK;
+}
+
+extern "C" int mfb_checking_read (const char *file, double *matrixNorm, double *precNorm)
+{
+    double a = 0, b = 0;
+    if (!file || read_checking (file, a, b) != 0) {
+        return fail (MFB_ERR_IO, std::string ("Error: cannot read reference checking: ") + (file ? file : "(null)") + ".");
+    }
+    if (matrixNorm) *matrixNorm = a;
+    if (precNorm) *precNorm = b;
+    return MFB_OK;
+}
+
+// -------------------------------------------------------------------------- NCCL
+// Loaded lazily with dlopen so that the library has no link-time NCCL dependency and,
+// inside a PyTorch process, shares the libnccl.so.2 torch already mapped.
+
+namespace {
+
+struct NcclId { char internal[MFB_COMM_ID_BYTES]; };
+typedef void *NcclComm;
+
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId) (NcclId*) = nullptr;
+    int (*CommInitRank) (NcclComm*, int, NcclId, int) = nullptr;
+    int (*CommDestroy) (NcclComm) = nullptr;
+    int (*Send) (const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv) (void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart) () = nullptr;
+    int (*GroupEnd) () = nullptr;
+    const char *(*GetErrorString) (int) = nullptr;
+};
+
+const int kNcclFloat64 = 8;   // ncclDouble
+
+NcclApi *nccl_api (std::string &why)
+{
+    static NcclApi api;
+    static bool tried = false;
+    static std::string error;
+    if (!tried) {
+        tried = true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            api.lib = dlopen (n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) { error = std::string ("NCCL not found: ") + dlerror (); }
+        else {
+            bool ok = true;
+            auto sym = [&] (const char *name) { void *p = dlsym (api.lib, name); if (!p) ok = false; return p; };
+            api.GetUniqueId = (int (*) (NcclId*))sym ("ncclGetUniqueId");
+            api.CommInitRank = (int (*) (NcclComm*, int, NcclId, int))sym ("ncclCommInitRank");
+            api.CommDestroy = (int (*) (NcclComm))sym ("ncclCommDestroy");
+            api.Send = (int (*) (const void*, size_t, int, int, NcclComm, cudaStream_t))sym ("ncclSend");
+            api.Recv = (int (*) (void*, size_t, int, int, NcclComm, cudaStream_t))sym ("ncclRecv");
+            api.GroupStart = (int (*) ())sym ("ncclGroupStart");
+            api.GroupEnd = (int (*) ())sym ("ncclGroupEnd");
+            api.GetErrorString = (const char *(*) (int))sym ("ncclGetErrorString");
+            if (!ok) { error = "NCCL library lacks a required symbol"; api.lib = nullptr; }
+        }
+    }
+    why = error;
+    return api.lib ? &api : nullptr;
+}
+
+template <class T>
+cudaError_t upload (T **dst, const T *src, size_t count, int64_t &bytes)
+{
+    *dst = nullptr;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc ((void**)dst, count * sizeof (T));
+    if (e != cudaSuccess) return e;
+    bytes += (int64_t)(count * sizeof (T));
+    return src ? cudaMemcpy (*dst, src, count * sizeof (T), cudaMemcpyHostToDevice) : cudaSuccess;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------- context
+
+struct mfb_ctx {
+    int path = MFB_PATH_TILED, device = 0, threads = 256, useGraph = 0;
+    int operatorID = 0, operatorDim = 1;
+    int nbElem = 0, nbNodes = 0, nbEdges = 0, nbBlocks = 1, rank = 0;
+    int nbIntf = 0, nbIntfNodes = 0, nbUniqIntf = 0, nbTotalColors = 0;
+    std::vector<int> colorToElem, intfIndex, neighbors;
+
+    cudaStream_t stream = nullptr, commStream = nullptr;
+    cudaEvent_t evStart[5] = {}, evStop[5] = {}, evIntfDone = nullptr, evCommDone = nullptr;
+    bool stageRan[5] = {};
+
+    double *dCoord = nullptr, *dValues = nullptr, *dPrec = nullptr, *dSend = nullptr, *dRecv = nullptr;
+    int *dElemToNode = nullptr, *dRow = nullptr, *dCol = nullptr, *dElemToEdge = nullptr,
+        *dCheckBounds = nullptr, *dDiagIndex = nullptr, *dIntfNodes = nullptr, *dUniqNodes = nullptr,
+        *dSlotIndex = nullptr, *dSlots = nullptr;
+    std::vector<void*> planAllocs;
+    DeviceTilePlan plan;
+    TilePlan hostPlanStats;       // counters only (vectors released after upload)
+    size_t tiledSmem = 0;
+    int64_t meshBytes = 0, planBytes = 0, launches = 0, graphLaunches = 0;
+
+    NcclComm comm = nullptr;
+    cudaGraphExec_t graphExec = nullptr;
+};
+
+namespace {
+
+template <class T>
+cudaError_t put_plan (mfb_ctx *c, const T **dst, const std::vector<T> &vec)
+{
+    T *d = nullptr;
+    cudaError_t e = upload (&d, vec.data (), vec.size (), c->planBytes);
+    if (e == cudaSuccess) { *dst = d; c->planAllocs.push_back ((void*)d); }
+    return e;
+}
+
+int build_device_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options *o)
+{
+    std::vector<uint8_t> isIntf;
+    if (p->nbBlocks > 1 && p->nbIntfNodes > 0) {
+        isIntf.assign ((size_t)p->nbNodes, 0);
+        for (int j = 0; j < p->nbIntfNodes; j++) isIntf[p->intfNodes[j] - 1] = 1;
+    }
+    TilePlanLimits lim;
+    if (o && o->tileRows > 0) lim.maxRows = o->tileRows;
+    if (o && o->tileElems > 0) lim.maxElems = o->tileElems;
+    lim.maxNodesRef = std::min (65535, std::max (lim.maxElems, 64));   // 24 B of staging per referenced node
+    lim.maxEntries = 65535;
+    TilePlan hp;
+    std::string err;
+    if (build_tile_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn,
+                         p->coord, isIntf.empty () ? nullptr : isIntf.data (), lim, hp, err) != 0) {
+        return fail (MFB_ERR_ARG, "tile plan: " + err);
+    }
+    // make sure zero-sized vectors still upload one element (avoids null pointers in the kernel)
+    if (hp.tiles.empty ()) hp.tiles.resize (1);
+    if (hp.tileNodes.empty ()) hp.tileNodes.resize (1);
+    if (hp.tileElems.empty ()) hp.tileElems.resize (4);
+    if (hp.entryRow.empty ()) hp.entryRow.resize (1);
+    if (hp.batches.empty ()) hp.batches.resize (1);
+    if (hp.pairCodes.empty ()) hp.pairCodes.resize (1);
+    if (hp.diagCodes.empty ()) hp.diagCodes.resize (1);
+    MFB_CUDA (put_plan (c, &c->plan.tiles, hp.tiles));
+    MFB_CUDA (put_plan (c, &c->plan.tileNodes, hp.tileNodes));
+    MFB_CUDA (put_plan (c, &c->plan.tileElems, hp.tileElems));
+    MFB_CUDA (put_plan (c, &c->plan.rows, hp.rows));
+    MFB_CUDA (put_plan (c, &c->plan.entryRow, hp.entryRow));
+    MFB_CUDA (put_plan (c, &c->plan.batches, hp.batches));
+    MFB_CUDA (put_plan (c, &c->plan.pairCodes, hp.pairCodes));
+    MFB_CUDA (put_plan (c, &c->plan.diagCodes, hp.diagCodes));
+    c->plan.nbTiles = hp.nbTiles; c->plan.nbInterfaceTiles = hp.nbInterfaceTiles;
+    c->plan.maxRows = std::max (hp.maxRows, 1); c->plan.maxElems = std::max (hp.maxElems, 1);
+    c->plan.maxNodesRef = std::max (hp.maxNodesRef, 4);
+    c->hostPlanStats.nbTiles = hp.nbTiles; c->hostPlanStats.nbTileElems = hp.nbTileElems;
+    c->hostPlanStats.nbContributions = hp.nbContributions; c->hostPlanStats.maxRows = hp.maxRows;
+    c->hostPlanStats.maxElems = hp.maxElems;
+    c->tiledSmem = tiled_smem_bytes (c->operatorID, c->plan, c->threads);
+    if (c->tiledSmem > 227 * 1024) return fail (MFB_ERR_ARG, "tile plan needs more than 227 KB of shared memory per CTA; lower tileElems");
+    MFB_CUDA (tiled_configure (c->operatorID, c->tiledSmem));
+    return MFB_OK;
+}
+
+int record (mfb_ctx *c, int stage, bool start)
+{
+    MFB_CUDA (cudaEventRecord (start ? c->evStart[stage] : c->evStop[stage], c->stream));
+    if (!start) c->stageRan[stage] = true;
+    return MFB_OK;
+}
+
+int do_zero (mfb_ctx *c)
+{
+    MFB_CUDA (cudaMemsetAsync (c->dValues, 0, sizeof (double) * (size_t)c->nbEdges * c->operatorDim, c->stream));
+    return MFB_OK;
+}
+
+int do_scatter_interval (mfb_ctx *c, int first, int count)
+{
+    MFB_CUDA (launch_scatter (c->operatorID, c->path == MFB_PATH_ATOMIC, c->dCoord, c->dElemToNode,
+                              c->dElemToEdge, c->dValues, first, count, c->stream));
+    if (count > 0) c->launches++;
+    return MFB_OK;
+}
+
+// assembly(): src/assembly.cc:615-720
+int do_assembly (mfb_ctx *c, int fusePrec)
+{
+    if (c->path == MFB_PATH_TILED) {
+        MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, c->plan.nbTiles, c->threads, c->tiledSmem,
+                                c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, c->stream));
+        if (c->plan.nbTiles > 0) c->launches++;
+        return MFB_OK;
+    }
+    int rc = do_zero (c);                                  // :649-651 / :663-666
+    if (rc) return rc;
+    if (c->path == MFB_PATH_ATOMIC) return do_scatter_interval (c, 0, c->nbElem);   // :653-659
+    for (int color = 0; color < c->nbTotalColors; color++) {                        // :593-611
+        rc = do_scatter_interval (c, c->colorToElem[color], c->colorToElem[color + 1] - c->colorToElem[color]);
+        if (rc) return rc;
+    }
+    return MFB_OK;
+}
+
+int do_prec_init (mfb_ctx *c)
+{
+    MFB_CUDA (launch_prec_init (c->operatorDim, c->dPrec, c->dValues, c->dDiagIndex, c->nbNodes, c->stream));
+    if (c->nbNodes > 0) c->launches++;
+    return MFB_OK;
+}
+
+// MPI_halo_exchange(): src/halo.cc:39-122, on `s`
+int do_halo (mfb_ctx *c, cudaStream_t s)
+{
+    if (c->nbBlocks < 2 || c->nbIntf == 0) return MFB_OK;         // halo.cc:44
+    if (!c->comm) return fail (MFB_ERR_STATE, "mfb_ctx_halo_exchange: call mfb_ctx_comm_init first (nbBlocks > 1)");
+    std::string why;
+    NcclApi *api = nccl_api (why);
+    if (!api) return fail (MFB_ERR_COMM, why);
+    const int dim = c->operatorDim;
+    MFB_CUDA (launch_halo_pack (c->dSend, c->dPrec, c->dIntfNodes, dim, c->nbIntfNodes, s));
+    c->launches++;
+    int rc = api->GroupStart ();
+    for (int i = 0; i < c->nbIntf && rc == 0; i++) {
+        const size_t begin = (size_t)c->intfIndex[i] * dim, count = (size_t)(c->intfIndex[i + 1] - c->intfIndex[i]) * dim;
+        const int peer = c->neighbors[i] - 1;
+        rc = api->Recv (c->dRecv + begin, count, kNcclFloat64, peer, c->comm, s);
+        if (rc == 0) rc = api->Send (c->dSend + begin, count, kNcclFloat64, peer, c->comm, s);
+    }
+    int rc2 = api->GroupEnd ();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) return fail (MFB_ERR_COMM, std::string ("NCCL halo exchange: ") + api->GetErrorString (rc));
+    MFB_CUDA (launch_halo_add (c->dPrec, c->dRecv, c->dUniqNodes, c->dSlotIndex, c->dSlots, dim, c->nbUniqIntf, s));
+    c->launches++;
+    return MFB_OK;
+}
+
+int do_prec_inversion (mfb_ctx *c)
+{
+    MFB_CUDA (launch_prec_inversion (c->operatorID, c->dPrec, c->dDiagIndex, c->dCheckBounds, c->nbNodes, c->stream));
+    if (c->nbNodes > 0) c->launches++;
+    return MFB_OK;
+}
+
+// One FEM_loop iteration (src/FEM.cc:183-233) with no per-stage timing.
+int do_iteration (mfb_ctx *c)
+{
+    int rc;
+    if (c->path != MFB_PATH_TILED) {
+        if ((rc = do_assembly (c, 0))) return rc;
+        if ((rc = do_prec_init (c))) return rc;
+        if ((rc = do_halo (c, c->stream))) return rc;
+        return do_prec_inversion (c);
+    }
+    const bool exchange = c->nbBlocks > 1 && c->nbIntf > 0;
+    if (!exchange) return do_assembly (c, 1);
+    if (!c->comm) return fail (MFB_ERR_STATE, "mfb_ctx_iteration: call mfb_ctx_comm_init first (nbBlocks > 1)");
+    // interface tiles first; their raw diagonal blocks travel while the interior assembles
+    const int nIntfTiles = c->plan.nbInterfaceTiles;
+    MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, c->threads, c->tiledSmem, c->dCoord,
+                            c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream));
+    if (nIntfTiles > 0) c->launches++;
+    MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));
+    MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, c->threads,
+                            c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream));
+    if (c->plan.nbTiles - nIntfTiles > 0) c->launches++;
+    MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
+    if ((rc = do_halo (c, c->commStream))) return rc;
+    MFB_CUDA (launch_prec_inversion_list (c->operatorID, c->dPrec, c->dDiagIndex, c->dCheckBounds, c->nbNodes,
+                                          c->dUniqNodes, c->nbUniqIntf, c->commStream));
+    if (c->nbUniqIntf > 0) c->launches++;
+    MFB_CUDA (cudaEventRecord (c->evCommDone, c->commStream));
+    MFB_CUDA (cudaStreamWaitEvent (c->stream, c->evCommDone, 0));
+    return MFB_OK;
+}
+
+}  // namespace
+
+extern "C" int mfb_device_count (void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount (&n) != cudaSuccess) { cudaGetLastError (); return 0; }
+    return n;
+}
+
+extern "C" void mfb_ctx_destroy (mfb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice (c->device);
+    if (c->stream) cudaStreamSynchronize (c->stream);
+    if (c->commStream) cudaStreamSynchronize (c->commStream);
+    if (c->comm) { std::string why; NcclApi *api = nccl_api (why); if (api) api->CommDestroy (c->comm); }
+    if (c->graphExec) cudaGraphExecDestroy (c->graphExec);
+    void *ptrs[] = {c->dCoord, c->dValues, c->dPrec, c->dSend, c->dRecv, c->dElemToNode, c->dRow, c->dCol,
+                    c->dElemToEdge, c->dCheckBounds, c->dDiagIndex, c->dIntfNodes, c->dUniqNodes,
+                    c->dSlotIndex, c->dSlots};
+    for (void *p : ptrs) if (p) cudaFree (p);
+    for (void *p : c->planAllocs) if (p) cudaFree (p);
+    for (int s = 0; s < 5; s++) {
+        if (c->evStart[s]) cudaEventDestroy (c->evStart[s]);
+        if (c->evStop[s]) cudaEventDestroy (c->evStop[s]);
+    }
+    if (c->evIntfDone) cudaEventDestroy (c->evIntfDone);
+    if (c->evCommDone) cudaEventDestroy (c->evCommDone);
+    if (c->stream) cudaStreamDestroy (c->stream);
+    if (c->commStream) cudaStreamDestroy (c->commStream);
+    delete c;
+}
+
+static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx *c)
+{
+    c->path = o ? o->path : MFB_PATH_TILED;
+    c->device = o ? o->device : 0;
+    c->threads = (o && o->threads > 0) ? o->threads : 256;
+    c->useGraph = o ? o->useGraph : 0;
+    if (c->path < MFB_PATH_TILED || c->path > MFB_PATH_COLOR) return fail (MFB_ERR_ARG, "mfb_ctx_create: unknown path");
+    if (c->threads % 32 || c->threads < 32 || c->threads > 256) return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256]");
+    if (p->operatorID != 0 && p->operatorID != 1) return fail (MFB_ERR_ARG, "mfb_ctx_create: operatorID must be 0 (lap) or 1 (ela)");
+    if (p->nbElem < 0 || p->nbNodes < 0 || p->nbEdges < 0) return fail (MFB_ERR_ARG, "mfb_ctx_create: negative size");
+    if ((p->nbNodes > 0 && (!p->coord || !p->nodeToNodeRow)) || (p->nbElem > 0 && !p->elemToNode) ||
+        (p->nbEdges > 0 && !p->nodeToNodeColumn)) return fail (MFB_ERR_ARG, "mfb_ctx_create: missing array");
+    if (p->nbNodes > 0 && p->nodeToNodeRow[p->nbNodes] != p->nbEdges) {
+        return fail (MFB_ERR_ARG, "mfb_ctx_create: nbEdges does not match nodeToNodeRow[nbNodes]");
+    }
+    if (c->path == MFB_PATH_COLOR && (!p->colorToElem || p->nbTotalColors < 1)) {
+        return fail (MFB_ERR_ARG, "mfb_ctx_create: the COLOR path needs colorToElem / nbTotalColors (coloring.cc)");
+    }
+    if (p->nbBlocks > 1 && p->nbIntf > 0 && (!p->intfIndex || !p->intfNodes || !p->neighborsList)) {
+        return fail (MFB_ERR_ARG, "mfb_ctx_create: missing interface arrays");
+    }
+    c->operatorID = p->operatorID;
+    c->operatorDim = p->operatorID == 0 ? 1 : 9;
+    c->nbElem = p->nbElem; c->nbNodes = p->nbNodes; c->nbEdges = p->nbEdges;
+    c->nbBlocks = std::max (p->nbBlocks, 1); c->rank = p->rank;
+    c->nbIntf = c->nbBlocks > 1 ? p->nbIntf : 0;
+    c->nbIntfNodes = c->nbBlocks > 1 ? p->nbIntfNodes : 0;
+
+    int count = 0;
+    if (cudaGetDeviceCount (&count) != cudaSuccess || count == 0) {
+        cudaGetLastError ();
+        return fail (MFB_ERR_CUDA, "mfb_ctx_create: no CUDA device (this path has no CPU fallback)");
+    }
+    MFB_CUDA (cudaSetDevice (c->device));
+    MFB_CUDA (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
+    MFB_CUDA (cudaStreamCreateWithFlags (&c->commStream, cudaStreamNonBlocking));
+    for (int s = 0; s < 5; s++) { MFB_CUDA (cudaEventCreate (&c->evStart[s])); MFB_CUDA (cudaEventCreate (&c->evStop[s])); }
+    MFB_CUDA (cudaEventCreateWithFlags (&c->evIntfDone, cudaEventDisableTiming));
+    MFB_CUDA (cudaEventCreateWithFlags (&c->evCommDone, cudaEventDisableTiming));
+
+    MFB_CUDA (upload (&c->dCoord, p->coord, (size_t)p->nbNodes * 3, c->meshBytes));
+    MFB_CUDA (upload (&c->dRow, p->nodeToNodeRow, (size_t)p->nbNodes + 1, c->meshBytes));
+    MFB_CUDA (upload (&c->dCol, p->nodeToNodeColumn, (size_t)p->nbEdges, c->meshBytes));
+    MFB_CUDA (upload (&c->dCheckBounds, p->checkBounds, p->checkBounds ? (size_t)p->nbNodes * 3 : 0, c->meshBytes));
+    MFB_CUDA (upload<double> (&c->dValues, nullptr, std::max<size_t> ((size_t)p->nbEdges * c->operatorDim, 1), c->meshBytes));
+    MFB_CUDA (upload<double> (&c->dPrec, nullptr, std::max<size_t> ((size_t)p->nbNodes * c->operatorDim, 1), c->meshBytes));
+    MFB_CUDA (upload<int> (&c->dDiagIndex, nullptr, std::max<size_t> ((size_t)p->nbNodes, 1), c->meshBytes));
+    MFB_CUDA (launch_diag_index (c->dRow, c->dCol, c->dDiagIndex, c->nbNodes, c->stream));
+
+    if (c->path != MFB_PATH_TILED) {
+        MFB_CUDA (upload (&c->dElemToNode, p->elemToNode, (size_t)p->nbElem * 4, c->meshBytes));
+        MFB_CUDA (upload (&c->dElemToEdge, p->elemToEdge, (size_t)p->nbElem * 16, c->meshBytes));
+        if (!p->elemToEdge && p->nbElem > 0) {            // create_elemToEdge on the device
+            int *dMissing = nullptr, missing = 0;
+            MFB_CUDA (cudaMalloc ((void**)&dMissing, sizeof (int)));
+            MFB_CUDA (cudaMemsetAsync (dMissing, 0, sizeof (int), c->stream));
+            MFB_CUDA (launch_elem_to_edge (c->dRow, c->dCol, c->dElemToNode, c->dElemToEdge, c->nbElem, dMissing, c->stream));
+            MFB_CUDA (cudaMemcpyAsync (&missing, dMissing, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+            MFB_CUDA (cudaStreamSynchronize (c->stream));
+            cudaFree (dMissing);
+            if (missing) return fail (MFB_ERR_ARG, "mfb_ctx_create: the CSR lacks a node pair of an element");
+        }
+        if (c->path == MFB_PATH_COLOR) {
+            c->nbTotalColors = p->nbTotalColors;
+            c->colorToElem.assign (p->colorToElem, p->colorToElem + p->nbTotalColors + 1);
+            if (c->colorToElem[0] != 0 || c->colorToElem[p->nbTotalColors] != p->nbElem) {
+                return fail (MFB_ERR_ARG, "mfb_ctx_create: colorToElem does not cover [0, nbElem)");
+            }
+        }
+    }
+    else {
+        int rc = build_device_plan (c, p, o);
+        if (rc) return rc;
+    }
+
+    if (c->nbIntf > 0) {
+        c->intfIndex.assign (p->intfIndex, p->intfIndex + p->nbIntf + 1);
+        c->neighbors.assign (p->neighborsList, p->neighborsList + p->nbIntf);
+        if (c->intfIndex[p->nbIntf] != p->nbIntfNodes) return fail (MFB_ERR_ARG, "mfb_ctx_create: intfIndex / nbIntfNodes mismatch");
+        for (int j = 0; j < p->nbIntfNodes; j++) {
+            if (p->intfNodes[j] < 1 || p->intfNodes[j] > p->nbNodes) return fail (MFB_ERR_ARG, "mfb_ctx_create: interface node id out of range");
+        }
+        // unique interface nodes and, for each, its positions j in increasing order
+        std::vector<std::pair<int, int>> byNode ((size_t)p->nbIntfNodes);
+        for (int j = 0; j < p->nbIntfNodes; j++) byNode[j] = {p->intfNodes[j] - 1, j};
+        std::sort (byNode.begin (), byNode.end ());
+        std::vector<int> uniq, slotIndex (1, 0), slots;
+        for (size_t k = 0; k < byNode.size (); k++) {
+            if (k == 0 || byNode[k].first != byNode[k - 1].first) {
+                if (k) slotIndex.push_back ((int)slots.size ());
+                uniq.push_back (byNode[k].first);
+            }
+            slots.push_back (byNode[k].second);
+        }
+        slotIndex.push_back ((int)slots.size ());
+        c->nbUniqIntf = (int)uniq.size ();
+        const size_t bufDoubles = (size_t)p->nbIntfNodes * c->operatorDim;
+        MFB_CUDA (upload (&c->dIntfNodes, p->intfNodes, (size_t)p->nbIntfNodes, c->meshBytes));
+        MFB_CUDA (upload (&c->dUniqNodes, uniq.data (), uniq.size (), c->meshBytes));
+        MFB_CUDA (upload (&c->dSlotIndex, slotIndex.data (), slotIndex.size (), c->meshBytes));
+        MFB_CUDA (upload (&c->dSlots, slots.data (), slots.size (), c->meshBytes));
+        MFB_CUDA (upload<double> (&c->dSend, nullptr, bufDoubles, c->meshBytes));
+        MFB_CUDA (upload<double> (&c->dRecv, nullptr, bufDoubles, c->meshBytes));
+    }
+    MFB_CUDA (cudaStreamSynchronize (c->stream));
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_create (const mfb_problem *problem, const mfb_options *options, mfb_ctx **out)
+{
+    if (!problem || !out) return fail (MFB_ERR_ARG, "mfb_ctx_create: NULL argument");
+    *out = nullptr;
+    mfb_ctx *c = new mfb_ctx ();
+    int rc = ctx_create_impl (problem, options, c);
+    if (rc != MFB_OK) {
+        std::string keep = g_lastError;
+        mfb_ctx_destroy (c);
+        g_lastError = keep;
+        return rc;
+    }
+    *out = c;
+    return MFB_OK;
+}
+
+#define CTX_ENTER(c)                                                        \
+    if (!(c)) return fail (MFB_ERR_ARG, "NULL context");                    \
+    MFB_CUDA (cudaSetDevice ((c)->device))
+
+extern "C" int mfb_ctx_zero_values (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    return do_zero (c);
+}
+
+extern "C" int mfb_ctx_assembly_interval (mfb_ctx *c, int firstElem, int lastElem)
+{
+    CTX_ENTER (c);
+    if (c->path == MFB_PATH_TILED) return fail (MFB_ERR_STATE, "mfb_ctx_assembly_interval: element intervals exist on the ATOMIC / COLOR paths only");
+    if (firstElem < 0 || lastElem >= c->nbElem) return fail (MFB_ERR_ARG, "mfb_ctx_assembly_interval: interval out of range");
+    return do_scatter_interval (c, firstElem, lastElem - firstElem + 1);
+}
+
+extern "C" int mfb_ctx_assembly (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    int rc = record (c, 0, true);
+    if (!rc) rc = do_assembly (c, 0);
+    if (!rc) rc = record (c, 0, false);
+    return rc;
+}
+
+extern "C" int mfb_ctx_prec_init (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    int rc = record (c, 1, true);
+    if (!rc) rc = do_prec_init (c);
+    if (!rc) rc = record (c, 1, false);
+    return rc;
+}
+
+extern "C" int mfb_ctx_halo_exchange (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    int rc = record (c, 2, true);
+    if (!rc) rc = do_halo (c, c->stream);
+    if (!rc) rc = record (c, 2, false);
+    return rc;
+}
+
+extern "C" int mfb_ctx_prec_inversion (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    int rc = record (c, 3, true);
+    if (!rc) rc = do_prec_inversion (c);
+    if (!rc) rc = record (c, 3, false);
+    return rc;
+}
+
+extern "C" int mfb_ctx_iteration (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    int rc = record (c, 4, true);
+    if (rc) return rc;
+    const bool graphable = c->useGraph && c->nbBlocks < 2;
+    if (graphable) {
+        if (!c->graphExec) {
+            cudaGraph_t graph = nullptr;
+            const int64_t before = c->launches;
+            MFB_CUDA (cudaStreamBeginCapture (c->stream, cudaStreamCaptureModeThreadLocal));
+            rc = do_iteration (c);
+            cudaError_t e = cudaStreamEndCapture (c->stream, &graph);
+            c->graphLaunches = c->launches - before;      // kernels one replay runs
+            c->launches = before;
+            if (rc) { if (graph) cudaGraphDestroy (graph); return rc; }
+            MFB_CUDA (e);
+            MFB_CUDA (cudaGraphInstantiate (&c->graphExec, graph, 0));
+            cudaGraphDestroy (graph);
+        }
+        MFB_CUDA (cudaGraphLaunch (c->graphExec, c->stream));
+        c->launches += c->graphLaunches;
+    }
+    else {
+        rc = do_iteration (c);
+        if (rc) return rc;
+    }
+    return record (c, 4, false);
+}
+
+extern "C" int mfb_ctx_sync (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    MFB_CUDA (cudaStreamSynchronize (c->stream));
+    MFB_CUDA (cudaStreamSynchronize (c->commStream));
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_download (mfb_ctx *c, double *nodeToNodeValue, double *prec)
+{
+    CTX_ENTER (c);
+    if (nodeToNodeValue && c->nbEdges > 0) {
+        MFB_CUDA (cudaMemcpyAsync (nodeToNodeValue, c->dValues, sizeof (double) * (size_t)c->nbEdges * c->operatorDim,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (prec && c->nbNodes > 0) {
+        MFB_CUDA (cudaMemcpyAsync (prec, c->dPrec, sizeof (double) * (size_t)c->nbNodes * c->operatorDim,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    }
+    MFB_CUDA (cudaStreamSynchronize (c->stream));
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_upload_coord (mfb_ctx *c, const double *coord)
+{
+    CTX_ENTER (c);
+    if (!coord) return fail (MFB_ERR_ARG, "mfb_ctx_upload_coord: NULL");
+    if (c->nbNodes > 0) {
+        MFB_CUDA (cudaMemcpyAsync (c->dCoord, coord, sizeof (double) * (size_t)c->nbNodes * 3, cudaMemcpyHostToDevice, c->stream));
+    }
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_iteration_host (mfb_ctx *c, const double *coord, double *nodeToNodeValue, double *prec)
+{
+    int rc = mfb_ctx_upload_coord (c, coord);
+    if (!rc) rc = mfb_ctx_iteration (c);
+    if (!rc) rc = mfb_ctx_download (c, nodeToNodeValue, prec);
+    return rc;
+}
+
+extern "C" int mfb_ctx_device_ptrs (mfb_ctx *c, void **values, void **prec)
+{
+    if (!c) return fail (MFB_ERR_ARG, "NULL context");
+    if (values) *values = c->dValues;
+    if (prec) *prec = c->dPrec;
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_stream (mfb_ctx *c, void **stream)
+{
+    if (!c || !stream) return fail (MFB_ERR_ARG, "NULL argument");
+    *stream = (void*)c->stream;
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_stage_ms (mfb_ctx *c, float ms[5])
+{
+    CTX_ENTER (c);
+    for (int s = 0; s < 5; s++) {
+        ms[s] = 0.f;
+        if (!c->stageRan[s]) continue;
+        MFB_CUDA (cudaEventSynchronize (c->evStop[s]));
+        MFB_CUDA (cudaEventElapsedTime (&ms[s], c->evStart[s], c->evStop[s]));
+    }
+    return MFB_OK;
+}
+
+extern "C" int64_t mfb_ctx_launch_count (mfb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int mfb_ctx_device_bytes (mfb_ctx *c, int64_t *meshBytes, int64_t *planBytes)
+{
+    if (!c) return fail (MFB_ERR_ARG, "NULL context");
+    if (meshBytes) *meshBytes = c->meshBytes;
+    if (planBytes) *planBytes = c->planBytes;
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_plan_stats (mfb_ctx *c, int64_t stats[6])
+{
+    if (!c || !stats) return fail (MFB_ERR_ARG, "NULL argument");
+    stats[0] = c->hostPlanStats.nbTiles; stats[1] = c->hostPlanStats.nbTileElems;
+    stats[2] = c->hostPlanStats.nbContributions; stats[3] = c->hostPlanStats.maxRows;
+    stats[4] = c->hostPlanStats.maxElems; stats[5] = (int64_t)c->tiledSmem;
+    return MFB_OK;
+}
+
+extern "C" int mfb_comm_unique_id (unsigned char id[MFB_COMM_ID_BYTES])
+{
+    std::string why;
+    NcclApi *api = nccl_api (why);
+    if (!api) return fail (MFB_ERR_COMM, why);
+    NcclId nid;
+    int rc = api->GetUniqueId (&nid);
+    if (rc != 0) return fail (MFB_ERR_COMM, std::string ("ncclGetUniqueId: ") + api->GetErrorString (rc));
+    memcpy (id, nid.internal, MFB_COMM_ID_BYTES);
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_comm_init (mfb_ctx *c, const unsigned char id[MFB_COMM_ID_BYTES])
+{
+    CTX_ENTER (c);
+    if (c->nbBlocks < 2) return MFB_OK;
+    std::string why;
+    NcclApi *api = nccl_api (why);
+    if (!api) return fail (MFB_ERR_COMM, why);
+    NcclId nid;
+    memcpy (nid.internal, id, MFB_COMM_ID_BYTES);
+    int rc = api->CommInitRank (&c->comm, c->nbBlocks, nid, c->rank);
+    if (rc != 0) { c->comm = nullptr; return fail (MFB_ERR_COMM, std::string ("ncclCommInitRank: ") + api->GetErrorString (rc)); }
+    return MFB_OK;
+}
+
+extern "C" int mfb_host_alloc (void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return fail (MFB_ERR_ARG, "mfb_host_alloc: bad argument");
+    MFB_CUDA (cudaMallocHost (ptr, (size_t)std::max<int64_t> (bytes, 1)));
+    return MFB_OK;
+}
+
+extern "C" void mfb_host_free (void *ptr) { if (ptr) cudaFreeHost (ptr); }

@@ -1,0 +1,59 @@
+// Launchers of every kernel on the path (definitions in kernels_*.cu).
+#ifndef MFB_KERNELS_CUH
+#define MFB_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../host/tile_plan.h"
+
+namespace mfb {
+
+// ATOMIC / COLOR element kernels over an element interval [firstElem, firstElem+count).
+cudaError_t launch_scatter (int operatorID, bool atomic, const double *coord, const int *elemToNode,
+                            const int *elemToEdge, double *values, int firstElem, int count,
+                            cudaStream_t stream);
+cudaError_t launch_elem_to_edge (const int *row, const int *col, const int *elemToNode,
+                                 int *elemToEdge, int nbElem, int *missing, cudaStream_t stream);
+cudaError_t launch_diag_index (const int *row, const int *col, int *diagIndex, int nbNodes,
+                               cudaStream_t stream);
+
+cudaError_t launch_prec_init (int operatorDim, double *prec, const double *values,
+                              const int *diagIndex, int nbNodes, cudaStream_t stream);
+cudaError_t launch_prec_inversion (int operatorID, double *prec, const int *diagIndex,
+                                   const int *checkBounds, int nbNodes, cudaStream_t stream);
+cudaError_t launch_prec_inversion_list (int operatorID, double *prec, const int *diagIndex,
+                                        const int *checkBounds, int nbNodes, const int *nodes,
+                                        int count, cudaStream_t stream);
+cudaError_t launch_halo_pack (double *sendBuf, const double *prec, const int *intfNodes, int dim,
+                              int nbIntfNodes, cudaStream_t stream);
+cudaError_t launch_halo_add (double *prec, const double *recvBuf, const int *uniqNodes,
+                             const int *slotIndex, const int *slots, int dim, int nbUniq,
+                             cudaStream_t stream);
+
+// Device copy of a TilePlan.
+struct DeviceTilePlan {
+    const TileHeader *tiles = nullptr;
+    const int *tileNodes = nullptr;
+    const uint16_t *tileElems = nullptr;
+    const TileRow *rows = nullptr;
+    const uint8_t *entryRow = nullptr;
+    const TileBatch *batches = nullptr;
+    const uint16_t *pairCodes = nullptr;
+    const uint16_t *diagCodes = nullptr;
+    int nbTiles = 0, nbInterfaceTiles = 0;
+    int maxRows = 0, maxElems = 0, maxNodesRef = 0;
+};
+
+// fusePrec: 0 = values only; 1 = also write prec: the raw diagonal block for interface
+// nodes (they still need the halo sum), the masked + inverted block for all others.
+size_t tiled_smem_bytes (int operatorID, const DeviceTilePlan &plan, int threads);
+cudaError_t tiled_configure (int operatorID, size_t smemBytes);
+cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstTile, int nbTiles,
+                          int threads, size_t smemBytes, const double *coord, double *values,
+                          double *prec, const int *checkBounds, int nbNodes, int fusePrec,
+                          cudaStream_t stream);
+
+}  // namespace mfb
+
+#endif

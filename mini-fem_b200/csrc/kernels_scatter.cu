@@ -1,0 +1,136 @@
+// Element-parallel scatter-add kernels: the ATOMIC path (native FP64 red.global.add)
+// and the COLOR path (plain read-modify-write inside one of the reference's colours).
+// Both do, per element, what assembly_{lap,ela}_seq do (src/assembly.cc:485-588,
+// :332-479) through the precomputed elemToEdge index (the OPTIMIZED variant, :380-412
+// / :533-544); they differ only in how a contribution reaches nodeToNodeValue.
+//
+// Also here: the once-per-context index kernels (elemToEdge on the GPU, diagonal index).
+#include "kernels.cuh"
+#include "device_math.cuh"
+
+namespace mfb {
+
+namespace {
+
+template <bool ATOMIC>
+__device__ __forceinline__ void accumulate (double *addr, double v)
+{
+    if (ATOMIC) atomicAdd (addr, v);       // RED.E.ADD.F64 (result unused)
+    else        *addr += v;                // conflict-free by colouring
+}
+
+template <int OPDIM, bool ATOMIC>
+__global__ void __launch_bounds__(128)
+scatter_elements_kernel (const double *__restrict__ coord, const int4 *__restrict__ elemToNode,
+                         const int4 *__restrict__ elemToEdge, double *__restrict__ values,
+                         int firstElem, int nbElemInterval)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbElemInterval) return;
+    const size_t e = (size_t)firstElem + t;
+
+    const int4 nd = __ldg (elemToNode + e);                 // 1-based ids, one 16 B load
+    const int ids[4] = {nd.x - 1, nd.y - 1, nd.z - 1, nd.w - 1};
+    double p[12], c[12];
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double *q = coord + (size_t)ids[i] * 3;
+        p[3 * i] = __ldg (q); p[3 * i + 1] = __ldg (q + 1); p[3 * i + 2] = __ldg (q + 2);
+    }
+    elem_coef (p, c);
+
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int4 idx4 = __ldg (elemToEdge + e * 4 + j);
+        const int idx[4] = {idx4.x, idx4.y, idx4.z, idx4.w};
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (OPDIM == 1) {
+                const double v = c[3 * j] * c[3 * k] + c[3 * j + 1] * c[3 * k + 1] + c[3 * j + 2] * c[3 * k + 2];
+                accumulate<ATOMIC> (values + idx[k], v);
+            }
+            else {
+                double blk[9];
+                ela_block (c + 3 * j, c + 3 * k, blk);
+                double *dst = values + (size_t)idx[k] * 9;
+                #pragma unroll
+                for (int q = 0; q < 9; q++) accumulate<ATOMIC> (dst + q, blk[q]);
+            }
+        }
+    }
+}
+
+// create_elemToEdge (src/matrix.cc:25-52) on the device: one thread per (element, j, k).
+__global__ void elem_to_edge_kernel (const int *__restrict__ row, const int *__restrict__ col,
+                                     const int *__restrict__ elemToNode, int *__restrict__ elemToEdge,
+                                     size_t nbPairs, int *__restrict__ missing)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbPairs) return;
+    const size_t e = t >> 4;
+    const int j = (t >> 2) & 3, k = t & 3;
+    const int n1 = elemToNode[e * 4 + j] - 1, n2 = elemToNode[e * 4 + k];
+    int found = -1;
+    for (int l = row[n1]; l < row[n1 + 1]; l++) {
+        if (col[l] == n2) { found = l; break; }
+    }
+    if (found < 0) atomicAdd (missing, 1);
+    elemToEdge[t] = found;
+}
+
+// Position of each node's own column in its row (prec_init's search,
+// src/preconditioner.cc:78-79), -1 if the row has none.
+__global__ void diag_index_kernel (const int *__restrict__ row, const int *__restrict__ col,
+                                   int *__restrict__ diagIndex, int nbNodes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbNodes) return;
+    int found = -1;
+    for (int j = row[i]; j < row[i + 1]; j++) {
+        if (col[j] - 1 == i) { found = j; break; }
+    }
+    diagIndex[i] = found;
+}
+
+}  // namespace
+
+cudaError_t launch_scatter (int operatorID, bool atomic, const double *coord, const int *elemToNode,
+                            const int *elemToEdge, double *values, int firstElem, int count,
+                            cudaStream_t stream)
+{
+    if (count <= 0) return cudaSuccess;
+    const int threads = 128, blocks = (count + threads - 1) / threads;
+    const int4 *e2n = reinterpret_cast<const int4*> (elemToNode);
+    const int4 *e2e = reinterpret_cast<const int4*> (elemToEdge);
+    if (operatorID == 0) {
+        if (atomic) scatter_elements_kernel<1, true><<<blocks, threads, 0, stream>>> (coord, e2n, e2e, values, firstElem, count);
+        else        scatter_elements_kernel<1, false><<<blocks, threads, 0, stream>>> (coord, e2n, e2e, values, firstElem, count);
+    }
+    else {
+        if (atomic) scatter_elements_kernel<9, true><<<blocks, threads, 0, stream>>> (coord, e2n, e2e, values, firstElem, count);
+        else        scatter_elements_kernel<9, false><<<blocks, threads, 0, stream>>> (coord, e2n, e2e, values, firstElem, count);
+    }
+    return cudaGetLastError ();
+}
+
+cudaError_t launch_elem_to_edge (const int *row, const int *col, const int *elemToNode,
+                                 int *elemToEdge, int nbElem, int *missing, cudaStream_t stream)
+{
+    const size_t pairs = (size_t)nbElem * 16;
+    if (pairs == 0) return cudaSuccess;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((pairs + threads - 1) / threads);
+    elem_to_edge_kernel<<<blocks, threads, 0, stream>>> (row, col, elemToNode, elemToEdge, pairs, missing);
+    return cudaGetLastError ();
+}
+
+cudaError_t launch_diag_index (const int *row, const int *col, int *diagIndex, int nbNodes,
+                               cudaStream_t stream)
+{
+    if (nbNodes <= 0) return cudaSuccess;
+    const int threads = 256, blocks = (nbNodes + threads - 1) / threads;
+    diag_index_kernel<<<blocks, threads, 0, stream>>> (row, col, diagIndex, nbNodes);
+    return cudaGetLastError ();
+}
+
+}  // namespace mfb
