@@ -192,6 +192,30 @@ int mfb_ctx_plan_stats (mfb_ctx *ctx, int64_t stats[6]);
 int mfb_comm_unique_id (unsigned char id[MFB_COMM_ID_BYTES]);              /* rank 0, then broadcast */
 int mfb_ctx_comm_init (mfb_ctx *ctx, const unsigned char id[MFB_COMM_ID_BYTES]);
 
+/* The two halves of the halo exchange with the transport left to the caller (tests, or a
+ * host MPI): pack = halo.cc:77-80 into sendBuf[nbIntfNodes*operatorDim]; add = halo.cc:113-116
+ * from recvBuf laid out like bufferRecv (segment i at intfIndex[i]*operatorDim). */
+int mfb_ctx_halo_pack_host (mfb_ctx *ctx, double *sendBuf);
+int mfb_ctx_halo_add_host (mfb_ctx *ctx, const double *recvBuf);
+/* TILED only: the fused kernel of mfb_ctx_iteration without the exchange — values, plus
+ * prec holding the inverted block of every non-interface node and the raw diagonal block of
+ * every interface node (assembly + prec_init + the interior part of prec_inversion). */
+int mfb_ctx_assembly_fused (mfb_ctx *ctx);
+/* Inversion restricted to the interface nodes (what the fused iteration leaves undone
+ * until the halo sum has arrived). */
+int mfb_ctx_prec_inversion_interface (mfb_ctx *ctx);
+
+/* `steps` back-to-back fused iterations bracketed by CUDA events on the context's stream;
+ * *ms = total device time.  Used by bench.py for the kernel-time roofline. */
+int mfb_ctx_run_timed (mfb_ctx *ctx, int steps, float *ms);
+
+/* Builds the TILED plan on the host and verifies its invariants without a GPU: every
+ * (element, j, k) contribution of the reference's double loop (assembly.cc:382-412) appears
+ * exactly once, on the CSR entry elemToEdge names.  stats: [0] tiles [1] tile elements
+ * [2] contributions [3] max rows [4] max elems [5] plan bytes. */
+int mfb_tile_plan_selfcheck (const mfb_problem *problem, int tileRows, int tileElems,
+                             int64_t stats[6]);
+
 /* Pinned host memory for the *_host calls. */
 int mfb_host_alloc (void **ptr, int64_t bytes);
 void mfb_host_free (void *ptr);

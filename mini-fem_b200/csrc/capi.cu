@@ -802,6 +802,99 @@ extern "C" int mfb_ctx_comm_init (mfb_ctx *c, const unsigned char id[MFB_COMM_ID
     return MFB_OK;
 }
 
+extern "C" int mfb_ctx_halo_pack_host (mfb_ctx *c, double *sendBuf)
+{
+    CTX_ENTER (c);
+    if (c->nbIntfNodes == 0) return MFB_OK;
+    if (!sendBuf) return fail (MFB_ERR_ARG, "mfb_ctx_halo_pack_host: NULL buffer");
+    MFB_CUDA (launch_halo_pack (c->dSend, c->dPrec, c->dIntfNodes, c->operatorDim, c->nbIntfNodes, c->stream));
+    c->launches++;
+    MFB_CUDA (cudaMemcpyAsync (sendBuf, c->dSend, sizeof (double) * (size_t)c->nbIntfNodes * c->operatorDim,
+                               cudaMemcpyDeviceToHost, c->stream));
+    MFB_CUDA (cudaStreamSynchronize (c->stream));
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_halo_add_host (mfb_ctx *c, const double *recvBuf)
+{
+    CTX_ENTER (c);
+    if (c->nbIntfNodes == 0) return MFB_OK;
+    if (!recvBuf) return fail (MFB_ERR_ARG, "mfb_ctx_halo_add_host: NULL buffer");
+    MFB_CUDA (cudaMemcpyAsync (c->dRecv, recvBuf, sizeof (double) * (size_t)c->nbIntfNodes * c->operatorDim,
+                               cudaMemcpyHostToDevice, c->stream));
+    MFB_CUDA (launch_halo_add (c->dPrec, c->dRecv, c->dUniqNodes, c->dSlotIndex, c->dSlots, c->operatorDim,
+                               c->nbUniqIntf, c->stream));
+    c->launches++;
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_assembly_fused (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    if (c->path != MFB_PATH_TILED) return fail (MFB_ERR_STATE, "mfb_ctx_assembly_fused: only the TILED path fuses the preconditioner into assembly");
+    int rc = record (c, 0, true);
+    if (!rc) rc = do_assembly (c, 1);
+    if (!rc) rc = record (c, 0, false);
+    return rc;
+}
+
+extern "C" int mfb_ctx_prec_inversion_interface (mfb_ctx *c)
+{
+    CTX_ENTER (c);
+    MFB_CUDA (launch_prec_inversion_list (c->operatorID, c->dPrec, c->dDiagIndex, c->dCheckBounds, c->nbNodes,
+                                          c->dUniqNodes, c->nbUniqIntf, c->stream));
+    if (c->nbUniqIntf > 0) c->launches++;
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_run_timed (mfb_ctx *c, int steps, float *ms)
+{
+    CTX_ENTER (c);
+    if (steps < 1 || !ms) return fail (MFB_ERR_ARG, "mfb_ctx_run_timed: bad argument");
+    MFB_CUDA (cudaStreamSynchronize (c->commStream));
+    MFB_CUDA (cudaEventRecord (c->evStart[4], c->stream));
+    for (int k = 0; k < steps; k++) {
+        int rc;
+        if (c->useGraph && c->nbBlocks < 2 && c->graphExec) {
+            MFB_CUDA (cudaGraphLaunch (c->graphExec, c->stream));
+            c->launches += c->graphLaunches;
+        }
+        else if ((rc = do_iteration (c))) return rc;
+    }
+    MFB_CUDA (cudaEventRecord (c->evStop[4], c->stream));
+    MFB_CUDA (cudaEventSynchronize (c->evStop[4]));
+    MFB_CUDA (cudaEventElapsedTime (ms, c->evStart[4], c->evStop[4]));
+    c->stageRan[4] = true;
+    return MFB_OK;
+}
+
+extern "C" int mfb_tile_plan_selfcheck (const mfb_problem *p, int tileRows, int tileElems, int64_t stats[6])
+{
+    if (!p || !stats) return fail (MFB_ERR_ARG, "mfb_tile_plan_selfcheck: NULL argument");
+    TilePlanLimits lim;
+    if (tileRows > 0) lim.maxRows = tileRows;
+    if (tileElems > 0) lim.maxElems = tileElems;
+    lim.maxNodesRef = std::min (65535, std::max (lim.maxElems, 64));
+    lim.maxEntries = 65535;
+    std::vector<uint8_t> isIntf;
+    if (p->nbBlocks > 1 && p->nbIntfNodes > 0) {
+        isIntf.assign ((size_t)p->nbNodes, 0);
+        for (int j = 0; j < p->nbIntfNodes; j++) isIntf[p->intfNodes[j] - 1] = 1;
+    }
+    TilePlan plan;
+    std::string err;
+    if (build_tile_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, p->coord,
+                         isIntf.empty () ? nullptr : isIntf.data (), lim, plan, err) != 0) {
+        return fail (MFB_ERR_ARG, "tile plan: " + err);
+    }
+    if (verify_tile_plan (plan, p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, err) != 0) {
+        return fail (MFB_ERR_STATE, "tile plan self-check: " + err);
+    }
+    stats[0] = plan.nbTiles; stats[1] = plan.nbTileElems; stats[2] = plan.nbContributions;
+    stats[3] = plan.maxRows; stats[4] = plan.maxElems; stats[5] = plan.bytes ();
+    return MFB_OK;
+}
+
 extern "C" int mfb_host_alloc (void **ptr, int64_t bytes)
 {
     if (!ptr || bytes < 0) return fail (MFB_ERR_ARG, "mfb_host_alloc: bad argument");

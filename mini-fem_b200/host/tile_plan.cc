@@ -292,3 +292,118 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
 }
 
 }  // namespace mfb
+
+namespace mfb {
+
+int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *elemToNode,
+                      const int *row, const int *col, std::string &error)
+{
+    std::vector<uint8_t> rowSeen ((size_t)nbNodes, 0);
+    std::vector<uint16_t> tripleSeen ((size_t)nbElem, 0);      // bit 4j+k per element
+    int64_t rowsTotal = 0;
+    for (int t = 0; t < plan.nbTiles; t++) {
+        const TileHeader &h = plan.tiles[t];
+        // global element of each tile-local element, recovered from its 4 node ids
+        for (int r = 0; r < h.nbRows; r++) {
+            const TileRow &tr = plan.rows[h.rowBase + r];
+            const int n = tr.node & 0x7fffffff;
+            if (n < 0 || n >= nbNodes || rowSeen[n]) { error = "row owned twice or out of range"; return -1; }
+            rowSeen[n] = 1;
+            rowsTotal++;
+            if (plan.tileNodes[h.nodeBase + r] != n) { error = "owned rows must lead the tile's node list"; return -1; }
+            if (tr.valueStart != row[n]) { error = "row offset differs from nodeToNodeRow"; return -1; }
+            const int len = row[n + 1] - row[n];
+            for (int l = 0; l < len; l++) {
+                if (plan.entryRow[h.entryBase + tr.localStart + l] != r) { error = "entryRow mismatch"; return -1; }
+            }
+            // diagonal codes: one per incident element, local index a must be this node
+            const int dEnd = plan.rows[h.rowBase + r + 1].diagCodeBase;
+            for (int k = tr.diagCodeBase; k < dEnd; k++) {
+                const int code = plan.diagCodes[k], el = code >> 2, a = code & 3;
+                if (el >= h.nbElems) { error = "diagonal code names a foreign element"; return -1; }
+                const uint16_t *ln = &plan.tileElems[((size_t)h.elemBase + el) * 4];
+                if (plan.tileNodes[h.nodeBase + ln[a]] != n) { error = "diagonal code: wrong local node"; return -1; }
+                if (tr.diagLocal == 0xFFFF) { error = "diagonal contribution on a row without diagonal entry"; return -1; }
+            }
+        }
+        // off-diagonal codes, batch by batch
+        const int nbBatches = (h.nbEntries + 31) / 32;
+        for (int b = 0; b < nbBatches; b++) {
+            const TileBatch &tb = plan.batches[h.batchBase + b];
+            for (int lane = 0; lane < 32; lane++) {
+                const int q = b * 32 + lane;
+                for (int s = 0; s < tb.steps; s++) {
+                    const int code = plan.pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
+                    const int el = code >> 4, a = (code >> 2) & 3, bb = code & 3;
+                    if (el == h.nbElems) { if (a || bb) { error = "bad padding code"; return -1; } continue; }
+                    if (el > h.nbElems || q >= h.nbEntries) { error = "pair code out of range"; return -1; }
+                    const int r = plan.entryRow[h.entryBase + q];
+                    const TileRow &tr = plan.rows[h.rowBase + r];
+                    const int n = tr.node & 0x7fffffff;
+                    const uint16_t *ln = &plan.tileElems[((size_t)h.elemBase + el) * 4];
+                    const int na = plan.tileNodes[h.nodeBase + ln[a]], nb = plan.tileNodes[h.nodeBase + ln[bb]];
+                    const int l = tr.valueStart + (q - tr.localStart);
+                    if (na != n || col[l] != nb + 1) { error = "pair code lands on the wrong CSR entry"; return -1; }
+                }
+            }
+        }
+    }
+    if (rowsTotal != nbNodes) { error = "not every node is owned by a tile"; return -1; }
+
+    // every (element, j, k) exactly once: count per tile through the element identity
+    // (tile-local element -> global element by matching its node quadruple among the
+    // elements incident to its first node)
+    std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
+    node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
+    auto mark = [&] (int e, int j, int k) -> bool {
+        const uint16_t bit = (uint16_t)(1u << (4 * j + k));
+        if (tripleSeen[e] & bit) return false;
+        tripleSeen[e] |= bit;
+        return true;
+    };
+    for (int t = 0; t < plan.nbTiles; t++) {
+        const TileHeader &h = plan.tiles[t];
+        std::vector<int> globalElem (h.nbElems, -1);
+        for (int el = 0; el < h.nbElems; el++) {
+            const uint16_t *ln = &plan.tileElems[((size_t)h.elemBase + el) * 4];
+            int g[4];
+            for (int k = 0; k < 4; k++) g[k] = plan.tileNodes[h.nodeBase + ln[k]] + 1;
+            for (int p = n2eIndex[g[0] - 1]; p < n2eIndex[g[0]]; p++) {
+                const int *cand = elemToNode + (size_t)n2eValue[p] * 4;
+                if (cand[0] == g[0] && cand[1] == g[1] && cand[2] == g[2] && cand[3] == g[3]) {
+                    // duplicates of one quadruple are interchangeable; take the first not yet used by this tile
+                    if (std::find (globalElem.begin (), globalElem.end (), n2eValue[p]) == globalElem.end ()) {
+                        globalElem[el] = n2eValue[p];
+                        break;
+                    }
+                }
+            }
+            if (globalElem[el] < 0) { error = "tile element matches no mesh element"; return -1; }
+        }
+        for (int r = 0; r < h.nbRows; r++) {
+            const TileRow &tr = plan.rows[h.rowBase + r];
+            const int dEnd = plan.rows[h.rowBase + r + 1].diagCodeBase;
+            for (int k = tr.diagCodeBase; k < dEnd; k++) {
+                const int code = plan.diagCodes[k];
+                if (!mark (globalElem[code >> 2], code & 3, code & 3)) { error = "diagonal contribution listed twice"; return -1; }
+            }
+        }
+        const int nbBatches = (h.nbEntries + 31) / 32;
+        for (int b = 0; b < nbBatches; b++) {
+            const TileBatch &tb = plan.batches[h.batchBase + b];
+            for (int s = 0; s < tb.steps; s++) {
+                for (int lane = 0; lane < 32; lane++) {
+                    const int code = plan.pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
+                    if ((code >> 4) == h.nbElems) continue;
+                    if (!mark (globalElem[code >> 4], (code >> 2) & 3, code & 3)) { error = "pair contribution listed twice"; return -1; }
+                }
+            }
+        }
+    }
+    for (int e = 0; e < nbElem; e++) {
+        if (tripleSeen[e] != 0xFFFF) { error = "element " + std::to_string (e) + " misses a contribution"; return -1; }
+    }
+    return 0;
+}
+
+}  // namespace mfb

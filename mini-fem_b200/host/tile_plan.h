@@ -81,6 +81,13 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                      const int *col, const double *coord, const uint8_t *isInterface,
                      const TilePlanLimits &limits, TilePlan &plan, std::string &error);
 
+// Replays the plan on the host and compares it with the reference's double loop over
+// (element, j, k) (src/assembly.cc:382-412): every triple must appear exactly once, on the
+// entry whose row is node_j and whose column is node_k; rows, tiles and batches must tile
+// the CSR exactly.  Returns 0 or -1 with `error` set.
+int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *elemToNode,
+                      const int *row, const int *col, std::string &error);
+
 }  // namespace mfb
 
 #endif

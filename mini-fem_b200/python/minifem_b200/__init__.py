@@ -72,7 +72,7 @@ lib.mfb_mesh_free.restype = None
 lib.mfb_ctx_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(C.c_void_p)]
 lib.mfb_ctx_destroy.argtypes = [C.c_void_p]
 lib.mfb_ctx_destroy.restype = None
-for _name in ("assembly", "prec_init", "halo_exchange", "prec_inversion", "iteration", "sync",
+for _name in ("assembly", "assembly_fused", "prec_init", "halo_exchange", "prec_inversion", "iteration", "sync",
               "zero_values"):
     getattr(lib, "mfb_ctx_" + _name).argtypes = [C.c_void_p]
 lib.mfb_ctx_assembly_interval.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -86,6 +86,11 @@ lib.mfb_ctx_device_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER
 lib.mfb_ctx_plan_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
 lib.mfb_comm_unique_id.argtypes = [C.c_void_p]
 lib.mfb_ctx_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+lib.mfb_ctx_halo_pack_host.argtypes = [C.c_void_p, C.c_void_p]
+lib.mfb_ctx_halo_add_host.argtypes = [C.c_void_p, C.c_void_p]
+lib.mfb_ctx_prec_inversion_interface.argtypes = [C.c_void_p]
+lib.mfb_ctx_run_timed.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+lib.mfb_tile_plan_selfcheck.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, C.POINTER(C.c_int64)]
 lib.mfb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
 lib.mfb_host_free.argtypes = [C.c_void_p]
 lib.mfb_host_free.restype = None
@@ -105,7 +110,9 @@ DECLARED_SYMBOLS = [
     "mfb_ctx_halo_exchange", "mfb_ctx_prec_inversion", "mfb_ctx_iteration", "mfb_ctx_sync",
     "mfb_ctx_download", "mfb_ctx_upload_coord", "mfb_ctx_iteration_host", "mfb_ctx_device_ptrs",
     "mfb_ctx_stream", "mfb_ctx_stage_ms", "mfb_ctx_launch_count", "mfb_ctx_device_bytes",
-    "mfb_ctx_plan_stats", "mfb_comm_unique_id", "mfb_ctx_comm_init", "mfb_host_alloc",
+    "mfb_ctx_plan_stats", "mfb_comm_unique_id", "mfb_ctx_comm_init", "mfb_ctx_halo_pack_host",
+    "mfb_ctx_halo_add_host", "mfb_ctx_assembly_fused", "mfb_ctx_prec_inversion_interface", "mfb_ctx_run_timed",
+    "mfb_tile_plan_selfcheck", "mfb_host_alloc",
     "mfb_host_free", "mfb_device_count",
 ]
 
@@ -305,6 +312,7 @@ class Context:
             pass
 
     def assembly(self): _check(lib.mfb_ctx_assembly(self.handle), "mfb_ctx_assembly")
+    def assembly_fused(self): _check(lib.mfb_ctx_assembly_fused(self.handle), "mfb_ctx_assembly_fused")
     def zero_values(self): _check(lib.mfb_ctx_zero_values(self.handle), "mfb_ctx_zero_values")
     def assembly_interval(self, first, last): _check(lib.mfb_ctx_assembly_interval(self.handle, first, last), "mfb_ctx_assembly_interval")
     def prec_init(self): _check(lib.mfb_ctx_prec_init(self.handle), "mfb_ctx_prec_init")
@@ -325,6 +333,25 @@ class Context:
 
     def iteration_host(self, coord_ptr, values_ptr, prec_ptr):
         _check(lib.mfb_ctx_iteration_host(self.handle, coord_ptr, values_ptr, prec_ptr), "mfb_ctx_iteration_host")
+
+    def halo_pack_host(self):
+        buf = np.zeros(max(self.setup.mesh.nbIntfNodes * self.setup.operatorDim, 1), np.float64)
+        _check(lib.mfb_ctx_halo_pack_host(self.handle, _ptr(buf)), "mfb_ctx_halo_pack_host")
+        return buf[:self.setup.mesh.nbIntfNodes * self.setup.operatorDim]
+
+    def halo_add_host(self, recvbuf):
+        buf = np.ascontiguousarray(recvbuf, dtype=np.float64)
+        if buf.size == 0:
+            buf = np.zeros(1)
+        _check(lib.mfb_ctx_halo_add_host(self.handle, _ptr(buf)), "mfb_ctx_halo_add_host")
+
+    def prec_inversion_interface(self):
+        _check(lib.mfb_ctx_prec_inversion_interface(self.handle), "mfb_ctx_prec_inversion_interface")
+
+    def run_timed(self, steps):
+        ms = C.c_float(0)
+        _check(lib.mfb_ctx_run_timed(self.handle, steps, C.byref(ms)), "mfb_ctx_run_timed")
+        return ms.value
 
     def stage_ms(self):
         ms = (C.c_float * 5)()

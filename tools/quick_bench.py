@@ -1,0 +1,52 @@
+"""Scratch timing of the three assembly paths on one GPU (development aid, not bench.py)."""
+import argparse, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "mini-fem_b200", "python"))
+import numpy as np
+import minifem_b200 as mfb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--grid", type=int, nargs=3, default=[100, 100, 100])
+ap.add_argument("--op", default="ela")
+ap.add_argument("--paths", default="tiled,atomic,color")
+ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--tile-rows", type=int, default=0)
+ap.add_argument("--tile-elems", type=int, default=0)
+ap.add_argument("--threads", type=int, default=0)
+a = ap.parse_args()
+
+t0 = time.time()
+mesh = mfb.Mesh.generate(*a.grid, seed=1)
+print(f"mesh {a.grid}: E={mesh.nbElem} N={mesh.nbNodes} Z={mesh.nbEdges}  ({time.time()-t0:.1f}s)", flush=True)
+E, N, Z = mesh.nbElem, mesh.nbNodes, mesh.nbEdges
+alg = (16 * E + 76 * Z + 112 * N) if a.op == "ela" else (16 * E + 12 * Z + 36 * N)
+ref = None
+for path in a.paths.split(","):
+    t0 = time.time()
+    setup = mfb.Setup(mesh, a.op, coloring=(path == "color"))
+    t1 = time.time()
+    ctx = mfb.Context(setup, path=path, tile_rows=a.tile_rows, tile_elems=a.tile_elems, threads=a.threads,
+                      use_graph=(path == "color"))
+    t2 = time.time()
+    for _ in range(3):
+        ctx.iteration()
+    ctx.sync()
+    ms = []
+    for _ in range(a.steps):
+        ctx.iteration()
+        ms.append(ctx.stage_ms()[4])
+    ms = np.array(ms)
+    line = f"{path:7s} setup {t1-t0:.1f}s ctx {t2-t1:.1f}s  iter ms: med {np.median(ms):.4f} min {ms.min():.4f}  -> {E/np.median(ms)/1e6:.2f} Gelem/s, alg {alg/np.median(ms)/1e6:.1f} GB/s"
+    if path == "tiled":
+        line += f"  plan {ctx.plan_stats()} bytes {ctx.device_bytes()}"
+    print(line, flush=True)
+    v, p = ctx.download()
+    if path != "color":
+        if ref is None:
+            ref = (v, p)
+        else:
+            dim = setup.operatorDim
+            sv = np.abs(ref[0].reshape(-1, dim)).max(axis=1, keepdims=True)
+            print("   vs first path: values", (np.abs(v - ref[0]).reshape(-1, dim) / sv).max(),
+                  "prec", np.nanmax(np.abs(p - ref[1]) / np.maximum(np.abs(ref[1]), 1e-300)))
+    ctx.close()
