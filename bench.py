@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the Mini-FEM assembly hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repository's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path
+
+A "step" is one iteration of FEM_loop (src/FEM.cc:177-257): assembly + preconditioner
+initialisation + halo sum + preconditioner inversion over one subdomain per GPU.  The
+workload at N = 1 is the EIB-like elasticity case BASELINE.json quotes its metric on
+(100^3 cubes x 6 tetrahedra: 1,030,301 nodes, 6,000,000 elements, 15,210,901 CSR blocks of
+3x3); for N > 1 every GPU gets one such block of an N-times larger mesh (weak scaling) and
+only interface preconditioner values cross NVLink (NCCL), as in the reference's domain
+decomposition.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mini-fem_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+METRIC = "EIB ela assembly+precond elements/s"
+UNIT = "elements/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, nargs=3, default=[100, 100, 100], help="cubes per GPU block")
+    ap.add_argument("--op", default="ela", choices=["ela", "lap"])
+    ap.add_argument("--path", default="tiled", choices=["tiled", "atomic", "color"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--tile-rows", type=int, default=0)
+    ap.add_argument("--tile-elems", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-paths", action="store_true")
+    ap.add_argument("--cpu-ranks", type=int, default=0, help="ranks of the CPU reference (0 = host cores)")
+    return ap.parse_args()
+
+
+def algorithmic_bytes(op, E, Z, N):
+    """every input read once, every output written once."""
+    return 16 * E + 76 * Z + 112 * N if op == "ela" else 16 * E + 12 * Z + 36 * N
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def global_layout(args, world):
+    """Grid of cubes of the whole job and its block partition."""
+    import minifem_b200 as mfb
+    if args.scaling == "strong" or world == 1:
+        grid = tuple(args.grid)
+        return grid, mfb.choose_blocks(*grid, world)
+    px, py, pz = mfb.choose_blocks(world, world, world, world)     # most cubic factorisation of N
+    return (args.grid[0] * px, args.grid[1] * py, args.grid[2] * pz), (px, py, pz)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.samples, self.stop_flag, self.window = [], False, [0.0, 0.0]
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[device_index]) if visible and visible.replace(",", "").isdigit() else device_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                                   # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        nv = self.nv
+        inside = [s for s in self.samples if self.window[0] <= s[0] <= self.window[1]] or self.samples
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap,
+                 "hw_power_brake": nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown}
+        seen = sorted(n for n, bit in names.items() if any(s[2] & bit for s in inside))
+        mhz = sorted(s[1] for s in inside)
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": seen,
+                "samples_in_timed_region": len([s for s in self.samples if self.window[0] <= s[0] <= self.window[1]])}
+
+
+def load_traffic(key):
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+
+def run_reference_cpu(op, grid, nb_iter, ranks):
+    """The reference's own FEM_loop (oracle/_ref, REF build = pure MPI, one rank per
+    subdomain, ranks as threads) on the EIB-like mesh cut into `ranks` blocks.  Falls back
+    to the C oracle port when oracle/_ref was not built."""
+    import minifem_b200 as mfb
+    from oracle_lib import Oracle, Reference, ref_available
+    blocks = mfb.choose_blocks(*grid, ranks)
+    n = blocks[0] * blocks[1] * blocks[2]
+    meshes = [mfb.Mesh.generate(*grid, blocks=blocks, rank=r, seed=1) for r in range(n)]
+    setups = [mfb.Setup(m, op) for m in meshes]
+    elements = sum(m.nbElem for m in meshes)
+    if ref_available("ref"):
+        ref = Reference("ref")
+        _, _, cycles, hz = ref.fem_loop(setups, nb_iter)
+        seconds = sum(cycles) / hz                                   # FEM.cc:132: total of the 4 stage averages
+        kind, detail = "reference", "oracle/_ref libminifem_ref_ref.so (src/*.cc, -O2 -mavx, REF build, search path as shipped)"
+    else:
+        oracle = Oracle()
+        t0 = time.perf_counter()
+        for s in setups:
+            oracle.fem_iteration(s)
+        seconds = (time.perf_counter() - t0)
+        n, kind, detail = 1, "port", "oracle/minifem_oracle.c, one thread"
+    return elements / seconds, n, kind, detail, elements, blocks
+
+
+def reference_main(args, rank, world):
+    if rank != 0:
+        return
+    cores = args.cpu_ranks or (os.cpu_count() or 1)
+    grid = tuple(args.grid)
+    one_iter_guess = 6.0e6 * (np.prod(grid) / 1e6) / 4.0e6 / max(min(cores, 64), 1) * 3
+    nb_timed = max(1, min(args.steps, int(60.0 / max(one_iter_guess, 1e-3))))
+    t0 = time.perf_counter()
+    value, n, kind, detail, elements, blocks = run_reference_cpu(args.op, grid, nb_timed + 1, min(cores, 64))
+    wall = time.perf_counter() - t0
+    sample = (f"{grid[0]}x{grid[1]}x{grid[2]}-cube EIB-like mesh ({elements} elements) in {blocks[0]}x{blocks[1]}x{blocks[2]} "
+              f"subdomains, {nb_timed} timed iterations after 1 untimed (FEM.cc:182); {detail}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": nb_timed, "warmup": 1, "ms_per_step": 1e3 * elements / value, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"EIB-like {grid[0]}^3-cube Kuhn mesh, {args.op}, CPU reference on host cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------ our arm (GPU)
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_main(args, rank, world)
+        return
+    if args.gpus != world:
+        if args.gpus > 1:
+            sys.exit(f"bench.py --gpus {args.gpus}: launch with `python -m torch.distributed.run --nproc-per-node {args.gpus} "
+                     f"--master-addr 127.0.0.1 ... bench.py --gpus {args.gpus}` (one process per GPU)")
+    import torch
+    import minifem_b200 as mfb
+    from minifem_b200 import dist as mdist
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if mfb.device_count() < 1:
+        sys.exit("bench.py: no CUDA device; the assembly path has no CPU fallback")
+    torch.cuda.set_device(local)
+    mdist.init_from_env("nccl")
+
+    grid, blocks = global_layout(args, world)
+    t0 = time.perf_counter()
+    mesh = mfb.Mesh.generate(*grid, blocks=blocks, rank=rank, seed=1)
+    setup = mfb.Setup(mesh, args.op, coloring=(args.path == "color"))
+    ctx = mfb.Context(setup, path=args.path, device=local, nbBlocks=world, rank=rank, tile_rows=args.tile_rows,
+                      tile_elems=args.tile_elems, use_graph=(args.path == "color"))
+    if world > 1:
+        mdist.comm_init(ctx)
+    setup_s = time.perf_counter() - t0
+    E, N, Z = mesh.nbElem, mesh.nbNodes, setup.nbEdges
+    total_elements = mdist.sum_over_ranks(E)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler and sampler.ok:
+        sampler.start()
+
+    for _ in range(max(args.warmup, 3)):
+        ctx.iteration()
+    ctx.sync()
+    launches_before = ctx.launch_count()
+    mdist.barrier(); torch.cuda.synchronize()
+    t_begin = time.perf_counter()
+    ms_total = ctx.run_timed(args.steps)                 # CUDA events on the launching stream
+    ctx.sync()
+    torch.cuda.synchronize(); mdist.barrier()
+    t_end = time.perf_counter()
+    if sampler:
+        sampler.window = [t_begin, t_end]
+    launches = ctx.launch_count() - launches_before
+    ms_step = mdist.max_over_ranks(ms_total) / args.steps
+    value = total_elements / (ms_step * 1e-3)
+
+    # end to end through the host-buffer entry point: H2D coord, iteration, D2H values + prec
+    e2e = None
+    if args.e2e_steps > 0:
+        pins = [mfb.PinnedArray(N * 3), mfb.PinnedArray(ctx.nbValues), mfb.PinnedArray(ctx.nbPrec)]
+        pins[0].array[:] = mesh.coord
+        ctx.iteration_host(pins[0].ptr, pins[1].ptr, pins[2].ptr)          # warm
+        mdist.barrier(); torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            ctx.iteration_host(pins[0].ptr, pins[1].ptr, pins[2].ptr)
+        torch.cuda.synchronize(); mdist.barrier()
+        e2e_s = mdist.max_over_ranks((time.perf_counter() - t1) / args.e2e_steps)
+        checksum = float(pins[2].array[:9].sum())
+        e2e = {"value": total_elements / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(pins[0].bytes),
+               "d2h_bytes_per_step": int(pins[1].bytes + pins[2].bytes), "ms_per_step": 1e3 * e2e_s,
+               "steps": args.e2e_steps, "note": "per GPU: pinned coord -> device, fused iteration, values + prec -> pinned host",
+               "prec_checksum": checksum}
+        for p in pins:
+            p.free()
+    if sampler and sampler.ok:
+        sampler.stop_flag = True
+        sampler.join()
+
+    stats = ctx.plan_stats() if args.path == "tiled" else None
+    mesh_bytes, plan_bytes = ctx.device_bytes()
+    ctx.close()
+
+    other = {}
+    if world == 1 and not args.no_other_paths:
+        for path in ("tiled", "atomic", "color"):
+            if path == args.path:
+                continue
+            s2 = mfb.Setup(mesh, args.op, coloring=(path == "color"))
+            c2 = mfb.Context(s2, path=path, device=local, use_graph=(path == "color"))
+            for _ in range(3):
+                c2.iteration()
+            c2.sync()
+            other[path] = {"ms_per_step": c2.run_timed(10) / 10}
+            other[path]["value"] = E / (other[path]["ms_per_step"] * 1e-3)
+            if path == "color":
+                other[path]["colors"] = s2.nbTotalColors
+            c2.close()
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    alg = algorithmic_bytes(args.op, E, Z, N)
+    achieved = alg / (ms_step * 1e-3) / 1e9
+    workload = (f"EIB-like Kuhn mesh, {args.grid[0]}x{args.grid[1]}x{args.grid[2]} cubes x 6 tets per GPU "
+                f"({E} elements, {N} nodes, {Z} CSR entries per GPU), operator {args.op}, path {args.path}")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "global_grid": list(grid), "blocks": list(blocks),
+                       "parallelism": f"dd{world} (one subdomain per GPU, NCCL interface sum)" if world > 1 else "single subdomain",
+                       "l2": "inputs + outputs per step (>= 1.5 GB for ela) exceed the 126 MB L2; no flush needed",
+                       "setup_s": round(setup_s, 2), "device_mesh_bytes": mesh_bytes, "device_plan_bytes": plan_bytes,
+                       "plan": stats},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": load_traffic(f"{args.op}_{args.path}_{args.grid[0]}"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg,
+                         "note": "one fused kernel launch per step at N=1; duration = CUDA events over the timed region / steps"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
+            "other_paths": other}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = args.cpu_ranks or (os.cpu_count() or 1)
+        try:
+            cv, n, kind, detail, elements, cb = run_reference_cpu(args.op, tuple(args.grid), 3, min(cores, 64))
+            line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": n, "kind": kind,
+                                    "sample": f"whole {elements}-element mesh in {cb[0]}x{cb[1]}x{cb[2]} subdomains (one rank thread each), "
+                                              f"2 timed iterations after 1 untimed; {detail}"}
+        except Exception as e:                                   # the bench line must still appear
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

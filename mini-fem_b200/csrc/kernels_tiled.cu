@@ -224,10 +224,14 @@ size_t tiled_smem_bytes (int operatorID, const DeviceTilePlan &plan, int threads
 
 cudaError_t tiled_configure (int operatorID, size_t smemBytes)
 {
+    // The attribute belongs to the kernel, not to a context: several contexts (one per
+    // subdomain) with different tile caps share it, so always opt in to the device maximum.
+    (void)smemBytes;
+    const int optIn = 227 * 1024;
     if (operatorID == 0) {
-        return cudaFuncSetAttribute (tiled_assembly_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+        return cudaFuncSetAttribute (tiled_assembly_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optIn);
     }
-    return cudaFuncSetAttribute (tiled_assembly_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+    return cudaFuncSetAttribute (tiled_assembly_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, optIn);
 }
 
 cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstTile, int nbTiles,

@@ -193,14 +193,14 @@ def test_eib_size_properties(op):
         va, vb = v.reshape(-1, 3, 3)[a], v.reshape(-1, 3, 3)[b].transpose(0, 1, 3, 2)
         assert np.abs(va - vb).max() <= 1e-13 * np.abs(va).max()
     # preconditioner = inverse of the diagonal block on free nodes
-    free = mesh.boundNodesCode == 0
-    diag_idx = np.array([r + list(setup.col[r:r + 4]).index(i + 1) for i, r in enumerate(row[:-1][:2000])])
+    pick = np.flatnonzero(mesh.boundNodesCode == 0)[::509][:2000]
+    diag_idx = np.array([row[i] + list(setup.col[row[i]:row[i + 1]]).index(i + 1) for i in pick])
     d = v.reshape(-1, dim)[diag_idx]
     if dim == 1:
-        assert np.abs(d[:, 0] * p[:2000] - 1)[free[:2000]].max() < 1e-13
+        assert np.abs(d[:, 0] * p[pick] - 1).max() < 1e-13
     else:
-        prod = np.einsum("nij,njk->nik", p.reshape(-1, 3, 3)[:2000], d.reshape(-1, 3, 3))
-        assert np.abs(prod - np.eye(3))[free[:2000]].max() < 1e-12
+        prod = np.einsum("nij,njk->nik", p.reshape(-1, 3, 3)[pick], d.reshape(-1, 3, 3))
+        assert np.abs(prod - np.eye(3)).max() < 1e-12
     atomic = mfb.Context(setup, path="atomic")
     atomic.iteration()
     va, pa = atomic.download()
