@@ -135,6 +135,10 @@ typedef struct {
     int tileElems;                  /* TILED: max elements per tile (0 = default) */
     int threads;                    /* TILED: threads per CTA (0 = default) */
     int useGraph;                   /* capture mfb_ctx_iteration in a CUDA graph */
+    int ctas;                       /* TILED: CTAs walking the tiles (0 = default, -1 = one per tile) */
+    int bankAware;                  /* TILED: order inside each contribution list: 0 / 1 = chosen against
+                                       shared-memory bank conflicts (default), -1 = increasing element id
+                                       (the REF build's summation order) */
 } mfb_options;
 
 int mfb_ctx_create (const mfb_problem *problem, const mfb_options *options, mfb_ctx **out);
@@ -184,8 +188,9 @@ int64_t mfb_ctx_launch_count (mfb_ctx *ctx);
 /* Bytes of the device-resident plan and mesh (reporting). */
 int mfb_ctx_device_bytes (mfb_ctx *ctx, int64_t *meshBytes, int64_t *planBytes);
 /* Tile statistics of the TILED plan: [0] tiles [1] tile elements (with duplicates)
- * [2] contributions [3] max rows [4] max elems [5] shared memory bytes per CTA. */
-int mfb_ctx_plan_stats (mfb_ctx *ctx, int64_t stats[6]);
+ * [2] contributions [3] max rows [4] max elems [5] shared memory bytes per CTA
+ * [6] padded lane-steps of the off-diagonal pass [7] largest tile record in bytes. */
+int mfb_ctx_plan_stats (mfb_ctx *ctx, int64_t stats[8]);
 
 /* Multi-GPU: one context per process / GPU, NCCL over NVLink for the interface sum. */
 #define MFB_COMM_ID_BYTES 128

@@ -273,6 +273,7 @@ struct mfb_ctx {
     DeviceTilePlan plan;
     TilePlan hostPlanStats;       // counters only (vectors released after upload)
     size_t tiledSmem = 0;
+    int tiledCtas = 1;
     int64_t meshBytes = 0, planBytes = 0, launches = 0, graphLaunches = 0;
 
     NcclComm comm = nullptr;
@@ -302,37 +303,31 @@ int build_device_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options *o)
     if (o && o->tileElems > 0) lim.maxElems = o->tileElems;
     lim.maxNodesRef = std::min (65535, std::max (lim.maxElems, 64));   // 24 B of staging per referenced node
     lim.maxEntries = 65535;
+    lim.bankAware = !(o && o->bankAware < 0);
     TilePlan hp;
     std::string err;
     if (build_tile_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn,
                          p->coord, isIntf.empty () ? nullptr : isIntf.data (), lim, hp, err) != 0) {
         return fail (MFB_ERR_ARG, "tile plan: " + err);
     }
-    // make sure zero-sized vectors still upload one element (avoids null pointers in the kernel)
-    if (hp.tiles.empty ()) hp.tiles.resize (1);
-    if (hp.tileNodes.empty ()) hp.tileNodes.resize (1);
-    if (hp.tileElems.empty ()) hp.tileElems.resize (4);
-    if (hp.entryRow.empty ()) hp.entryRow.resize (1);
-    if (hp.batches.empty ()) hp.batches.resize (1);
-    if (hp.pairCodes.empty ()) hp.pairCodes.resize (1);
-    if (hp.diagCodes.empty ()) hp.diagCodes.resize (1);
-    MFB_CUDA (put_plan (c, &c->plan.tiles, hp.tiles));
-    MFB_CUDA (put_plan (c, &c->plan.tileNodes, hp.tileNodes));
-    MFB_CUDA (put_plan (c, &c->plan.tileElems, hp.tileElems));
-    MFB_CUDA (put_plan (c, &c->plan.rows, hp.rows));
-    MFB_CUDA (put_plan (c, &c->plan.entryRow, hp.entryRow));
-    MFB_CUDA (put_plan (c, &c->plan.batches, hp.batches));
-    MFB_CUDA (put_plan (c, &c->plan.pairCodes, hp.pairCodes));
-    MFB_CUDA (put_plan (c, &c->plan.diagCodes, hp.diagCodes));
+    if (hp.blob.empty ()) hp.blob.resize (16);
+    MFB_CUDA (put_plan (c, &c->plan.blob, hp.blob));
+    MFB_CUDA (put_plan (c, &c->plan.tileOffset, hp.tileOffset));
     c->plan.nbTiles = hp.nbTiles; c->plan.nbInterfaceTiles = hp.nbInterfaceTiles;
-    c->plan.maxRows = std::max (hp.maxRows, 1); c->plan.maxElems = std::max (hp.maxElems, 1);
-    c->plan.maxNodesRef = std::max (hp.maxNodesRef, 4);
+    c->plan.maxRows = std::max (hp.maxRows, 1); c->plan.elemStride = hp.elemStride;
+    c->plan.maxNodesRef = std::max (hp.maxNodesRef, 4); c->plan.maxBlobBytes = std::max (hp.maxBlobBytes, 16u);
     c->hostPlanStats.nbTiles = hp.nbTiles; c->hostPlanStats.nbTileElems = hp.nbTileElems;
     c->hostPlanStats.nbContributions = hp.nbContributions; c->hostPlanStats.maxRows = hp.maxRows;
-    c->hostPlanStats.maxElems = hp.maxElems;
+    c->hostPlanStats.maxElems = hp.maxElems; c->hostPlanStats.nbPaddedSteps = hp.nbPaddedSteps;
+    c->hostPlanStats.maxBlobBytes = hp.maxBlobBytes;
     c->tiledSmem = tiled_smem_bytes (c->operatorID, c->plan, c->threads);
     if (c->tiledSmem > 227 * 1024) return fail (MFB_ERR_ARG, "tile plan needs more than 227 KB of shared memory per CTA; lower tileElems");
     MFB_CUDA (tiled_configure (c->operatorID, c->tiledSmem));
+    // persistent grid: as many CTAs as fit on the device at once, each walking tiles with that stride
+    cudaDeviceProp prop;
+    MFB_CUDA (cudaGetDeviceProperties (&prop, c->device));
+    const int perSM = std::max (1, std::min ((int)(prop.sharedMemPerMultiprocessor / (c->tiledSmem + 1024)), 2048 / c->threads));
+    c->tiledCtas = (o && o->ctas > 0) ? o->ctas : (o && o->ctas == -1) ? (1 << 30) : prop.multiProcessorCount * perSM;
     return MFB_OK;
 }
 
@@ -361,7 +356,7 @@ int do_scatter_interval (mfb_ctx *c, int first, int count)
 int do_assembly (mfb_ctx *c, int fusePrec)
 {
     if (c->path == MFB_PATH_TILED) {
-        MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, c->plan.nbTiles, c->threads, c->tiledSmem,
+        MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, c->plan.nbTiles, c->tiledCtas, c->threads, c->tiledSmem,
                                 c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, c->stream));
         if (c->plan.nbTiles > 0) c->launches++;
         return MFB_OK;
@@ -431,11 +426,11 @@ int do_iteration (mfb_ctx *c)
     if (!c->comm) return fail (MFB_ERR_STATE, "mfb_ctx_iteration: call mfb_ctx_comm_init first (nbBlocks > 1)");
     // interface tiles first; their raw diagonal blocks travel while the interior assembles
     const int nIntfTiles = c->plan.nbInterfaceTiles;
-    MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, c->threads, c->tiledSmem, c->dCoord,
+    MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, c->tiledCtas, c->threads, c->tiledSmem, c->dCoord,
                             c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream));
     if (nIntfTiles > 0) c->launches++;
     MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));
-    MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, c->threads,
+    MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, c->tiledCtas, c->threads,
                             c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream));
     if (c->plan.nbTiles - nIntfTiles > 0) c->launches++;
     MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
@@ -767,12 +762,13 @@ extern "C" int mfb_ctx_device_bytes (mfb_ctx *c, int64_t *meshBytes, int64_t *pl
     return MFB_OK;
 }
 
-extern "C" int mfb_ctx_plan_stats (mfb_ctx *c, int64_t stats[6])
+extern "C" int mfb_ctx_plan_stats (mfb_ctx *c, int64_t stats[8])
 {
     if (!c || !stats) return fail (MFB_ERR_ARG, "NULL argument");
     stats[0] = c->hostPlanStats.nbTiles; stats[1] = c->hostPlanStats.nbTileElems;
     stats[2] = c->hostPlanStats.nbContributions; stats[3] = c->hostPlanStats.maxRows;
     stats[4] = c->hostPlanStats.maxElems; stats[5] = (int64_t)c->tiledSmem;
+    stats[6] = c->hostPlanStats.nbPaddedSteps * 32; stats[7] = c->hostPlanStats.maxBlobBytes;
     return MFB_OK;
 }
 

@@ -31,25 +31,21 @@ cudaError_t launch_halo_add (double *prec, const double *recvBuf, const int *uni
                              const int *slotIndex, const int *slots, int dim, int nbUniq,
                              cudaStream_t stream);
 
-// Device copy of a TilePlan.
+// Device copy of a TilePlan (host/tile_plan.h): one blob per tile.
 struct DeviceTilePlan {
-    const TileHeader *tiles = nullptr;
-    const int *tileNodes = nullptr;
-    const uint16_t *tileElems = nullptr;
-    const TileRow *rows = nullptr;
-    const uint8_t *entryRow = nullptr;
-    const TileBatch *batches = nullptr;
-    const uint16_t *pairCodes = nullptr;
-    const uint16_t *diagCodes = nullptr;
+    const uint8_t *blob = nullptr;
+    const uint64_t *tileOffset = nullptr;     // nbTiles + 1
     int nbTiles = 0, nbInterfaceTiles = 0;
-    int maxRows = 0, maxElems = 0, maxNodesRef = 0;
+    int maxRows = 0, elemStride = 0, maxNodesRef = 0;
+    unsigned maxBlobBytes = 0;
 };
 
 // fusePrec: 0 = values only; 1 = also write prec: the raw diagonal block for interface
 // nodes (they still need the halo sum), the masked + inverted block for all others.
 size_t tiled_smem_bytes (int operatorID, const DeviceTilePlan &plan, int threads);
 cudaError_t tiled_configure (int operatorID, size_t smemBytes);
-cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstTile, int nbTiles,
+// `ctas` CTAs walk the tiles [firstTile, firstTile + nbTiles) with stride `ctas`.
+cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstTile, int nbTiles, int ctas,
                           int threads, size_t smemBytes, const double *coord, double *values,
                           double *prec, const int *checkBounds, int nbNodes, int fusePrec,
                           cudaStream_t stream);

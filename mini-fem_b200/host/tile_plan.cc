@@ -24,27 +24,109 @@ inline uint64_t spread21 (uint64_t v)
     return v;
 }
 
+inline uint32_t align16 (uint32_t x) { return (x + 15u) & ~15u; }
+
 struct TileScratch {
     std::vector<int> elems;                   // global element ids, first-touch order
     std::vector<int> nodes;                   // global node ids, owned first
     std::vector<uint16_t> elemNodes;          // 4 local ids per element
-    std::vector<TileRow> rows;
+    std::vector<TileRow> rows;                // + sentinel
     std::vector<uint8_t> entryRow;
     std::vector<TileBatch> batches;
     std::vector<uint16_t> pairCodes, diagCodes;
-    int64_t contributions = 0;
-    bool bad = false;
+    int64_t contributions = 0, paddedSteps = 0;
+    bool bad = false, hasInterface = false;
+    uint32_t blobBytes = 0;
 };
 
-}  // namespace
+// Shared-memory bank pair (8-byte words, 16 per 128-byte line) of coefficient slot
+// (local node a, element e); the planes start on a 128-byte boundary.
+inline int bank_of (int a, int e, int stride) { return (a * stride + e) & 15; }
 
-int64_t TilePlan::bytes () const
+// Reorders the contribution lists of up to 16 lanes (one half-warp) so that, step by step,
+// the row-side slots (a,e) and the column-side slots (b,e) of the lanes fall into different
+// banks where possible.  Identical slots are a broadcast and cost nothing.  Greedy, lane by
+// lane and step by step (a pairwise-swap refinement was measured: 6 % fewer modelled
+// wavefronts for 10x the build time, not kept).
+struct HalfWarpSchedule {
+    int nbLanes = 0, steps = 0, stride = 0;
+    std::vector<uint16_t> code;                 // [step][lane], 0xFFFF = nothing
+
+    int slot_a (uint16_t c) const { return ((c >> 2) & 3) * stride + (c >> 4); }
+    int slot_b (uint16_t c) const { return (c & 3) * stride + (c >> 4); }
+
+};
+
+void order_half_warp (std::vector<uint16_t> *lists, int nbLanes, int stride)
 {
-    return (int64_t)tiles.size () * sizeof (TileHeader) + tileNodes.size () * sizeof (int) +
-           tileElems.size () * sizeof (uint16_t) + rows.size () * sizeof (TileRow) +
-           entryRow.size () + batches.size () * sizeof (TileBatch) +
-           pairCodes.size () * sizeof (uint16_t) + diagCodes.size () * sizeof (uint16_t);
+    HalfWarpSchedule S;
+    S.nbLanes = nbLanes; S.stride = stride;
+    for (int l = 0; l < nbLanes; l++) S.steps = std::max (S.steps, (int)lists[l].size ());
+    if (S.steps == 0) return;
+    S.code.assign ((size_t)S.steps * 16, 0xFFFF);
+    std::vector<std::vector<uint16_t>> rest (lists, lists + nbLanes);
+    for (int t = 0; t < S.steps; t++) {                       // greedy construction
+        int cntA[16] = {0}, cntB[16] = {0};
+        int usedA[16], usedB[16], nUsed = 0;
+        for (int l = 0; l < nbLanes; l++) {
+            std::vector<uint16_t> &r = rest[l];
+            if (r.empty ()) continue;
+            int best = 0, bestCost = 1 << 30;
+            for (size_t k = 0; k < r.size (); k++) {
+                const int slotA = S.slot_a (r[k]), slotB = S.slot_b (r[k]);
+                int costA = cntA[slotA & 15], costB = cntB[slotB & 15];
+                for (int u = 0; u < nUsed; u++) {
+                    if (usedA[u] == slotA) costA = 0;
+                    if (usedB[u] == slotB) costB = 0;
+                }
+                const int cost = std::max (costA, costB) * 64 + costA + costB;
+                if (cost < bestCost) { bestCost = cost; best = (int)k; }
+            }
+            const uint16_t code = r[best];
+            r.erase (r.begin () + best);
+            S.code[(size_t)t * 16 + l] = code;
+            const int slotA = S.slot_a (code), slotB = S.slot_b (code);
+            bool dupA = false, dupB = false;
+            for (int u = 0; u < nUsed; u++) { dupA |= usedA[u] == slotA; dupB |= usedB[u] == slotB; }
+            if (!dupA) cntA[slotA & 15]++;
+            if (!dupB) cntB[slotB & 15]++;
+            usedA[nUsed] = slotA; usedB[nUsed] = slotB; nUsed++;
+        }
+    }
+    for (int l = 0; l < nbLanes; l++) {
+        const size_t len = lists[l].size ();
+        for (size_t t = 0; t < len; t++) lists[l][t] = S.code[t * 16 + l];
+    }
 }
+
+// Same idea for the diagonal pass: 4 lanes share one row's list (lane `sub` takes codes
+// sub, sub+4, ...), 4 rows per half-warp.
+void order_diag_half_warp (std::vector<uint16_t> *rowLists, int nbRows, int stride)
+{
+    size_t steps = 0;
+    for (int r = 0; r < nbRows; r++) steps = std::max (steps, (rowLists[r].size () + 3) / 4);
+    std::vector<std::vector<uint16_t>> out ((size_t)nbRows);
+    std::vector<std::vector<uint16_t>> rest (rowLists, rowLists + nbRows);
+    for (size_t t = 0; t < steps; t++) {
+        int cnt[16] = {0};
+        for (int r = 0; r < nbRows; r++) {
+            for (int sub = 0; sub < 4 && !rest[r].empty (); sub++) {
+                int best = 0, bestCost = 1 << 30;
+                for (size_t k = 0; k < rest[r].size (); k++) {
+                    const int cost = cnt[bank_of (rest[r][k] & 3, rest[r][k] >> 2, stride)];
+                    if (cost < bestCost) { bestCost = cost; best = (int)k; }
+                }
+                const uint16_t code = rest[r][best];
+                rest[r].erase (rest[r].begin () + best);
+                out[r].push_back (code);
+                cnt[bank_of (code & 3, code >> 2, stride)]++;
+            }
+        }
+    }
+    for (int r = 0; r < nbRows; r++) rowLists[r].swap (out[r]);
+}
+
+}  // namespace
 
 int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *row,
                      const int *col, const double *coord, const uint8_t *isInterface,
@@ -56,6 +138,10 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         error = "tile plan limits out of range";
         return -1;
     }
+    // odd stride: the 4 local-node planes of one element land in 4 different banks
+    const int stride = (lim.maxElems + 1) | 1;
+    plan.elemStride = stride;
+
     std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
     node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
 
@@ -138,7 +224,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
     #pragma omp parallel num_threads(team)
     {
         std::vector<int> nodeLocal ((size_t)nbNodes, -1), elemLocal ((size_t)nbElem, -1);
-        std::vector<std::vector<uint16_t>> lists;
+        std::vector<std::vector<uint16_t>> lists, diagLists;
         #pragma omp for schedule(dynamic, 16)
         for (int t = 0; t < nbTiles; t++) {
             TileScratch &s = scratch[t];
@@ -164,17 +250,21 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
             }
             int nbEntries = 0;
             for (int r = 0; r < nbRows; r++) nbEntries += row[s.nodes[r] + 1] - row[s.nodes[r]];
-            if ((int)lists.size () < nbEntries) lists.resize (nbEntries);
-            for (int q = 0; q < nbEntries; q++) lists[q].clear ();
+            if ((int)lists.size () < nbEntries + 32) lists.resize (nbEntries + 32);
+            for (int q = 0; q < nbEntries + 32; q++) lists[q].clear ();
+            if ((int)diagLists.size () < nbRows + 8) diagLists.resize (nbRows + 8);
+            for (int r = 0; r < nbRows + 8; r++) diagLists[r].clear ();
             s.entryRow.resize (nbEntries);
 
             int localStart = 0;
             for (int r = 0; r < nbRows; r++) {
                 const int n = s.nodes[r], begin = row[n], end = row[n + 1];
                 TileRow tr;
-                tr.node = n | ((isInterface && isInterface[n]) ? (int)0x80000000u : 0);
+                const bool intf = isInterface && isInterface[n];
+                s.hasInterface |= intf;
+                tr.node = n | (intf ? (int)0x80000000u : 0);
                 tr.valueStart = begin;
-                tr.diagCodeBase = (int)s.diagCodes.size ();
+                tr.diagCodeBase = 0;
                 tr.localStart = (uint16_t)localStart;
                 tr.diagLocal = 0xFFFF;
                 for (int l = begin; l < end; l++) {
@@ -188,7 +278,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                     while (nodes[a] != n + 1) a++;
                     for (int b = 0; b < kDimElem; b++) {
                         if (b == a) {
-                            s.diagCodes.push_back ((uint16_t)((el << 2) | a));
+                            diagLists[r].push_back ((uint16_t)((el << 2) | a));
                             continue;
                         }
                         int l = begin;
@@ -200,159 +290,107 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                 s.rows.push_back (tr);
                 localStart += end - begin;
             }
+
+            // diagonal codes, 8 rows (= one warp pass) at a time
+            for (int r0 = 0; r0 < nbRows; r0 += 4) {
+                if (lim.bankAware) order_diag_half_warp (&diagLists[r0], std::min (4, nbRows - r0), stride);
+            }
+            for (int r = 0; r < nbRows; r++) {
+                s.rows[r].diagCodeBase = (int)s.diagCodes.size ();
+                s.diagCodes.insert (s.diagCodes.end (), diagLists[r].begin (), diagLists[r].end ());
+            }
+            TileRow sentinel = {0, 0, (int)s.diagCodes.size (), 0, 0xFFFF};
+            s.rows.push_back (sentinel);
             s.contributions = (int64_t)s.diagCodes.size ();
+
+            // off-diagonal codes: transposed per 32 entries, ordered per half-warp
+            const uint16_t padCode = (uint16_t)(s.elems.size () << 4);
             const int nbBatches = (nbEntries + 31) / 32;
             for (int b = 0; b < nbBatches; b++) {
-                int steps = 0;
-                for (int lane = 0; lane < 32 && b * 32 + lane < nbEntries; lane++) {
-                    steps = std::max (steps, (int)lists[b * 32 + lane].size ());
+                const int lanes = std::min (32, nbEntries - b * 32);
+                if (lim.bankAware) {
+                    order_half_warp (&lists[b * 32], std::min (16, lanes), stride);
+                    if (lanes > 16) order_half_warp (&lists[b * 32 + 16], lanes - 16, stride);
                 }
+                int steps = 0;
+                for (int lane = 0; lane < lanes; lane++) steps = std::max (steps, (int)lists[b * 32 + lane].size ());
                 TileBatch tb = { (int)s.pairCodes.size (), steps };
                 s.batches.push_back (tb);
-                s.pairCodes.resize (s.pairCodes.size () + (size_t)steps * 32, (uint16_t)(s.elems.size () << 4));
-                for (int lane = 0; lane < 32 && b * 32 + lane < nbEntries; lane++) {
+                s.pairCodes.resize (s.pairCodes.size () + (size_t)steps * 32, padCode);
+                for (int lane = 0; lane < lanes; lane++) {
                     const std::vector<uint16_t> &l = lists[b * 32 + lane];
                     for (size_t k = 0; k < l.size (); k++) s.pairCodes[tb.codeBase + k * 32 + lane] = l[k];
                     s.contributions += (int64_t)l.size ();
                 }
+                s.paddedSteps += steps;
             }
+            uint32_t bytes = (uint32_t)sizeof (TileBlobHeader) + (uint32_t)(s.rows.size () * sizeof (TileRow));
+            bytes = align16 (bytes) + align16 ((uint32_t)(s.nodes.size () * 4));
+            bytes += align16 ((uint32_t)(s.elems.size () * 8)) + align16 ((uint32_t)s.entryRow.size ());
+            bytes += align16 ((uint32_t)(s.batches.size () * sizeof (TileBatch)));
+            bytes += align16 ((uint32_t)(s.diagCodes.size () * 2)) + align16 ((uint32_t)(s.pairCodes.size () * 2));
+            s.blobBytes = bytes;
             for (int n : s.nodes) nodeLocal[n] = -1;
             for (int e : s.elems) elemLocal[e] = -1;
         }
     }
 
-    // ---- 4. concatenate ---------------------------------------------------------
+    // ---- 4. serialise: interface tiles first ----------------------------------------
+    std::vector<int> execOrder;
+    for (int t = 0; t < nbTiles; t++) if (scratch[t].hasInterface) execOrder.push_back (t);
+    plan.nbInterfaceTiles = (int)execOrder.size ();
+    for (int t = 0; t < nbTiles; t++) if (!scratch[t].hasInterface) execOrder.push_back (t);
     plan.nbTiles = nbTiles;
-    plan.tiles.resize ((size_t)nbTiles);
-    size_t nNodes = 0, nElems = 0, nRows = 0, nEntries = 0, nBatches = 0, nPair = 0, nDiag = 0;
-    for (int t = 0; t < nbTiles; t++) {
-        const TileScratch &s = scratch[t];
-        if (s.bad) { error = "CSR lacks a node pair of an element (tile " + std::to_string (t) + ")"; return -1; }
-        TileHeader &h = plan.tiles[t];
-        h.nodeBase = (int)nNodes; h.elemBase = (int)nElems; h.rowBase = (int)nRows;
-        h.entryBase = (int)nEntries; h.batchBase = (int)nBatches;
-        h.nbRows = (uint16_t)s.rows.size (); h.nbNodesRef = (uint16_t)s.nodes.size ();
-        h.nbElems = (uint16_t)s.elems.size (); h.nbEntries = (uint16_t)s.entryRow.size ();
-        h.pad = 0;
-        nNodes += s.nodes.size (); nElems += s.elems.size (); nRows += s.rows.size ();
-        nEntries += s.entryRow.size (); nBatches += s.batches.size ();
-        nPair += s.pairCodes.size (); nDiag += s.diagCodes.size ();
-        plan.maxRows = std::max (plan.maxRows, (int)h.nbRows);
-        plan.maxElems = std::max (plan.maxElems, (int)h.nbElems);
-        plan.maxNodesRef = std::max (plan.maxNodesRef, (int)h.nbNodesRef);
-        plan.maxEntries = std::max (plan.maxEntries, (int)h.nbEntries);
+    plan.tileOffset.assign ((size_t)nbTiles + 1, 0);
+    for (int k = 0; k < nbTiles; k++) {
+        const TileScratch &s = scratch[execOrder[k]];
+        if (s.bad) { error = "CSR lacks a node pair of an element (tile " + std::to_string (execOrder[k]) + ")"; return -1; }
+        plan.tileOffset[k + 1] = plan.tileOffset[k] + s.blobBytes;
+        plan.maxBlobBytes = std::max (plan.maxBlobBytes, s.blobBytes);
+        plan.maxRows = std::max (plan.maxRows, (int)s.rows.size () - 1);
+        plan.maxElems = std::max (plan.maxElems, (int)s.elems.size ());
+        plan.maxNodesRef = std::max (plan.maxNodesRef, (int)s.nodes.size ());
+        plan.maxEntries = std::max (plan.maxEntries, (int)s.entryRow.size ());
+        plan.nbTileElems += (int64_t)s.elems.size ();
         plan.nbContributions += s.contributions;
+        plan.nbPaddedSteps += s.paddedSteps;
     }
-    if (nPair > (size_t)INT32_MAX || nDiag > (size_t)INT32_MAX || nElems > (size_t)INT32_MAX) {
-        error = "tile plan exceeds 32-bit offsets";
-        return -1;
-    }
-    plan.nbTileElems = (int64_t)nElems;
-    plan.tileNodes.resize (nNodes); plan.tileElems.resize (nElems * 4); plan.rows.resize (nRows + 1);
-    plan.entryRow.resize (nEntries); plan.batches.resize (nBatches);
-    plan.pairCodes.resize (nPair); plan.diagCodes.resize (nDiag);
-    std::vector<size_t> pairBase ((size_t)nbTiles + 1, 0), diagBase ((size_t)nbTiles + 1, 0);
-    for (int t = 0; t < nbTiles; t++) {
-        pairBase[t + 1] = pairBase[t] + scratch[t].pairCodes.size ();
-        diagBase[t + 1] = diagBase[t] + scratch[t].diagCodes.size ();
-    }
+    plan.blob.assign ((size_t)plan.tileOffset[nbTiles], 0);
     #pragma omp parallel for schedule(dynamic, 64)
-    for (int t = 0; t < nbTiles; t++) {
-        const TileScratch &s = scratch[t];
-        const TileHeader &h = plan.tiles[t];
-        std::copy (s.nodes.begin (), s.nodes.end (), plan.tileNodes.begin () + h.nodeBase);
-        std::copy (s.elemNodes.begin (), s.elemNodes.end (), plan.tileElems.begin () + (size_t)h.elemBase * 4);
-        std::copy (s.entryRow.begin (), s.entryRow.end (), plan.entryRow.begin () + h.entryBase);
-        std::copy (s.pairCodes.begin (), s.pairCodes.end (), plan.pairCodes.begin () + pairBase[t]);
-        std::copy (s.diagCodes.begin (), s.diagCodes.end (), plan.diagCodes.begin () + diagBase[t]);
-        for (size_t r = 0; r < s.rows.size (); r++) {
-            TileRow tr = s.rows[r];
-            tr.diagCodeBase += (int)diagBase[t];
-            plan.rows[h.rowBase + r] = tr;
-        }
-        for (size_t b = 0; b < s.batches.size (); b++) {
-            TileBatch tb = s.batches[b];
-            tb.codeBase += (int)pairBase[t];
-            plan.batches[h.batchBase + b] = tb;
-        }
-    }
-    TileRow sentinel = {0, 0, (int)nDiag, 0, 0xFFFF};
-    plan.rows[nRows] = sentinel;
-
-    // tiles that own interface nodes first: their diagonal blocks feed the halo exchange
-    if (isInterface) {
-        auto owns = [&] (const TileHeader &h) {
-            for (int r = 0; r < h.nbRows; r++) if (plan.rows[h.rowBase + r].node < 0) return true;
-            return false;
-        };
-        auto mid = std::stable_partition (plan.tiles.begin (), plan.tiles.end (), owns);
-        plan.nbInterfaceTiles = (int)(mid - plan.tiles.begin ());
+    for (int k = 0; k < nbTiles; k++) {
+        const TileScratch &s = scratch[execOrder[k]];
+        uint8_t *base = plan.blob.data () + plan.tileOffset[k];
+        TileBlobHeader h;
+        memset (&h, 0, sizeof h);
+        h.nbRows = (uint16_t)(s.rows.size () - 1); h.nbNodesRef = (uint16_t)s.nodes.size ();
+        h.nbElems = (uint16_t)s.elems.size (); h.nbEntries = (uint16_t)s.entryRow.size ();
+        h.nbBatches = (uint16_t)s.batches.size (); h.hasInterface = s.hasInterface ? 1 : 0;
+        uint32_t at = (uint32_t)sizeof (TileBlobHeader);
+        memcpy (base + at, s.rows.data (), s.rows.size () * sizeof (TileRow));
+        at = align16 (at + (uint32_t)(s.rows.size () * sizeof (TileRow)));
+        h.offNodes = at; memcpy (base + at, s.nodes.data (), s.nodes.size () * 4);
+        at += align16 ((uint32_t)(s.nodes.size () * 4));
+        h.offElems = at; memcpy (base + at, s.elemNodes.data (), s.elemNodes.size () * 2);
+        at += align16 ((uint32_t)(s.elems.size () * 8));
+        h.offEntryRow = at; memcpy (base + at, s.entryRow.data (), s.entryRow.size ());
+        at += align16 ((uint32_t)s.entryRow.size ());
+        h.offBatches = at; memcpy (base + at, s.batches.data (), s.batches.size () * sizeof (TileBatch));
+        at += align16 ((uint32_t)(s.batches.size () * sizeof (TileBatch)));
+        h.offDiag = at; memcpy (base + at, s.diagCodes.data (), s.diagCodes.size () * 2);
+        at += align16 ((uint32_t)(s.diagCodes.size () * 2));
+        h.offPair = at; memcpy (base + at, s.pairCodes.data (), s.pairCodes.size () * 2);
+        at += align16 ((uint32_t)(s.pairCodes.size () * 2));
+        h.blobBytes = at;
+        memcpy (base, &h, sizeof h);
     }
     return 0;
 }
-
-}  // namespace mfb
-
-namespace mfb {
 
 int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *elemToNode,
                       const int *row, const int *col, std::string &error)
 {
     std::vector<uint8_t> rowSeen ((size_t)nbNodes, 0);
     std::vector<uint16_t> tripleSeen ((size_t)nbElem, 0);      // bit 4j+k per element
-    int64_t rowsTotal = 0;
-    for (int t = 0; t < plan.nbTiles; t++) {
-        const TileHeader &h = plan.tiles[t];
-        // global element of each tile-local element, recovered from its 4 node ids
-        for (int r = 0; r < h.nbRows; r++) {
-            const TileRow &tr = plan.rows[h.rowBase + r];
-            const int n = tr.node & 0x7fffffff;
-            if (n < 0 || n >= nbNodes || rowSeen[n]) { error = "row owned twice or out of range"; return -1; }
-            rowSeen[n] = 1;
-            rowsTotal++;
-            if (plan.tileNodes[h.nodeBase + r] != n) { error = "owned rows must lead the tile's node list"; return -1; }
-            if (tr.valueStart != row[n]) { error = "row offset differs from nodeToNodeRow"; return -1; }
-            const int len = row[n + 1] - row[n];
-            for (int l = 0; l < len; l++) {
-                if (plan.entryRow[h.entryBase + tr.localStart + l] != r) { error = "entryRow mismatch"; return -1; }
-            }
-            // diagonal codes: one per incident element, local index a must be this node
-            const int dEnd = plan.rows[h.rowBase + r + 1].diagCodeBase;
-            for (int k = tr.diagCodeBase; k < dEnd; k++) {
-                const int code = plan.diagCodes[k], el = code >> 2, a = code & 3;
-                if (el >= h.nbElems) { error = "diagonal code names a foreign element"; return -1; }
-                const uint16_t *ln = &plan.tileElems[((size_t)h.elemBase + el) * 4];
-                if (plan.tileNodes[h.nodeBase + ln[a]] != n) { error = "diagonal code: wrong local node"; return -1; }
-                if (tr.diagLocal == 0xFFFF) { error = "diagonal contribution on a row without diagonal entry"; return -1; }
-            }
-        }
-        // off-diagonal codes, batch by batch
-        const int nbBatches = (h.nbEntries + 31) / 32;
-        for (int b = 0; b < nbBatches; b++) {
-            const TileBatch &tb = plan.batches[h.batchBase + b];
-            for (int lane = 0; lane < 32; lane++) {
-                const int q = b * 32 + lane;
-                for (int s = 0; s < tb.steps; s++) {
-                    const int code = plan.pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
-                    const int el = code >> 4, a = (code >> 2) & 3, bb = code & 3;
-                    if (el == h.nbElems) { if (a || bb) { error = "bad padding code"; return -1; } continue; }
-                    if (el > h.nbElems || q >= h.nbEntries) { error = "pair code out of range"; return -1; }
-                    const int r = plan.entryRow[h.entryBase + q];
-                    const TileRow &tr = plan.rows[h.rowBase + r];
-                    const int n = tr.node & 0x7fffffff;
-                    const uint16_t *ln = &plan.tileElems[((size_t)h.elemBase + el) * 4];
-                    const int na = plan.tileNodes[h.nodeBase + ln[a]], nb = plan.tileNodes[h.nodeBase + ln[bb]];
-                    const int l = tr.valueStart + (q - tr.localStart);
-                    if (na != n || col[l] != nb + 1) { error = "pair code lands on the wrong CSR entry"; return -1; }
-                }
-            }
-        }
-    }
-    if (rowsTotal != nbNodes) { error = "not every node is owned by a tile"; return -1; }
-
-    // every (element, j, k) exactly once: count per tile through the element identity
-    // (tile-local element -> global element by matching its node quadruple among the
-    // elements incident to its first node)
     std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
     node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
     auto mark = [&] (int e, int j, int k) -> bool {
@@ -361,45 +399,93 @@ int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *
         tripleSeen[e] |= bit;
         return true;
     };
+    int64_t rowsTotal = 0;
+    bool interiorSeen = false;
     for (int t = 0; t < plan.nbTiles; t++) {
-        const TileHeader &h = plan.tiles[t];
+        const uint8_t *base = plan.blob.data () + plan.tileOffset[t];
+        const TileBlobHeader &h = *plan.header (t);
+        if (h.blobBytes != plan.tileOffset[t + 1] - plan.tileOffset[t] || (plan.tileOffset[t] & 15)) {
+            error = "blob size / alignment"; return -1;
+        }
+        if (h.hasInterface && interiorSeen) { error = "interface tiles must come first"; return -1; }
+        if (!h.hasInterface) interiorSeen = true;
+        if ((t < plan.nbInterfaceTiles) != (h.hasInterface != 0)) { error = "nbInterfaceTiles mismatch"; return -1; }
+        const TileRow *rows = reinterpret_cast<const TileRow*> (base + sizeof (TileBlobHeader));
+        const int *tileNodes = reinterpret_cast<const int*> (base + h.offNodes);
+        const uint16_t *tileElems = reinterpret_cast<const uint16_t*> (base + h.offElems);
+        const uint8_t *entryRow = base + h.offEntryRow;
+        const TileBatch *batches = reinterpret_cast<const TileBatch*> (base + h.offBatches);
+        const uint16_t *diagCodes = reinterpret_cast<const uint16_t*> (base + h.offDiag);
+        const uint16_t *pairCodes = reinterpret_cast<const uint16_t*> (base + h.offPair);
+        if (h.nbElems > plan.maxElems || h.nbElems >= plan.elemStride || h.nbRows > plan.maxRows ||
+            h.nbNodesRef > plan.maxNodesRef || h.nbBatches != (h.nbEntries + 31) / 32) {
+            error = "tile exceeds the plan maxima"; return -1;
+        }
+        // tile-local element -> global element, by matching its node quadruple
         std::vector<int> globalElem (h.nbElems, -1);
         for (int el = 0; el < h.nbElems; el++) {
-            const uint16_t *ln = &plan.tileElems[((size_t)h.elemBase + el) * 4];
+            const uint16_t *ln = tileElems + (size_t)el * 4;
             int g[4];
-            for (int k = 0; k < 4; k++) g[k] = plan.tileNodes[h.nodeBase + ln[k]] + 1;
+            for (int k = 0; k < 4; k++) {
+                if (ln[k] >= h.nbNodesRef) { error = "local node index out of range"; return -1; }
+                g[k] = tileNodes[ln[k]] + 1;
+            }
             for (int p = n2eIndex[g[0] - 1]; p < n2eIndex[g[0]]; p++) {
                 const int *cand = elemToNode + (size_t)n2eValue[p] * 4;
-                if (cand[0] == g[0] && cand[1] == g[1] && cand[2] == g[2] && cand[3] == g[3]) {
-                    // duplicates of one quadruple are interchangeable; take the first not yet used by this tile
-                    if (std::find (globalElem.begin (), globalElem.end (), n2eValue[p]) == globalElem.end ()) {
-                        globalElem[el] = n2eValue[p];
-                        break;
-                    }
+                if (cand[0] == g[0] && cand[1] == g[1] && cand[2] == g[2] && cand[3] == g[3] &&
+                    std::find (globalElem.begin (), globalElem.end (), n2eValue[p]) == globalElem.end ()) {
+                    globalElem[el] = n2eValue[p];
+                    break;
                 }
             }
             if (globalElem[el] < 0) { error = "tile element matches no mesh element"; return -1; }
         }
+        int expectStart = 0;
         for (int r = 0; r < h.nbRows; r++) {
-            const TileRow &tr = plan.rows[h.rowBase + r];
-            const int dEnd = plan.rows[h.rowBase + r + 1].diagCodeBase;
-            for (int k = tr.diagCodeBase; k < dEnd; k++) {
-                const int code = plan.diagCodes[k];
-                if (!mark (globalElem[code >> 2], code & 3, code & 3)) { error = "diagonal contribution listed twice"; return -1; }
+            const TileRow &tr = rows[r];
+            const int n = tr.node & 0x7fffffff;
+            if (n < 0 || n >= nbNodes || rowSeen[n]) { error = "row owned twice or out of range"; return -1; }
+            rowSeen[n] = 1;
+            rowsTotal++;
+            if (tileNodes[r] != n) { error = "owned rows must lead the tile's node list"; return -1; }
+            if (tr.valueStart != row[n] || tr.localStart != expectStart) { error = "row offsets differ from nodeToNodeRow"; return -1; }
+            const int len = row[n + 1] - row[n];
+            expectStart += len;
+            for (int l = 0; l < len; l++) {
+                if (entryRow[tr.localStart + l] != r) { error = "entryRow mismatch"; return -1; }
+            }
+            if (tr.diagLocal != 0xFFFF && col[tr.valueStart + (tr.diagLocal - tr.localStart)] != n + 1) {
+                error = "diagLocal is not the diagonal entry"; return -1;
+            }
+            for (int k = tr.diagCodeBase; k < rows[r + 1].diagCodeBase; k++) {
+                const int code = diagCodes[k], el = code >> 2, a = code & 3;
+                if (el >= h.nbElems) { error = "diagonal code names a foreign element"; return -1; }
+                if (tileNodes[tileElems[(size_t)el * 4 + a]] != n) { error = "diagonal code: wrong local node"; return -1; }
+                if (tr.diagLocal == 0xFFFF) { error = "diagonal contribution on a row without diagonal entry"; return -1; }
+                if (!mark (globalElem[el], a, a)) { error = "diagonal contribution listed twice"; return -1; }
             }
         }
-        const int nbBatches = (h.nbEntries + 31) / 32;
-        for (int b = 0; b < nbBatches; b++) {
-            const TileBatch &tb = plan.batches[h.batchBase + b];
+        if (expectStart != h.nbEntries) { error = "entry count mismatch"; return -1; }
+        for (int b = 0; b < h.nbBatches; b++) {
+            const TileBatch &tb = batches[b];
             for (int s = 0; s < tb.steps; s++) {
                 for (int lane = 0; lane < 32; lane++) {
-                    const int code = plan.pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
-                    if ((code >> 4) == h.nbElems) continue;
-                    if (!mark (globalElem[code >> 4], (code >> 2) & 3, code & 3)) { error = "pair contribution listed twice"; return -1; }
+                    const int q = b * 32 + lane;
+                    const int code = pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
+                    const int el = code >> 4, a = (code >> 2) & 3, bb = code & 3;
+                    if (el == h.nbElems) { if (a || bb) { error = "bad padding code"; return -1; } continue; }
+                    if (el > h.nbElems || q >= h.nbEntries) { error = "pair code out of range"; return -1; }
+                    const TileRow &tr = rows[entryRow[q]];
+                    const int n = tr.node & 0x7fffffff;
+                    const uint16_t *ln = tileElems + (size_t)el * 4;
+                    const int l = tr.valueStart + (q - tr.localStart);
+                    if (tileNodes[ln[a]] != n || col[l] != tileNodes[ln[bb]] + 1) { error = "pair code lands on the wrong CSR entry"; return -1; }
+                    if (!mark (globalElem[el], a, bb)) { error = "pair contribution listed twice"; return -1; }
                 }
             }
         }
     }
+    if (rowsTotal != nbNodes) { error = "not every node is owned by a tile"; return -1; }
     for (int e = 0; e < nbElem; e++) {
         if (tripleSeen[e] != 0xFFFF) { error = "element " + std::to_string (e) + " misses a contribution"; return -1; }
     }

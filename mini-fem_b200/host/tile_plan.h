@@ -6,17 +6,18 @@
 // writes every CSR entry exactly once:
 //
 //   * nodes (= CSR rows) are grouped into spatially compact TILES (Morton order of the
-//     coordinates, cut greedily under shared-memory caps); one CTA owns one tile;
+//     coordinates, cut greedily under shared-memory caps); one CTA works on one tile;
 //   * a tile lists every element touching its rows (elements on tile borders appear in
 //     several tiles and their 12 gradient coefficients are recomputed there);
 //   * each CSR entry (i,j) of an owned row carries the list of (element, a, b) triples
-//     that contribute to it, a/b = local index of i/j in the element, elements in
-//     increasing id (the reference REF build's summation order);
+//     that contribute to it, a/b = local index of i/j in the element;
 //   * the diagonal entry (i,i) has one contribution per incident element and is handled
 //     by 4 lanes per row; the off-diagonal lists are stored transposed per 32 entries
-//     (one warp) so that a warp reads one coalesced 64-byte line per step.
+//     (one warp), and the order inside each list is chosen so that the 16 lanes of a
+//     half-warp hit different shared-memory banks at the same step where possible.
 //
-// All arrays are flat so that they can be copied to the device verbatim.
+// Everything one tile needs is ONE contiguous, 16-byte aligned record ("blob") so that a
+// single bulk copy (TMA, cp.async.bulk) stages it into shared memory.
 #ifndef MFB_TILE_PLAN_H
 #define MFB_TILE_PLAN_H
 
@@ -26,55 +27,58 @@
 
 namespace mfb {
 
-// 32 bytes per tile.
-struct TileHeader {
-    int nodeBase;     // first referenced node in TilePlan::tileNodes
-    int elemBase;     // first element in TilePlan::tileElems
-    int rowBase;      // first row in TilePlan::rows
-    int entryBase;    // first entry in TilePlan::entryRow
-    int batchBase;    // first 32-entry batch in TilePlan::batches
-    uint16_t nbRows, nbNodesRef, nbElems, nbEntries;
-    int pad;
+// First 48 bytes of a tile blob.  Offsets are in bytes from the start of the blob and
+// multiples of 16.  The row table follows the header immediately.
+struct TileBlobHeader {
+    uint16_t nbRows, nbNodesRef, nbElems, nbEntries, nbBatches, hasInterface;
+    uint32_t offNodes;      // int[nbNodesRef]: 0-based global ids, owned rows first
+    uint32_t offElems;      // ushort4[nbElems]: tile-local node indices of each element
+    uint32_t offEntryRow;   // uint8[nbEntries]: owned-row index of each tile-local entry
+    uint32_t offBatches;    // TileBatch[nbBatches]
+    uint32_t offDiag;       // uint16[]: (element<<2 | a) per diagonal contribution
+    uint32_t offPair;       // uint16[]: (element<<4 | a<<2 | b), transposed [step][lane]
+    uint32_t blobBytes;
+    uint32_t pad[2];
 };
 
-// 16 bytes per owned row.
+// 16 bytes per owned row, plus one sentinel whose diagCodeBase closes the last row.
 struct TileRow {
     int node;             // 0-based global node id; bit 31 set = interface node
     int valueStart;       // nodeToNodeRow[node]
-    int diagCodeBase;     // first (element<<2 | a) code of this row in TilePlan::diagCodes
+    int diagCodeBase;     // first diagonal code of this row (index into the blob's diag section)
     uint16_t localStart;  // tile-local index of the row's first entry
     uint16_t diagLocal;   // tile-local index of the diagonal entry (0xFFFF if none)
 };
 
 // 8 bytes per warp batch of 32 consecutive tile-local entries.
 struct TileBatch {
-    int codeBase;         // first code in TilePlan::pairCodes (transposed: [step][lane])
+    int codeBase;         // first code of the batch (index into the blob's pair section)
     int steps;            // longest contribution list in the batch
 };
 
 struct TilePlan {
     int nbTiles = 0, maxRows = 0, maxElems = 0, maxNodesRef = 0, maxEntries = 0;
     int nbInterfaceTiles = 0;            // tiles owning >= 1 interface node come first
-    int64_t nbTileElems = 0, nbContributions = 0;
-    std::vector<TileHeader> tiles;
-    std::vector<int> tileNodes;          // 0-based global ids; owned rows first, then halo nodes
-    std::vector<uint16_t> tileElems;     // 4 tile-local node indices per element
-    std::vector<TileRow> rows;           // + 1 sentinel: rows[r+1].diagCodeBase ends row r's codes
-    std::vector<uint8_t> entryRow;       // per tile-local entry: owned-row index
-    std::vector<TileBatch> batches;
-    std::vector<uint16_t> pairCodes;     // (element<<4 | a<<2 | b); padding = (nbElems<<4), a
-                                         // slot the kernel keeps at zero, so no branch is needed
-    std::vector<uint16_t> diagCodes;     // (element<<2 | a)
-    int64_t bytes () const;
+    int elemStride = 0;                  // shared-memory stride between the 4 local-node planes
+    int64_t nbTileElems = 0, nbContributions = 0, nbPaddedSteps = 0;
+    uint32_t maxBlobBytes = 0;
+    std::vector<uint64_t> tileOffset;    // nbTiles + 1 byte offsets into `blob`
+    std::vector<uint8_t> blob;
+    int64_t bytes () const { return (int64_t)blob.size () + (int64_t)tileOffset.size () * 8; }
+    const TileBlobHeader *header (int t) const { return reinterpret_cast<const TileBlobHeader*> (blob.data () + tileOffset[t]); }
 };
 
 struct TilePlanLimits {
     int maxRows = 64;        // <= 255 (entryRow is a byte)
-    int maxElems = 704;      // <= 4094 (12-bit element field, one slot kept for padding)
-    int maxNodesRef = 512;   // shared-memory coordinate staging
+    int maxElems = 640;      // <= 4094 (12-bit element field, one slot kept for padding)
+    int maxNodesRef = 640;   // shared-memory coordinate staging
     int maxEntries = 2048;   // <= 65535
+    bool bankAware = true;   // order each entry's contributions against bank conflicts
 };
 
+// Padding code of a tile = (nbElems << 4): the kernel keeps a zero coefficient vector in
+// that slot, so padded steps need no branch.
+//
 // isInterface may be null.  Returns 0, or -1 with `error` set (e.g. one node alone
 // exceeds a cap, or the CSR lacks a pair).
 int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *row,

@@ -53,7 +53,8 @@ class Problem(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("path", C.c_int), ("device", C.c_int), ("tileRows", C.c_int),
-                ("tileElems", C.c_int), ("threads", C.c_int), ("useGraph", C.c_int)]
+                ("tileElems", C.c_int), ("threads", C.c_int), ("useGraph", C.c_int),
+                ("ctas", C.c_int), ("bankAware", C.c_int)]
 
 
 lib.mfb_last_error.restype = C.c_char_p
@@ -280,7 +281,7 @@ class Context:
     """GPU context over one subdomain (mfb_ctx_*)."""
 
     def __init__(self, setup, path="tiled", device=0, nbBlocks=1, rank=0, tile_rows=0, tile_elems=0,
-                 threads=0, use_graph=False):
+                 threads=0, use_graph=False, ctas=0, bank_aware=True):
         m = setup.mesh
         self.setup = setup
         self._keep = dict(coord=np.ascontiguousarray(m.coord), e2n=_i32(setup.elemToNode), row=_i32(setup.row),
@@ -294,7 +295,7 @@ class Context:
                     setup.nbTotalColors, nbBlocks, rank, m.nbIntf, m.nbIntfNodes, _ptr(k["ii"]),
                     _ptr(k["inn"]), _ptr(k["nl"]))
         o = Options(PATH_NAMES[path] if isinstance(path, str) else path, device, tile_rows, tile_elems,
-                    threads, int(use_graph))
+                    threads, int(use_graph), ctas, 1 if bank_aware else -1)
         self.handle = C.c_void_p()
         _check(lib.mfb_ctx_create(C.byref(p), C.byref(o), C.byref(self.handle)), "mfb_ctx_create")
         self.nbValues = setup.nbEdges * setup.operatorDim
@@ -372,9 +373,10 @@ class Context:
         return a.value, b.value
 
     def plan_stats(self):
-        s = (C.c_int64 * 6)()
+        s = (C.c_int64 * 8)()
         _check(lib.mfb_ctx_plan_stats(self.handle, s), "mfb_ctx_plan_stats")
-        return dict(tiles=s[0], tile_elems=s[1], contributions=s[2], max_rows=s[3], max_elems=s[4], smem_bytes=s[5])
+        return dict(tiles=s[0], tile_elems=s[1], contributions=s[2], max_rows=s[3], max_elems=s[4], smem_bytes=s[5],
+                    padded_lane_steps=s[6], max_blob_bytes=s[7])
 
     def comm_init(self, unique_id: bytes):
         buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(unique_id)

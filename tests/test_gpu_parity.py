@@ -101,7 +101,7 @@ def test_unstructured_random(oracle, op, seed):
         ctx.close()
 
 
-@pytest.mark.parametrize("rows,elems,threads", [(1, 64, 32), (7, 120, 64), (32, 400, 128), (64, 704, 256), (200, 2000, 256)])
+@pytest.mark.parametrize("rows,elems,threads", [(1, 64, 32), (7, 120, 64), (32, 400, 128), (64, 640, 256), (128, 1200, 256)])
 def test_tile_shapes(oracle, rows, elems, threads):
     """Ragged tiles: one row per tile, tiles far below a warp batch, tiles near the caps."""
     mesh = mfb.Mesh.generate(9, 7, 8, seed=5)

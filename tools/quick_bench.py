@@ -13,6 +13,8 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--tile-rows", type=int, default=0)
 ap.add_argument("--tile-elems", type=int, default=0)
 ap.add_argument("--threads", type=int, default=0)
+ap.add_argument("--ctas", type=int, default=0)
+ap.add_argument("--no-bank-aware", action="store_true")
 a = ap.parse_args()
 
 t0 = time.time()
@@ -26,7 +28,7 @@ for path in a.paths.split(","):
     setup = mfb.Setup(mesh, a.op, coloring=(path == "color"))
     t1 = time.time()
     ctx = mfb.Context(setup, path=path, tile_rows=a.tile_rows, tile_elems=a.tile_elems, threads=a.threads,
-                      use_graph=(path == "color"))
+                      use_graph=(path == "color"), ctas=a.ctas, bank_aware=not a.no_bank_aware)
     t2 = time.time()
     for _ in range(3):
         ctx.iteration()
