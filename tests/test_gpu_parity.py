@@ -187,8 +187,8 @@ def test_eib_size_properties(op):
     # symmetry through elemToEdge: entry (j,k) of an element vs entry (k,j)
     e2e = setup.elemToEdge.reshape(-1, 4, 4)[::97]
     a, b = e2e.reshape(-1, 16), e2e.transpose(0, 2, 1).reshape(-1, 16)
-    if dim == 1:
-        assert np.array_equal(v[a], v[b])
+    if dim == 1:      # (i,j) and (j,i) sum the same products, possibly in a different order
+        assert np.abs(v[a] - v[b]).max() <= 1e-13 * np.abs(v).max()
     else:
         va, vb = v.reshape(-1, 3, 3)[a], v.reshape(-1, 3, 3)[b].transpose(0, 1, 3, 2)
         assert np.abs(va - vb).max() <= 1e-13 * np.abs(va).max()
