@@ -320,13 +320,15 @@ int build_device_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options *o)
     c->hostPlanStats.nbContributions = hp.nbContributions; c->hostPlanStats.maxRows = hp.maxRows;
     c->hostPlanStats.maxElems = hp.maxElems; c->hostPlanStats.nbPaddedSteps = hp.nbPaddedSteps;
     c->hostPlanStats.maxBlobBytes = hp.maxBlobBytes;
-    c->tiledSmem = tiled_smem_bytes (c->operatorID, c->plan, c->threads);
+    const bool pipelined = c->threads == tiled_pipeline_threads ();
+    c->tiledSmem = pipelined ? tiled_pipeline_smem_bytes (c->operatorID, c->plan)
+                             : tiled_smem_bytes (c->operatorID, c->plan, c->threads);
     if (c->tiledSmem > 227 * 1024) return fail (MFB_ERR_ARG, "tile plan needs more than 227 KB of shared memory per CTA; lower tileElems");
     MFB_CUDA (tiled_configure (c->operatorID, c->tiledSmem));
     // persistent grid: as many CTAs as fit on the device at once, each walking tiles with that stride
     cudaDeviceProp prop;
     MFB_CUDA (cudaGetDeviceProperties (&prop, c->device));
-    const int perSM = std::max (1, std::min ((int)(prop.sharedMemPerMultiprocessor / (c->tiledSmem + 1024)), 2048 / c->threads));
+    const int perSM = pipelined ? 1 : std::max (1, std::min ((int)(prop.sharedMemPerMultiprocessor / (c->tiledSmem + 1024)), 2048 / c->threads));
     c->tiledCtas = (o && o->ctas > 0) ? o->ctas : (o && o->ctas == -1) ? (1 << 30) : prop.multiProcessorCount * perSM;
     return MFB_OK;
 }
@@ -483,7 +485,9 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     c->threads = (o && o->threads > 0) ? o->threads : 256;
     c->useGraph = o ? o->useGraph : 0;
     if (c->path < MFB_PATH_TILED || c->path > MFB_PATH_COLOR) return fail (MFB_ERR_ARG, "mfb_ctx_create: unknown path");
-    if (c->threads % 32 || c->threads < 32 || c->threads > 256) return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256]");
+    if (c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {
+        return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256], or the pipelined kernel's CTA size");
+    }
     if (p->operatorID != 0 && p->operatorID != 1) return fail (MFB_ERR_ARG, "mfb_ctx_create: operatorID must be 0 (lap) or 1 (ela)");
     if (p->nbElem < 0 || p->nbNodes < 0 || p->nbEdges < 0) return fail (MFB_ERR_ARG, "mfb_ctx_create: negative size");
     if ((p->nbNodes > 0 && (!p->coord || !p->nodeToNodeRow)) || (p->nbElem > 0 && !p->elemToNode) ||

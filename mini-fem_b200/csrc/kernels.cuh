@@ -43,6 +43,9 @@ struct DeviceTilePlan {
 // fusePrec: 0 = values only; 1 = also write prec: the raw diagonal block for interface
 // nodes (they still need the halo sum), the masked + inverted block for all others.
 size_t tiled_smem_bytes (int operatorID, const DeviceTilePlan &plan, int threads);
+// Pipelined variant (one persistent 512-thread CTA per SM, warps specialised by role).
+size_t tiled_pipeline_smem_bytes (int operatorID, const DeviceTilePlan &plan);
+int tiled_pipeline_threads ();
 cudaError_t tiled_configure (int operatorID, size_t smemBytes);
 // `ctas` CTAs walk the tiles [firstTile, firstTile + nbTiles) with stride `ctas`.
 cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstTile, int nbTiles, int ctas,

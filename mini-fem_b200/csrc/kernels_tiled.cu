@@ -73,15 +73,15 @@ __device__ __forceinline__ void bulk_load (void *dst, const void *src, unsigned 
                   :: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
 }
 
-template <int OPDIM, int MINBLOCKS>
-__global__ void __launch_bounds__(256, MINBLOCKS)
+template <int OPDIM, int MINB, int STRIDE>
+__global__ void __launch_bounds__(256, MINB)
 tiled_assembly_kernel (const TiledArgs args)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const DeviceTilePlan &P = args.plan;
     const int tid = threadIdx.x, nThreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nWarps = nThreads >> 5;
-    const int strideE = P.elemStride;
+    const int strideE = STRIDE ? STRIDE : P.elemStride;     // compile-time where the plan uses a default cap
 
     // shared memory: [blob][cX cY cZ][sDiag][scratch = coordinates, later the warp slabs][mbarrier]
     unsigned char *sBlob = smemRaw;
@@ -115,6 +115,7 @@ tiled_assembly_kernel (const TiledArgs args)
         const int *tileNodes = reinterpret_cast<const int*> (sBlob + hdr.offNodes);
         const ushort4 *tileElems = reinterpret_cast<const ushort4*> (sBlob + hdr.offElems);
         const uint8_t *entryRow = sBlob + hdr.offEntryRow;
+        const uint16_t *laneEntry = reinterpret_cast<const uint16_t*> (sBlob + hdr.offLaneEntry);
         const TileBatch *batches = reinterpret_cast<const TileBatch*> (sBlob + hdr.offBatches);
         const uint16_t *diagCodes = reinterpret_cast<const uint16_t*> (sBlob + hdr.offDiag);
         const uint16_t *pairCodes = reinterpret_cast<const uint16_t*> (sBlob + hdr.offPair);
@@ -124,12 +125,16 @@ tiled_assembly_kernel (const TiledArgs args)
             const double *q = args.coord + (size_t)tileNodes[n] * 3;
             sX[n] = __ldg (q); sY[n] = __ldg (q + 1); sZ[n] = __ldg (q + 2);
         }
-        if (tid == 0) { cX[nbElems] = 0.0; cY[nbElems] = 0.0; cZ[nbElems] = 0.0; }   // padding slot
+        if (tid < 64) {                                   // the 16 all-zero slots of each plane (padding codes)
+            const int z = (tid >> 4) * strideE + nbElems + (tid & 15);
+            cX[z] = 0.0; cY[z] = 0.0; cZ[z] = 0.0;
+        }
         __syncthreads ();
 
         // ---- 2. gradient coefficients ----------------------------------------------------
         for (int e = tid; e < nbElems; e += nThreads) {
             const ushort4 ln = tileElems[e];
+            if (ln.x == 0xFFFF) continue;                 // hole of the coset numbering
             const int ids[4] = {ln.x, ln.y, ln.z, ln.w};
             double p[12], c[12];
             #pragma unroll
@@ -168,47 +173,23 @@ tiled_assembly_kernel (const TiledArgs args)
                 }
             }
             if (live && sub == 0) {
-                const int nodeField = sRows[r].node;
-                const int node = nodeField & 0x7fffffff;
-                const bool isInterface = nodeField < 0;
-                const bool hasDiag = sRows[r].diagLocal != 0xFFFF;
-                if (OPDIM == 1) {
-                    sDiag[r] = a00;
-                    if (args.fusePrec) args.prec[node] = isInterface ? a00 : 1.0 / a00;
-                }
+                if (OPDIM == 1) sDiag[r] = a00;
                 else {
                     const double tr = a00 + a11 + a22;
-                    double b[9] = {1.25 * a00 + tr, 1.25 * a01, 1.25 * a02,
-                                   1.25 * a01, 1.25 * a11 + tr, 1.25 * a12,
-                                   1.25 * a02, 1.25 * a12, 1.25 * a22 + tr};
-                    #pragma unroll
-                    for (int q = 0; q < 9; q++) sDiag[r * 9 + q] = b[q];
-                    if (args.fusePrec) {
-                        if (!isInterface) {
-                            int mx = 0, my = 0, mz = 0;
-                            if (args.checkBounds) {
-                                mx = __ldg (args.checkBounds + node);
-                                my = __ldg (args.checkBounds + (size_t)args.nbNodes + node);
-                                mz = __ldg (args.checkBounds + 2 * (size_t)args.nbNodes + node);
-                            }
-                            mask_block (b, mx, my, mz);
-                            if (hasDiag) invert3_lu (b);
-                        }
-                        double *dst = args.prec + (size_t)node * 9;
-                        #pragma unroll
-                        for (int q = 0; q < 9; q++) dst[q] = b[q];
-                    }
+                    sDiag[r * 9 + 0] = 1.25 * a00 + tr; sDiag[r * 9 + 1] = 1.25 * a01; sDiag[r * 9 + 2] = 1.25 * a02;
+                    sDiag[r * 9 + 3] = 1.25 * a01; sDiag[r * 9 + 4] = 1.25 * a11 + tr; sDiag[r * 9 + 5] = 1.25 * a12;
+                    sDiag[r * 9 + 6] = 1.25 * a02; sDiag[r * 9 + 7] = 1.25 * a12; sDiag[r * 9 + 8] = 1.25 * a22 + tr;
                 }
             }
         }
         __syncthreads ();      // sDiag complete; the coordinate planes are dead: scratch becomes the slabs
 
         // ---- 4. off-diagonal blocks, one lane per CSR entry ----------------------------------
-        const int nbBatches = (nbEntries + 31) >> 5;
+        const int nbBatches = hdr.nbBatches;
         for (int b = warp; b < nbBatches; b += nWarps) {
             const TileBatch tb = batches[b];
-            const int q = b * 32 + lane;
-            const bool live = q < nbEntries;
+            const int q = laneEntry[b * 32 + lane];
+            const bool live = q != 0xFFFF;
             const int r = live ? entryRow[q] : 0;
             const TileRow tr = sRows[r];
             const bool isDiag = live && q == tr.diagLocal;
@@ -247,18 +228,347 @@ tiled_assembly_kernel (const TiledArgs args)
                     slab[lane * 9 + k] = v;
                 }
                 __syncwarp ();
-                const int liveEntries = min (32, nbEntries - b * 32);
+                // each half-warp holds consecutive entries of one row: two contiguous runs
+                const unsigned liveMask = __ballot_sync (0xffffffffu, live);
+                const int run0 = __popc (liveMask & 0xffffu) * 9, run1 = __popc (liveMask >> 16) * 9;
+                double *out0 = args.values + (size_t)__shfl_sync (0xffffffffu, g, 0) * 9;
+                double *out1 = args.values + (size_t)__shfl_sync (0xffffffffu, g, 16) * 9 - 144;
                 #pragma unroll
                 for (int k = 0; k < 9; k++) {
                     const int m = k * 32 + lane;
-                    const int ent = m / 9, comp = m - ent * 9;
-                    const int gs = __shfl_sync (0xffffffffu, g, ent);
-                    if (ent < liveEntries) args.values[(size_t)gs * 9 + comp] = slab[m];
+                    if (m < 144) { if (m < run0) out0[m] = slab[m]; }
+                    else if (m - 144 < run1) out1[m] = slab[m];
                 }
                 __syncwarp ();
             }
         }
+        // ---- 5. fused preconditioner: one thread per owned row (last warps first: they get fewer batches) ----
+        if (args.fusePrec) {
+            for (int r = nThreads - 1 - tid; r < nbRows; r += nThreads) {
+                const int nodeField = sRows[r].node;
+                const int node = nodeField & 0x7fffffff;
+                const bool isInterface = nodeField < 0;
+                if (OPDIM == 1) {
+                    const double d = sDiag[r];
+                    args.prec[node] = isInterface ? d : 1.0 / d;
+                }
+                else {
+                    double b[9];
+                    #pragma unroll
+                    for (int q = 0; q < 9; q++) b[q] = sDiag[r * 9 + q];
+                    if (!isInterface) {
+                        int mx = 0, my = 0, mz = 0;
+                        if (args.checkBounds) {
+                            mx = __ldg (args.checkBounds + node);
+                            my = __ldg (args.checkBounds + (size_t)args.nbNodes + node);
+                            mz = __ldg (args.checkBounds + 2 * (size_t)args.nbNodes + node);
+                        }
+                        mask_block (b, mx, my, mz);
+                        if (sRows[r].diagLocal != 0xFFFF) invert3_lu (b);
+                    }
+                    double *dst = args.prec + (size_t)node * 9;
+                    #pragma unroll
+                    for (int q = 0; q < 9; q++) dst[q] = b[q];
+                }
+            }
+        }
         __syncthreads ();      // every reader of the blob / coefficients is done before the next tile lands
+    }
+}
+
+
+// ------------------------------------------------------------------------------------
+// Pipelined variant: ONE persistent CTA of 16 warps per SM, warps specialised by role, two
+// tiles in flight.  While the row warps run the shared-memory-bound diagonal / off-diagonal
+// passes of tile t, the coefficient warps run the FP64-bound element pass of tile t+1 and the
+// producer warp has the plan record of tile t+2 in flight (TMA) and gathers the coordinates
+// of tile t+1 with cp.async.  Stages are handed over through mbarriers:
+//   blobFull[s]   TMA bytes of the record have landed            (producer arms, TMA completes)
+//   coordFull[s]  the 32 producer lanes' cp.async copies are done (cp.async.mbarrier.arrive)
+//   coefFull[s]   the coefficient warps have written all planes
+//   stageFree[s]  every row-warp thread is done with the stage
+// ------------------------------------------------------------------------------------
+constexpr int kPipeWarps = 24, kCoefWarps = 4, kRowWarps = kPipeWarps - 1 - kCoefWarps;
+constexpr int kPipeThreads = kPipeWarps * 32;
+
+__device__ __forceinline__ void mbar_arrive (uint64_t *bar)
+{
+    asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (bar)) : "memory");
+}
+
+// Arrive on `bar` once all cp.async copies this thread issued so far have completed.
+__device__ __forceinline__ void cp_async_arrive (uint64_t *bar)
+{
+    asm volatile ("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32 (bar)) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_8 (void *dst, const void *src)
+{
+    asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32 (dst)), "l"(src) : "memory");
+}
+
+// Bounded wait: a protocol bug must trap instead of hanging the device.
+__device__ __forceinline__ void mbar_wait_bounded (uint64_t *bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (long spin = 0; spin < (1l << 22); spin++) {
+        asm volatile (
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32 (bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap ();
+}
+
+struct PipeStage {
+    unsigned char *blob;
+    double *sX, *sY, *sZ, *cX, *cY, *cZ, *sDiag;
+    uint64_t *blobFull, *coordFull, *coefFull, *stageFree;
+};
+
+template <int OPDIM>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+tiled_pipeline_kernel (const TiledArgs args)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const DeviceTilePlan &P = args.plan;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int strideE = P.elemStride;
+
+    // shared memory: per stage [blob][coordinates][coefficient planes][diagonal blocks], then the
+    // row warps' slabs, then 8 mbarriers
+    const size_t blobBytes = (P.maxBlobBytes + 127u) & ~127u;
+    const size_t stageDoubles = 3 * (size_t)P.maxNodesRef + 12 * (size_t)strideE + (size_t)P.maxRows * OPDIM;
+    const size_t stageBytes = blobBytes + ((stageDoubles * 8 + 127) & ~(size_t)127);
+    double *slabs = reinterpret_cast<double*> (smemRaw + 2 * stageBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t*> (slabs + (OPDIM == 9 ? kRowWarps * 288 : 0));
+    auto stage = [&] (int s) {                 // computed, not stored: keeps everything in registers
+        PipeStage S;
+        S.blob = smemRaw + s * stageBytes;
+        S.sX = reinterpret_cast<double*> (S.blob + blobBytes);
+        S.sY = S.sX + P.maxNodesRef;
+        S.sZ = S.sY + P.maxNodesRef;
+        S.cX = S.sZ + P.maxNodesRef;
+        S.cY = S.cX + 4 * strideE;
+        S.cZ = S.cY + 4 * strideE;
+        S.sDiag = S.cZ + 4 * strideE;
+        S.blobFull = bars + 4 * s; S.coordFull = bars + 4 * s + 1;
+        S.coefFull = bars + 4 * s + 2; S.stageFree = bars + 4 * s + 3;
+        return S;
+    };
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) {
+            const PipeStage S = stage (s);
+            mbar_init (S.blobFull, 1);
+            mbar_init (S.coordFull, 32);
+            mbar_init (S.coefFull, kCoefWarps * 32);
+            mbar_init (S.stageFree, kRowWarps * 32);
+        }
+    }
+    __syncthreads ();
+
+    const int firstTile = args.firstTile + blockIdx.x, tileStep = gridDim.x;
+
+    if (warp == 0) {
+        // ================= producer: plan records (TMA) and coordinates (cp.async) =========
+        int k = 0;
+        for (int tile = firstTile; tile < args.lastTile; tile += tileStep, k++) {
+            const PipeStage S = stage (k & 1);
+            const unsigned use = (unsigned)(k >> 1);
+            if (use > 0) mbar_wait_bounded (S.stageFree, (use - 1) & 1);     // previous tenant is gone
+            if (lane == 0) {
+                const uint64_t off = P.tileOffset[tile];
+                const unsigned bytes = (unsigned)(P.tileOffset[tile + 1] - off);
+                mbar_expect_tx (S.blobFull, bytes);
+                bulk_load (S.blob, P.blob + off, bytes, S.blobFull);
+            }
+            mbar_wait_bounded (S.blobFull, use & 1);
+            const TileBlobHeader &hdr = *reinterpret_cast<const TileBlobHeader*> (S.blob);
+            const int *tileNodes = reinterpret_cast<const int*> (S.blob + hdr.offNodes);
+            const int nbNodesRef = hdr.nbNodesRef;
+            for (int n = lane; n < nbNodesRef; n += 32) {
+                const double *q = args.coord + (size_t)tileNodes[n] * 3;
+                cp_async_8 (S.sX + n, q); cp_async_8 (S.sY + n, q + 1); cp_async_8 (S.sZ + n, q + 2);
+            }
+            cp_async_arrive (S.coordFull);
+        }
+    }
+    else if (warp <= kCoefWarps) {
+        // ================= coefficient warps: elem_coef of every tile element ==============
+        const int ct = tid - 32, nCoef = kCoefWarps * 32;
+        int k = 0;
+        for (int tile = firstTile; tile < args.lastTile; tile += tileStep, k++) {
+            const PipeStage S = stage (k & 1);
+            const unsigned use = (unsigned)(k >> 1);
+            mbar_wait_bounded (S.blobFull, use & 1);
+            mbar_wait_bounded (S.coordFull, use & 1);
+            const TileBlobHeader &hdr = *reinterpret_cast<const TileBlobHeader*> (S.blob);
+            const ushort4 *tileElems = reinterpret_cast<const ushort4*> (S.blob + hdr.offElems);
+            const int nbElems = hdr.nbElems;
+            if (ct < 64) {                                // the 16 all-zero slots of each plane (padding codes)
+                const int z = (ct >> 4) * strideE + nbElems + (ct & 15);
+                S.cX[z] = 0.0; S.cY[z] = 0.0; S.cZ[z] = 0.0;
+            }
+            for (int e = ct; e < nbElems; e += nCoef) {
+                const ushort4 ln = tileElems[e];
+                if (ln.x == 0xFFFF) continue;             // hole of the coset numbering
+                const int ids[4] = {ln.x, ln.y, ln.z, ln.w};
+                double p[12], c[12];
+                #pragma unroll
+                for (int i = 0; i < 4; i++) { p[3 * i] = S.sX[ids[i]]; p[3 * i + 1] = S.sY[ids[i]]; p[3 * i + 2] = S.sZ[ids[i]]; }
+                elem_coef (p, c);
+                #pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    S.cX[a * strideE + e] = c[3 * a]; S.cY[a * strideE + e] = c[3 * a + 1]; S.cZ[a * strideE + e] = c[3 * a + 2];
+                }
+            }
+            mbar_arrive (S.coefFull);
+        }
+    }
+    else {
+        // ================= row warps: diagonal pass, off-diagonal pass, write-out ============
+        const int rw = warp - 1 - kCoefWarps;
+        double *slab = slabs + rw * 288;
+        int k = 0;
+        for (int tile = firstTile; tile < args.lastTile; tile += tileStep, k++) {
+            const PipeStage S = stage (k & 1);
+            const unsigned use = (unsigned)(k >> 1);
+            mbar_wait_bounded (S.blobFull, use & 1);
+            mbar_wait_bounded (S.coefFull, use & 1);
+            const TileBlobHeader &hdr = *reinterpret_cast<const TileBlobHeader*> (S.blob);
+            const int nbRows = hdr.nbRows, nbElems = hdr.nbElems, nbEntries = hdr.nbEntries;
+            (void)nbElems;
+            const TileRow *sRows = reinterpret_cast<const TileRow*> (S.blob + sizeof (TileBlobHeader));
+            const uint8_t *entryRow = S.blob + hdr.offEntryRow;
+            const uint16_t *laneEntry = reinterpret_cast<const uint16_t*> (S.blob + hdr.offLaneEntry);
+            const TileBatch *batches = reinterpret_cast<const TileBatch*> (S.blob + hdr.offBatches);
+            const uint16_t *diagCodes = reinterpret_cast<const uint16_t*> (S.blob + hdr.offDiag);
+            const uint16_t *pairCodes = reinterpret_cast<const uint16_t*> (S.blob + hdr.offPair);
+            const double *cX = S.cX, *cY = S.cY, *cZ = S.cZ;
+            double *sDiag = S.sDiag;
+
+            for (int r0 = rw * 8; r0 < nbRows; r0 += kRowWarps * 8) {
+                const int r = r0 + (lane >> 2), sub = lane & 3;
+                const bool live = r < nbRows;
+                const int begin = live ? sRows[r].diagCodeBase : 0;
+                const int end   = live ? sRows[r + 1].diagCodeBase : 0;
+                double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+                for (int q = begin + sub; q < end; q += 4) {
+                    const int code = diagCodes[q];
+                    const int v = (code & 3) * strideE + (code >> 2);
+                    const double x = cX[v], y = cY[v], z = cZ[v];
+                    if (OPDIM == 1) { a00 += x * x + y * y + z * z; }
+                    else { a00 += x * x; a01 += x * y; a02 += x * z; a11 += y * y; a12 += y * z; a22 += z * z; }
+                }
+                #pragma unroll
+                for (int off = 1; off <= 2; off <<= 1) {
+                    a00 += __shfl_xor_sync (0xffffffffu, a00, off);
+                    if (OPDIM == 9) {
+                        a01 += __shfl_xor_sync (0xffffffffu, a01, off);
+                        a02 += __shfl_xor_sync (0xffffffffu, a02, off);
+                        a11 += __shfl_xor_sync (0xffffffffu, a11, off);
+                        a12 += __shfl_xor_sync (0xffffffffu, a12, off);
+                        a22 += __shfl_xor_sync (0xffffffffu, a22, off);
+                    }
+                }
+                if (live && sub == 0) {
+                    const int nodeField = sRows[r].node;
+                    const int node = nodeField & 0x7fffffff;
+                    const bool isInterface = nodeField < 0;
+                    const bool hasDiag = sRows[r].diagLocal != 0xFFFF;
+                    if (OPDIM == 1) {
+                        sDiag[r] = a00;
+                        if (args.fusePrec) args.prec[node] = isInterface ? a00 : 1.0 / a00;
+                    }
+                    else {
+                        const double tr = a00 + a11 + a22;
+                        double b[9] = {1.25 * a00 + tr, 1.25 * a01, 1.25 * a02,
+                                       1.25 * a01, 1.25 * a11 + tr, 1.25 * a12,
+                                       1.25 * a02, 1.25 * a12, 1.25 * a22 + tr};
+                        #pragma unroll
+                        for (int q = 0; q < 9; q++) sDiag[r * 9 + q] = b[q];
+                        if (args.fusePrec) {
+                            if (!isInterface) {
+                                int mx = 0, my = 0, mz = 0;
+                                if (args.checkBounds) {
+                                    mx = __ldg (args.checkBounds + node);
+                                    my = __ldg (args.checkBounds + (size_t)args.nbNodes + node);
+                                    mz = __ldg (args.checkBounds + 2 * (size_t)args.nbNodes + node);
+                                }
+                                mask_block (b, mx, my, mz);
+                                if (hasDiag) invert3_lu (b);
+                            }
+                            double *dst = args.prec + (size_t)node * 9;
+                            #pragma unroll
+                            for (int q = 0; q < 9; q++) dst[q] = b[q];
+                        }
+                    }
+                }
+            }
+            // the diagonal blocks of all rows must be in place before any entry lane copies one
+            asm volatile ("bar.sync 1, %0;" :: "n"(kRowWarps * 32) : "memory");
+
+            const int nbBatches = hdr.nbBatches;
+            for (int b = rw; b < nbBatches; b += kRowWarps) {
+                const TileBatch tb = batches[b];
+                const int q = laneEntry[b * 32 + lane];
+                const bool live = q != 0xFFFF;
+                const int r = live ? entryRow[q] : 0;
+                const TileRow tr = sRows[r];
+                const bool isDiag = live && q == tr.diagLocal;
+                const int g = tr.valueStart + (q - tr.localStart);         // global CSR entry
+                const uint16_t *codes = pairCodes + tb.codeBase + lane;
+
+                double acc[OPDIM];
+                #pragma unroll
+                for (int i = 0; i < OPDIM; i++) acc[i] = 0.0;
+                #pragma unroll 2
+                for (int t = 0; t < tb.steps; t++) {
+                    const int code = codes[t * 32];
+                    const int e = code >> 4;
+                    const int va = ((code >> 2) & 3) * strideE + e, vb = (code & 3) * strideE + e;
+                    const double ax = cX[va], ay = cY[va], az = cZ[va];
+                    const double bx = cX[vb], by = cY[vb], bz = cZ[vb];
+                    if (OPDIM == 1) {
+                        acc[0] += ax * bx + ay * by + az * bz;
+                    }
+                    else {
+                        acc[0] += ax * bx; acc[1] += ax * by; acc[2] += ax * bz;
+                        acc[3] += ay * bx; acc[4] += ay * by; acc[5] += ay * bz;
+                        acc[6] += az * bx; acc[7] += az * by; acc[8] += az * bz;
+                    }
+                }
+                if (OPDIM == 1) {
+                    if (live) args.values[g] = isDiag ? sDiag[r] : acc[0];
+                }
+                else {
+                    const double trA = acc[0] + acc[4] + acc[8];
+                    #pragma unroll
+                    for (int i = 0; i < 9; i++) {
+                        double v = 1.25 * acc[i] + ((i == 0 || i == 4 || i == 8) ? trA : 0.0);
+                        if (isDiag) v = sDiag[r * 9 + i];
+                        slab[lane * 9 + i] = v;
+                    }
+                    __syncwarp ();
+                    // each half-warp holds consecutive entries of one row: two contiguous runs
+                    const unsigned liveMask = __ballot_sync (0xffffffffu, live);
+                    const int run0 = __popc (liveMask & 0xffffu) * 9, run1 = __popc (liveMask >> 16) * 9;
+                    double *out0 = args.values + (size_t)__shfl_sync (0xffffffffu, g, 0) * 9;
+                    double *out1 = args.values + (size_t)__shfl_sync (0xffffffffu, g, 16) * 9 - 144;
+                    #pragma unroll
+                    for (int i = 0; i < 9; i++) {
+                        const int m = i * 32 + lane;
+                        if (m < 144) { if (m < run0) out0[m] = slab[m]; }
+                        else if (m - 144 < run1) out1[m] = slab[m];
+                    }
+                    __syncwarp ();
+                }
+            }
+            mbar_arrive (S.stageFree);
+        }
     }
 }
 
@@ -272,24 +582,60 @@ size_t tiled_smem_bytes (int operatorID, const DeviceTilePlan &plan, int threads
     return (((size_t)plan.maxBlobBytes + 127) & ~(size_t)127) + doubles * sizeof (double) + 16;
 }
 
-template <int OPDIM, int MINBLOCKS>
-cudaError_t configure_one ()
+size_t tiled_pipeline_smem_bytes (int operatorID, const DeviceTilePlan &plan)
+{
+    const int opDim = operatorID == 0 ? 1 : 9;
+    const size_t blobBytes = ((size_t)plan.maxBlobBytes + 127) & ~(size_t)127;
+    const size_t stageDoubles = 3 * (size_t)plan.maxNodesRef + 12 * (size_t)plan.elemStride + (size_t)plan.maxRows * opDim;
+    const size_t stageBytes = blobBytes + ((stageDoubles * 8 + 127) & ~(size_t)127);
+    return 2 * stageBytes + (opDim == 9 ? (size_t)kRowWarps * 288 * 8 : 0) + 8 * sizeof (uint64_t);
+}
+
+int tiled_pipeline_threads () { return kPipeThreads; }
+
+// Instantiations: stride 420 = default caps (36 rows / 384 elements, three CTAs per SM),
+// 660 = 64 rows / 624 elements (two CTAs per SM), 0 = any other cap (stride read at run time).
+constexpr int kStrideSmall = 420, kStrideLarge = 660;
+
+template <class K>
+cudaError_t opt_in (K kernel)
 {
     // The attribute belongs to the kernel, not to a context: several contexts (one per
     // subdomain) with different tile caps share it, so always opt in to the device maximum.
-    return cudaFuncSetAttribute (tiled_assembly_kernel<OPDIM, MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+template <int OPDIM>
+cudaError_t configure_op ()
+{
+    cudaError_t e;
+    if ((e = opt_in (tiled_assembly_kernel<OPDIM, 3, kStrideSmall>)) != cudaSuccess) return e;
+    if ((e = opt_in (tiled_assembly_kernel<OPDIM, 2, kStrideLarge>)) != cudaSuccess) return e;
+    if ((e = opt_in (tiled_assembly_kernel<OPDIM, 3, 0>)) != cudaSuccess) return e;
+    if ((e = opt_in (tiled_assembly_kernel<OPDIM, 2, 0>)) != cudaSuccess) return e;
+    return opt_in (tiled_pipeline_kernel<OPDIM>);
 }
 
 cudaError_t tiled_configure (int operatorID, size_t smemBytes)
 {
     (void)smemBytes;
-    cudaError_t e;
-    if (operatorID == 0) {
-        if ((e = configure_one<1, 2> ()) != cudaSuccess) return e;
-        return configure_one<1, 3> ();
+    return operatorID == 0 ? configure_op<1> () : configure_op<9> ();
+}
+
+template <int OPDIM>
+void launch_op (const TiledArgs &args, int grid, int threads, size_t smemBytes, cudaStream_t stream)
+{
+    if (threads == kPipeThreads) {          // pipelined variant: one 24-warp CTA per SM
+        tiled_pipeline_kernel<OPDIM><<<grid, kPipeThreads, smemBytes, stream>>> (args);
+        return;
     }
-    if ((e = configure_one<9, 2> ()) != cudaSuccess) return e;
-    return configure_one<9, 3> ();
+    // three co-resident CTAs per SM when the tile record is small enough (register cap 85)
+    const bool three = smemBytes + 1024 <= (size_t)(227 * 1024) / 3 && threads * 3 <= 2048;
+    const int stride = args.plan.elemStride;
+    if (three && stride == kStrideSmall)       tiled_assembly_kernel<OPDIM, 3, kStrideSmall><<<grid, threads, smemBytes, stream>>> (args);
+    else if (!three && stride == kStrideLarge) tiled_assembly_kernel<OPDIM, 2, kStrideLarge><<<grid, threads, smemBytes, stream>>> (args);
+    else if (three)                            tiled_assembly_kernel<OPDIM, 3, 0><<<grid, threads, smemBytes, stream>>> (args);
+    else                                       tiled_assembly_kernel<OPDIM, 2, 0><<<grid, threads, smemBytes, stream>>> (args);
 }
 
 cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstTile, int nbTiles, int ctas,
@@ -303,16 +649,8 @@ cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstT
     args.checkBounds = checkBounds; args.nbNodes = nbNodes; args.fusePrec = fusePrec;
     args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
     const int grid = std::max (1, std::min (ctas, nbTiles));
-    // three co-resident CTAs per SM when the tile record is small enough (register cap 85)
-    const bool three = smemBytes + 1024 <= (227 * 1024) / 3 && threads * 3 <= 2048;
-    if (operatorID == 0) {
-        if (three) tiled_assembly_kernel<1, 3><<<grid, threads, smemBytes, stream>>> (args);
-        else       tiled_assembly_kernel<1, 2><<<grid, threads, smemBytes, stream>>> (args);
-    }
-    else {
-        if (three) tiled_assembly_kernel<9, 3><<<grid, threads, smemBytes, stream>>> (args);
-        else       tiled_assembly_kernel<9, 2><<<grid, threads, smemBytes, stream>>> (args);
-    }
+    if (operatorID == 0) launch_op<1> (args, grid, threads, smemBytes, stream);
+    else                 launch_op<9> (args, grid, threads, smemBytes, stream);
     return cudaGetLastError ();
 }
 

@@ -10,6 +10,8 @@
 
 namespace mfb {
 
+int tile_plan_stride (int maxElems) { return ((maxElems + 3 + 16 + 15) / 16) * 16 + 4; }
+
 namespace {
 
 // Interleave the low 21 bits of x, y, z.
@@ -32,6 +34,8 @@ struct TileScratch {
     std::vector<uint16_t> elemNodes;          // 4 local ids per element
     std::vector<TileRow> rows;                // + sentinel
     std::vector<uint8_t> entryRow;
+    std::vector<uint16_t> laneEntry;          // per off-diagonal-pass lane: tile-local entry or 0xFFFF
+    int nbIds = 0;                            // element ids incl. holes of the coset numbering
     std::vector<TileBatch> batches;
     std::vector<uint16_t> pairCodes, diagCodes;
     int64_t contributions = 0, paddedSteps = 0;
@@ -43,60 +47,79 @@ struct TileScratch {
 // (local node a, element e); the planes start on a 128-byte boundary.
 inline int bank_of (int a, int e, int stride) { return (a * stride + e) & 15; }
 
-// Reorders the contribution lists of up to 16 lanes (one half-warp) so that, step by step,
-// the row-side slots (a,e) and the column-side slots (b,e) of the lanes fall into different
-// banks where possible.  Identical slots are a broadcast and cost nothing.  Greedy, lane by
-// lane and step by step (a pairwise-swap refinement was measured: 6 % fewer modelled
-// wavefronts for 10x the build time, not kept).
-struct HalfWarpSchedule {
-    int nbLanes = 0, steps = 0, stride = 0;
-    std::vector<uint16_t> code;                 // [step][lane], 0xFFFF = nothing
-
-    int slot_a (uint16_t c) const { return ((c >> 2) & 3) * stride + (c >> 4); }
-    int slot_b (uint16_t c) const { return (c & 3) * stride + (c >> 4); }
-
-};
-
-void order_half_warp (std::vector<uint16_t> *lists, int nbLanes, int stride)
+// Schedules the off-diagonal contributions of one ROW CHUNK (<= 16 consecutive entries of one
+// CSR row = one half-warp).  The (up to) three lanes whose column nodes belong to one element
+// are served in the same step: they read the same row-side slot (a broadcast) and three
+// different column-side planes.  Greedy per step: the element covering the most lanes that
+// cannot wait, then the most free lanes, at most four elements unless a lane without slack
+// needs a fifth.  The bank classes of the elements are chosen AFTERWARDS (coset numbering)
+// so that the elements of one step get different classes.
+// out[step*16 + lane] = code or 0xFFFF.  Returns the number of steps.
+int schedule_chunk (const std::vector<uint16_t> *lists, int nbLanes, bool bankAware, std::vector<uint16_t> &out)
 {
-    HalfWarpSchedule S;
-    S.nbLanes = nbLanes; S.stride = stride;
-    for (int l = 0; l < nbLanes; l++) S.steps = std::max (S.steps, (int)lists[l].size ());
-    if (S.steps == 0) return;
-    S.code.assign ((size_t)S.steps * 16, 0xFFFF);
-    std::vector<std::vector<uint16_t>> rest (lists, lists + nbLanes);
-    for (int t = 0; t < S.steps; t++) {                       // greedy construction
-        int cntA[16] = {0}, cntB[16] = {0};
-        int usedA[16], usedB[16], nUsed = 0;
-        for (int l = 0; l < nbLanes; l++) {
-            std::vector<uint16_t> &r = rest[l];
-            if (r.empty ()) continue;
-            int best = 0, bestCost = 1 << 30;
-            for (size_t k = 0; k < r.size (); k++) {
-                const int slotA = S.slot_a (r[k]), slotB = S.slot_b (r[k]);
-                int costA = cntA[slotA & 15], costB = cntB[slotB & 15];
-                for (int u = 0; u < nUsed; u++) {
-                    if (usedA[u] == slotA) costA = 0;
-                    if (usedB[u] == slotB) costB = 0;
-                }
-                const int cost = std::max (costA, costB) * 64 + costA + costB;
-                if (cost < bestCost) { bestCost = cost; best = (int)k; }
-            }
-            const uint16_t code = r[best];
-            r.erase (r.begin () + best);
-            S.code[(size_t)t * 16 + l] = code;
-            const int slotA = S.slot_a (code), slotB = S.slot_b (code);
-            bool dupA = false, dupB = false;
-            for (int u = 0; u < nUsed; u++) { dupA |= usedA[u] == slotA; dupB |= usedB[u] == slotB; }
-            if (!dupA) cntA[slotA & 15]++;
-            if (!dupB) cntB[slotB & 15]++;
-            usedA[nUsed] = slotA; usedB[nUsed] = slotB; nUsed++;
+    int T = 0, remaining[16], total = 0;
+    std::vector<uint16_t> rest[16];
+    for (int l = 0; l < nbLanes; l++) {
+        rest[l] = lists[l];
+        remaining[l] = (int)rest[l].size ();
+        T = std::max (T, remaining[l]);
+        total += remaining[l];
+    }
+    out.clear ();
+    if (!bankAware) {                               // plain element order, no gaps
+        out.assign ((size_t)T * 16, 0xFFFF);
+        for (int l = 0; l < nbLanes; l++) for (size_t t = 0; t < rest[l].size (); t++) out[t * 16 + l] = rest[l][t];
+        return T;
+    }
+    // contributions grouped by element: group g = (element, its remaining (lane, code) pairs)
+    struct Group { int elem; std::vector<std::pair<int, uint16_t>> pairs; };
+    std::vector<Group> groups;
+    for (int l = 0; l < nbLanes; l++) {
+        for (uint16_t code : rest[l]) {
+            const int e = code >> 4;
+            size_t g = 0;
+            while (g < groups.size () && groups[g].elem != e) g++;
+            if (g == groups.size ()) groups.push_back ({e, {}});
+            groups[g].pairs.push_back ({l, code});
         }
     }
-    for (int l = 0; l < nbLanes; l++) {
-        const size_t len = lists[l].size ();
-        for (size_t t = 0; t < len; t++) lists[l][t] = S.code[t * 16 + l];
+    int step = 0;
+    while (total > 0) {
+        out.resize ((size_t)(step + 1) * 16, 0xFFFF);
+        uint16_t *cur = &out[(size_t)step * 16];
+        const int stepsLeft = std::max (T - step, 1);
+        bool busy[16] = {false}, must[16];
+        int nMustOpen = 0, nChosen = 0;
+        for (int l = 0; l < nbLanes; l++) { must[l] = remaining[l] >= stepsLeft; nMustOpen += must[l]; }
+        for (;;) {
+            // element covering the most lanes that cannot wait, then the most free lanes,
+            // in a bank class this step does not use yet
+            int best = -1, bestScore = 0;
+            for (size_t g = 0; g < groups.size (); g++) {
+                int nMust = 0, nFree = 0;
+                for (auto &pr : groups[g].pairs) if (!busy[pr.first]) { nFree++; nMust += must[pr.first]; }
+                if (nFree == 0) continue;
+                if (nChosen >= 4 && nMust == 0) continue;            // four bank classes per step
+                if (nMustOpen == 0 && nFree < 2 && nChosen > 0) continue;   // do not open an element for one idle lane
+                const int score = nMust * 64 + nFree * 4 + (int)groups[g].pairs.size ();
+                if (score > bestScore) { bestScore = score; best = (int)g; }
+            }
+            if (best < 0) break;
+            Group &G = groups[best];
+            nChosen++;
+            for (size_t k = 0; k < G.pairs.size ();) {
+                const int l = G.pairs[k].first;
+                if (busy[l]) { k++; continue; }
+                cur[l] = G.pairs[k].second;
+                busy[l] = true; remaining[l]--; total--;
+                if (must[l]) nMustOpen--;
+                G.pairs.erase (G.pairs.begin () + k);
+            }
+        }
+        step++;
+        if (step > 4096) break;                     // cannot happen: every step places >= 1 code
     }
+    return step;
 }
 
 // Same idea for the diagonal pass: 4 lanes share one row's list (lane `sub` takes codes
@@ -133,13 +156,15 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                      const TilePlanLimits &lim, TilePlan &plan, std::string &error)
 {
     plan = TilePlan ();
-    if (lim.maxRows < 1 || lim.maxRows > 255 || lim.maxElems < 1 || lim.maxElems > 4094 ||
+    if (lim.maxRows < 1 || lim.maxRows > 255 || lim.maxElems < 1 || lim.maxElems > 4064 ||
         lim.maxNodesRef < 4 || lim.maxNodesRef > 65535 || lim.maxEntries < 1 || lim.maxEntries > 65535) {
         error = "tile plan limits out of range";
         return -1;
     }
-    // odd stride: the 4 local-node planes of one element land in 4 different banks
-    const int stride = (lim.maxElems + 1) | 1;
+    // plane stride = 4 (mod 16): the 4 local-node planes of element e occupy the 4 banks of the
+    // coset e mod 4 (8-byte words, 16 bank pairs); room for the ids (<= maxElems + 3 with the
+    // coset numbering's holes) and for the 16 all-zero slots the padding codes point at
+    const int stride = tile_plan_stride (lim.maxElems);
     plan.elemStride = stride;
 
     std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
@@ -256,6 +281,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
             for (int r = 0; r < nbRows + 8; r++) diagLists[r].clear ();
             s.entryRow.resize (nbEntries);
 
+            const int nbTileElems = (int)s.elems.size ();
             int localStart = 0;
             for (int r = 0; r < nbRows; r++) {
                 const int n = s.nodes[r], begin = row[n], end = row[n + 1];
@@ -291,7 +317,77 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                 localStart += end - begin;
             }
 
-            // diagonal codes, 8 rows (= one warp pass) at a time
+            // off-diagonal codes: every row starts on a half-warp boundary (chunks of <= 16
+            // consecutive entries), chunks are scheduled independently, two chunks of similar
+            // length share a warp; codes are stored transposed per warp [step][32 lanes]
+            struct Chunk { int firstEntry, nbLanes, steps; std::vector<uint16_t> codes; };
+            std::vector<Chunk> chunks;
+            for (int r = 0; r < nbRows; r++) {
+                const int len = row[s.nodes[r] + 1] - row[s.nodes[r]], first = s.rows[r].localStart;
+                for (int c0 = 0; c0 < len; c0 += 16) {
+                    Chunk ch;
+                    ch.firstEntry = first + c0; ch.nbLanes = std::min (16, len - c0);
+                    ch.steps = schedule_chunk (&lists[ch.firstEntry], ch.nbLanes, lim.bankAware, ch.codes);
+                    for (int l = 0; l < ch.nbLanes; l++) s.contributions += (int64_t)lists[ch.firstEntry + l].size ();
+                    chunks.push_back (std::move (ch));
+                }
+            }
+            // -- coset numbering: element id mod 4 = class.  Elements that meet in one step of one
+            //    chunk should differ in class; greedy colouring of that conflict graph, classes
+            //    kept equally large so that the ids stay dense.
+            std::vector<int> newId ((size_t)nbTileElems);
+            int nbIds = nbTileElems;
+            if (lim.bankAware && nbTileElems > 0) {
+                std::vector<std::vector<int>> meets ((size_t)nbTileElems);
+                for (const Chunk &ch : chunks) {
+                    for (int t = 0; t < ch.steps; t++) {
+                        int present[16], nPresent = 0;
+                        for (int l = 0; l < ch.nbLanes; l++) {
+                            const uint16_t code = ch.codes[(size_t)t * 16 + l];
+                            if (code == 0xFFFF) continue;
+                            const int e = code >> 4;
+                            bool known = false;
+                            for (int u = 0; u < nPresent; u++) known |= present[u] == e;
+                            if (!known) present[nPresent++] = e;
+                        }
+                        for (int u = 0; u < nPresent; u++) for (int v = 0; v < nPresent; v++) if (u != v) meets[present[u]].push_back (present[v]);
+                    }
+                }
+                std::vector<int> cls ((size_t)nbTileElems, -1), byDegree ((size_t)nbTileElems);
+                for (int el = 0; el < nbTileElems; el++) byDegree[el] = el;
+                std::stable_sort (byDegree.begin (), byDegree.end (), [&] (int x, int y) { return meets[x].size () > meets[y].size (); });
+                int classSize[4] = {0, 0, 0, 0};
+                const int classCap = (nbTileElems + 3) / 4;
+                for (int el : byDegree) {
+                    int clash[4] = {0, 0, 0, 0};
+                    for (int other : meets[el]) if (cls[other] >= 0) clash[cls[other]]++;
+                    int bestClass = -1, bestCost = 1 << 30;
+                    for (int c = 0; c < 4; c++) {
+                        if (classSize[c] >= classCap) continue;
+                        const int cost = clash[c] * 4096 + classSize[c];
+                        if (cost < bestCost) { bestCost = cost; bestClass = c; }
+                    }
+                    cls[el] = bestClass;
+                    classSize[bestClass]++;
+                }
+                int next[4] = {0, 0, 0, 0};
+                for (int el = 0; el < nbTileElems; el++) newId[el] = 4 * next[cls[el]]++ + cls[el];
+                nbIds = 4 * std::max ({classSize[0], classSize[1], classSize[2], classSize[3]});
+                std::vector<uint16_t> renum ((size_t)nbIds * 4, 0xFFFF);        // holes keep 0xFFFF
+                for (int el = 0; el < nbTileElems; el++) {
+                    for (int k = 0; k < 4; k++) renum[(size_t)newId[el] * 4 + k] = s.elemNodes[(size_t)el * 4 + k];
+                }
+                s.elemNodes.swap (renum);
+                for (Chunk &ch : chunks) {
+                    for (uint16_t &code : ch.codes) if (code != 0xFFFF) code = (uint16_t)((newId[code >> 4] << 4) | (code & 15));
+                }
+                for (int r = 0; r < nbRows; r++) {
+                    for (uint16_t &code : diagLists[r]) code = (uint16_t)((newId[code >> 2] << 2) | (code & 3));
+                }
+            }
+            s.nbIds = nbIds;
+
+            // diagonal codes, 4 rows (= one half-warp of the diagonal pass) at a time
             for (int r0 = 0; r0 < nbRows; r0 += 4) {
                 if (lim.bankAware) order_diag_half_warp (&diagLists[r0], std::min (4, nbRows - r0), stride);
             }
@@ -301,32 +397,51 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
             }
             TileRow sentinel = {0, 0, (int)s.diagCodes.size (), 0, 0xFFFF};
             s.rows.push_back (sentinel);
-            s.contributions = (int64_t)s.diagCodes.size ();
+            s.contributions += (int64_t)s.diagCodes.size ();
 
-            // off-diagonal codes: transposed per 32 entries, ordered per half-warp
-            const uint16_t padCode = (uint16_t)(s.elems.size () << 4);
-            const int nbBatches = (nbEntries + 31) / 32;
-            for (int b = 0; b < nbBatches; b++) {
-                const int lanes = std::min (32, nbEntries - b * 32);
-                if (lim.bankAware) {
-                    order_half_warp (&lists[b * 32], std::min (16, lanes), stride);
-                    if (lanes > 16) order_half_warp (&lists[b * 32 + 16], lanes - 16, stride);
-                }
-                int steps = 0;
-                for (int lane = 0; lane < lanes; lane++) steps = std::max (steps, (int)lists[b * 32 + lane].size ());
+            std::vector<int> byLength (chunks.size ());
+            for (size_t c = 0; c < chunks.size (); c++) byLength[c] = (int)c;
+            std::stable_sort (byLength.begin (), byLength.end (), [&] (int x, int y) { return chunks[x].steps > chunks[y].steps; });
+            // Idle lanes and gap steps get a padding code that names one of the 16 all-zero slots
+            // [nbIds, nbIds + 16) (local nodes 1 / 0): it adds nothing.  Where the half-warp has a
+            // live lane in that step, the slot is picked so that the padding lands in banks the
+            // live lanes leave free: on the column side the bank of a live element's row-side
+            // slot, on the row side a column-side bank of that element.
+            const uint16_t zeroPad = (uint16_t)(nbIds << 4);
+            for (size_t c = 0; c < byLength.size (); c += 2) {
+                const Chunk *half[2] = { &chunks[byLength[c]], c + 1 < byLength.size () ? &chunks[byLength[c + 1]] : nullptr };
+                const int steps = half[0]->steps;            // sorted: the first is the longer one
                 TileBatch tb = { (int)s.pairCodes.size (), steps };
                 s.batches.push_back (tb);
-                s.pairCodes.resize (s.pairCodes.size () + (size_t)steps * 32, padCode);
-                for (int lane = 0; lane < lanes; lane++) {
-                    const std::vector<uint16_t> &l = lists[b * 32 + lane];
-                    for (size_t k = 0; k < l.size (); k++) s.pairCodes[tb.codeBase + k * 32 + lane] = l[k];
-                    s.contributions += (int64_t)l.size ();
+                s.pairCodes.resize (s.pairCodes.size () + (size_t)steps * 32, zeroPad);
+                for (int h = 0; h < 2; h++) {
+                    for (int l = 0; l < 16; l++) {
+                        const bool liveLane = half[h] && l < half[h]->nbLanes;
+                        s.laneEntry.push_back (liveLane ? (uint16_t)(half[h]->firstEntry + l) : (uint16_t)0xFFFF);
+                    }
+                    if (!half[h]) continue;
+                    for (int t = 0; t < half[h]->steps; t++) {
+                        uint16_t pad = zeroPad;
+                        for (int l = 0; l < half[h]->nbLanes && pad == zeroPad; l++) {
+                            const uint16_t code = half[h]->codes[(size_t)t * 16 + l];
+                            if (code != 0xFFFF) {
+                                const int freeBank = (4 * ((code >> 2) & 3) + (code >> 4)) & 15;   // row-side slot's bank
+                                const int ez = nbIds + ((freeBank - nbIds) & 15);                  // ez = freeBank (mod 16)
+                                pad = (uint16_t)((ez << 4) | (1 << 2) | 0);
+                            }
+                        }
+                        for (int l = 0; l < 16; l++) {
+                            const uint16_t code = l < half[h]->nbLanes ? half[h]->codes[(size_t)t * 16 + l] : (uint16_t)0xFFFF;
+                            s.pairCodes[tb.codeBase + (size_t)t * 32 + h * 16 + l] = code != 0xFFFF ? code : pad;
+                        }
+                    }
                 }
                 s.paddedSteps += steps;
             }
             uint32_t bytes = (uint32_t)sizeof (TileBlobHeader) + (uint32_t)(s.rows.size () * sizeof (TileRow));
             bytes = align16 (bytes) + align16 ((uint32_t)(s.nodes.size () * 4));
-            bytes += align16 ((uint32_t)(s.elems.size () * 8)) + align16 ((uint32_t)s.entryRow.size ());
+            bytes += align16 ((uint32_t)(s.elemNodes.size () * 2)) + align16 ((uint32_t)s.entryRow.size ());
+            bytes += align16 ((uint32_t)(s.laneEntry.size () * 2));
             bytes += align16 ((uint32_t)(s.batches.size () * sizeof (TileBatch)));
             bytes += align16 ((uint32_t)(s.diagCodes.size () * 2)) + align16 ((uint32_t)(s.pairCodes.size () * 2));
             s.blobBytes = bytes;
@@ -348,7 +463,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         plan.tileOffset[k + 1] = plan.tileOffset[k] + s.blobBytes;
         plan.maxBlobBytes = std::max (plan.maxBlobBytes, s.blobBytes);
         plan.maxRows = std::max (plan.maxRows, (int)s.rows.size () - 1);
-        plan.maxElems = std::max (plan.maxElems, (int)s.elems.size ());
+        plan.maxElems = std::max (plan.maxElems, s.nbIds);
         plan.maxNodesRef = std::max (plan.maxNodesRef, (int)s.nodes.size ());
         plan.maxEntries = std::max (plan.maxEntries, (int)s.entryRow.size ());
         plan.nbTileElems += (int64_t)s.elems.size ();
@@ -363,7 +478,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         TileBlobHeader h;
         memset (&h, 0, sizeof h);
         h.nbRows = (uint16_t)(s.rows.size () - 1); h.nbNodesRef = (uint16_t)s.nodes.size ();
-        h.nbElems = (uint16_t)s.elems.size (); h.nbEntries = (uint16_t)s.entryRow.size ();
+        h.nbElems = (uint16_t)s.nbIds; h.nbEntries = (uint16_t)s.entryRow.size ();
         h.nbBatches = (uint16_t)s.batches.size (); h.hasInterface = s.hasInterface ? 1 : 0;
         uint32_t at = (uint32_t)sizeof (TileBlobHeader);
         memcpy (base + at, s.rows.data (), s.rows.size () * sizeof (TileRow));
@@ -371,9 +486,11 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         h.offNodes = at; memcpy (base + at, s.nodes.data (), s.nodes.size () * 4);
         at += align16 ((uint32_t)(s.nodes.size () * 4));
         h.offElems = at; memcpy (base + at, s.elemNodes.data (), s.elemNodes.size () * 2);
-        at += align16 ((uint32_t)(s.elems.size () * 8));
+        at += align16 ((uint32_t)(s.elemNodes.size () * 2));
         h.offEntryRow = at; memcpy (base + at, s.entryRow.data (), s.entryRow.size ());
         at += align16 ((uint32_t)s.entryRow.size ());
+        h.offLaneEntry = at; memcpy (base + at, s.laneEntry.data (), s.laneEntry.size () * 2);
+        at += align16 ((uint32_t)(s.laneEntry.size () * 2));
         h.offBatches = at; memcpy (base + at, s.batches.data (), s.batches.size () * sizeof (TileBatch));
         at += align16 ((uint32_t)(s.batches.size () * sizeof (TileBatch)));
         h.offDiag = at; memcpy (base + at, s.diagCodes.data (), s.diagCodes.size () * 2);
@@ -414,17 +531,19 @@ int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *
         const int *tileNodes = reinterpret_cast<const int*> (base + h.offNodes);
         const uint16_t *tileElems = reinterpret_cast<const uint16_t*> (base + h.offElems);
         const uint8_t *entryRow = base + h.offEntryRow;
+        const uint16_t *laneEntry = reinterpret_cast<const uint16_t*> (base + h.offLaneEntry);
         const TileBatch *batches = reinterpret_cast<const TileBatch*> (base + h.offBatches);
         const uint16_t *diagCodes = reinterpret_cast<const uint16_t*> (base + h.offDiag);
         const uint16_t *pairCodes = reinterpret_cast<const uint16_t*> (base + h.offPair);
         if (h.nbElems > plan.maxElems || h.nbElems >= plan.elemStride || h.nbRows > plan.maxRows ||
-            h.nbNodesRef > plan.maxNodesRef || h.nbBatches != (h.nbEntries + 31) / 32) {
+            h.nbNodesRef > plan.maxNodesRef) {
             error = "tile exceeds the plan maxima"; return -1;
         }
         // tile-local element -> global element, by matching its node quadruple
         std::vector<int> globalElem (h.nbElems, -1);
         for (int el = 0; el < h.nbElems; el++) {
             const uint16_t *ln = tileElems + (size_t)el * 4;
+            if (ln[0] == 0xFFFF) continue;                       // hole of the coset numbering
             int g[4];
             for (int k = 0; k < 4; k++) {
                 if (ln[k] >= h.nbNodesRef) { error = "local node index out of range"; return -1; }
@@ -459,22 +578,35 @@ int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *
             }
             for (int k = tr.diagCodeBase; k < rows[r + 1].diagCodeBase; k++) {
                 const int code = diagCodes[k], el = code >> 2, a = code & 3;
-                if (el >= h.nbElems) { error = "diagonal code names a foreign element"; return -1; }
+                if (el >= h.nbElems || globalElem[el] < 0) { error = "diagonal code names a foreign element"; return -1; }
                 if (tileNodes[tileElems[(size_t)el * 4 + a]] != n) { error = "diagonal code: wrong local node"; return -1; }
                 if (tr.diagLocal == 0xFFFF) { error = "diagonal contribution on a row without diagonal entry"; return -1; }
                 if (!mark (globalElem[el], a, a)) { error = "diagonal contribution listed twice"; return -1; }
             }
         }
         if (expectStart != h.nbEntries) { error = "entry count mismatch"; return -1; }
+        std::vector<uint8_t> entrySeen (h.nbEntries, 0);
         for (int b = 0; b < h.nbBatches; b++) {
             const TileBatch &tb = batches[b];
-            for (int s = 0; s < tb.steps; s++) {
-                for (int lane = 0; lane < 32; lane++) {
-                    const int q = b * 32 + lane;
+            for (int lane = 0; lane < 32; lane++) {
+                const int q = laneEntry[b * 32 + lane];
+                if (q != 0xFFFF) {
+                    if (q >= h.nbEntries || entrySeen[q]) { error = "entry mapped to two lanes"; return -1; }
+                    entrySeen[q] = 1;
+                    // a half-warp holds consecutive entries of ONE row
+                    if ((lane & 15) && laneEntry[b * 32 + lane - 1] != 0xFFFF &&
+                        (laneEntry[b * 32 + lane - 1] != q - 1 || entryRow[q - 1] != entryRow[q])) {
+                        error = "half-warp lanes are not consecutive entries of one row"; return -1;
+                    }
+                }
+                for (int s = 0; s < tb.steps; s++) {
                     const int code = pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
                     const int el = code >> 4, a = (code >> 2) & 3, bb = code & 3;
-                    if (el == h.nbElems) { if (a || bb) { error = "bad padding code"; return -1; } continue; }
-                    if (el > h.nbElems || q >= h.nbEntries) { error = "pair code out of range"; return -1; }
+                    if (el >= h.nbElems) {                           // padding: one of the 16 zero slots
+                        if (el >= h.nbElems + 16 || (el + 16) > plan.elemStride) { error = "bad padding code"; return -1; }
+                        continue;
+                    }
+                    if (el >= h.nbElems || q == 0xFFFF || globalElem[el] < 0) { error = "pair code out of range"; return -1; }
                     const TileRow &tr = rows[entryRow[q]];
                     const int n = tr.node & 0x7fffffff;
                     const uint16_t *ln = tileElems + (size_t)el * 4;
@@ -484,6 +616,7 @@ int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *
                 }
             }
         }
+        for (int q = 0; q < h.nbEntries; q++) if (!entrySeen[q]) { error = "entry without a lane"; return -1; }
     }
     if (rowsTotal != nbNodes) { error = "not every node is owned by a tile"; return -1; }
     for (int e = 0; e < nbElem; e++) {

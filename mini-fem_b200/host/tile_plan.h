@@ -12,9 +12,13 @@
 //   * each CSR entry (i,j) of an owned row carries the list of (element, a, b) triples
 //     that contribute to it, a/b = local index of i/j in the element;
 //   * the diagonal entry (i,i) has one contribution per incident element and is handled
-//     by 4 lanes per row; the off-diagonal lists are stored transposed per 32 entries
-//     (one warp), and the order inside each list is chosen so that the 16 lanes of a
-//     half-warp hit different shared-memory banks at the same step where possible.
+//     by 4 lanes per row;
+//   * in the off-diagonal pass every row starts on a half-warp boundary (chunks of <= 16
+//     entries), two chunks share a warp, and the contribution codes are stored transposed
+//     [step][32 lanes].  Tile-local element ids follow a coset numbering (id mod 4 = class,
+//     classes balanced around every row) and each chunk is scheduled so that one step touches
+//     elements of different classes: with a plane stride of 4 (mod 16) their coefficient
+//     slots then sit in disjoint shared-memory banks.
 //
 // Everything one tile needs is ONE contiguous, 16-byte aligned record ("blob") so that a
 // single bulk copy (TMA, cp.async.bulk) stages it into shared memory.
@@ -30,15 +34,16 @@ namespace mfb {
 // First 48 bytes of a tile blob.  Offsets are in bytes from the start of the blob and
 // multiples of 16.  The row table follows the header immediately.
 struct TileBlobHeader {
-    uint16_t nbRows, nbNodesRef, nbElems, nbEntries, nbBatches, hasInterface;
+    uint16_t nbRows, nbNodesRef, nbElems, nbEntries, nbBatches, hasInterface;   // nbElems counts ids (holes included)
     uint32_t offNodes;      // int[nbNodesRef]: 0-based global ids, owned rows first
     uint32_t offElems;      // ushort4[nbElems]: tile-local node indices of each element
     uint32_t offEntryRow;   // uint8[nbEntries]: owned-row index of each tile-local entry
+    uint32_t offLaneEntry;  // uint16[32*nbBatches]: tile-local entry of each off-diagonal-pass lane, 0xFFFF = idle
     uint32_t offBatches;    // TileBatch[nbBatches]
     uint32_t offDiag;       // uint16[]: (element<<2 | a) per diagonal contribution
     uint32_t offPair;       // uint16[]: (element<<4 | a<<2 | b), transposed [step][lane]
     uint32_t blobBytes;
-    uint32_t pad[2];
+    uint32_t pad[1];
 };
 
 // 16 bytes per owned row, plus one sentinel whose diagCodeBase closes the last row.
@@ -69,15 +74,17 @@ struct TilePlan {
 };
 
 struct TilePlanLimits {
-    int maxRows = 64;        // <= 255 (entryRow is a byte)
-    int maxElems = 640;      // <= 4094 (12-bit element field, one slot kept for padding)
-    int maxNodesRef = 640;   // shared-memory coordinate staging
+    int maxRows = 36;        // <= 255 (entryRow is a byte); 36 / 384 keeps a tile under 75 KB of shared
+                             // memory, i.e. three co-resident CTAs per SM (measured fastest on B200)
+    int maxElems = 384;      // <= 4064 (12-bit element field, slack for numbering holes + padding slot)
+    int maxNodesRef = 384;   // shared-memory coordinate staging
     int maxEntries = 2048;   // <= 65535
-    bool bankAware = true;   // order each entry's contributions against bank conflicts
+    bool bankAware = true;   // coset numbering + conflict-aware step schedule (false: element order)
 };
 
-// Padding code of a tile = (nbElems << 4): the kernel keeps a zero coefficient vector in
-// that slot, so padded steps need no branch.
+// Padding codes name an element id in [nbElems, nbElems + 16): the kernel keeps all-zero
+// coefficient vectors there, so padded steps need neither a branch nor a select.
+int tile_plan_stride (int maxElems);   // shared-memory stride between the 4 local-node planes
 //
 // isInterface may be null.  Returns 0, or -1 with `error` set (e.g. one node alone
 // exceeds a cap, or the CSR lacks a pair).

@@ -81,7 +81,7 @@ int main (int argc, char **argv)
             for (int k = 0; k < 4; k++) {
                 for (int half = 0; half < 2; half++) {
                     int sl[16];
-                    for (int l = 0; l < 16; l++) { int e = e0 + half * 16 + l; sl[l] = e < h.nbElems ? elems[e * 4 + k] : -1; }
+                    for (int l = 0; l < 16; l++) { int e = e0 + half * 16 + l; sl[l] = (e < h.nbElems && elems[e * 4 + k] != 0xFFFF) ? elems[e * 4 + k] : -1; }
                     wfP2 += 3 * wavefronts16 (sl, 16);
                 }
                 instrP2 += 3;
