@@ -25,7 +25,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
 
-METRIC = "EIB ela assembly+precond elements/s"
+METRIC = "EIB ela assembly+precond elements/s"      # BASELINE.json's metric (--op lap renames it)
 UNIT = "elements/s"
 
 
@@ -59,6 +59,11 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_text(grid, op, E, N, Z):
+    return (f"EIB-like Kuhn mesh, {grid[0]}x{grid[1]}x{grid[2]} cubes x 6 tets per GPU "
+            f"({E} elements, {N} nodes, {Z} CSR entries per GPU), operator {op}")
 
 
 def global_layout(args, world):
@@ -160,6 +165,8 @@ def reference_main(args, rank, world):
     grid = tuple(args.grid)
     one_iter_guess = 6.0e6 * (np.prod(grid) / 1e6) / 4.0e6 / max(min(cores, 64), 1) * 3
     nb_timed = max(1, min(args.steps, int(60.0 / max(one_iter_guess, 1e-3))))
+    import minifem_b200 as mfb
+    whole = mfb.Mesh.generate(*grid, seed=1)                      # header counts of the undivided mesh
     t0 = time.perf_counter()
     value, n, kind, detail, elements, blocks = run_reference_cpu(args.op, grid, nb_timed + 1, min(cores, 64))
     wall = time.perf_counter() - t0
@@ -168,7 +175,8 @@ def reference_main(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": nb_timed, "warmup": 1, "ms_per_step": 1e3 * elements / value, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"EIB-like {grid[0]}^3-cube Kuhn mesh, {args.op}, CPU reference on host cores"},
+            "config": {"workload": workload_text(grid, args.op, whole.nbElem, whole.nbNodes, whole.nbEdges),
+                       "arm": "the reference's CPU implementation on the host cores (no GPU work)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": n, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
@@ -178,7 +186,10 @@ def reference_main(args, rank, world):
 # ------------------------------------------------------------------------ our arm (GPU)
 
 def main():
+    global METRIC
     args = parse_args()
+    if args.op == "lap":
+        METRIC = "EIB lap assembly+precond elements/s"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
@@ -273,17 +284,19 @@ def main():
                 other[path]["colors"] = s2.nbTotalColors
             c2.close()
 
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes(args.op, E, Z, N)
     achieved = alg / (ms_step * 1e-3) / 1e9
-    workload = (f"EIB-like Kuhn mesh, {args.grid[0]}x{args.grid[1]}x{args.grid[2]} cubes x 6 tets per GPU "
-                f"({E} elements, {N} nodes, {Z} CSR entries per GPU), operator {args.op}, path {args.path}")
+    workload = workload_text(args.grid, args.op, E, N, Z)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "global_grid": list(grid), "blocks": list(blocks),
+            "config": {"workload": workload, "path": args.path, "global_grid": list(grid), "blocks": list(blocks),
                        "parallelism": f"dd{world} (one subdomain per GPU, NCCL interface sum)" if world > 1 else "single subdomain",
                        "l2": "inputs + outputs per step (>= 1.5 GB for ela) exceed the 126 MB L2; no flush needed",
                        "setup_s": round(setup_s, 2), "device_mesh_bytes": mesh_bytes, "device_plan_bytes": plan_bytes,

@@ -432,7 +432,9 @@ int do_iteration (mfb_ctx *c)
                             c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream));
     if (nIntfTiles > 0) c->launches++;
     MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));
-    MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, c->tiledCtas, c->threads,
+    // one CTA per interior tile (not a persistent grid): SM resources free up continuously, so
+    // the higher-priority halo kernels are scheduled as soon as their inputs are ready
+    MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, 1 << 30, c->threads,
                             c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream));
     if (c->plan.nbTiles - nIntfTiles > 0) c->launches++;
     MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
@@ -515,7 +517,11 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     }
     MFB_CUDA (cudaSetDevice (c->device));
     MFB_CUDA (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
-    MFB_CUDA (cudaStreamCreateWithFlags (&c->commStream, cudaStreamNonBlocking));
+    // the halo chain (pack, NCCL, add, interface inversion) must slip in between the CTAs of the
+    // interior assembly, not queue behind them
+    int leastPriority = 0, greatestPriority = 0;
+    MFB_CUDA (cudaDeviceGetStreamPriorityRange (&leastPriority, &greatestPriority));
+    MFB_CUDA (cudaStreamCreateWithPriority (&c->commStream, cudaStreamNonBlocking, greatestPriority));
     for (int s = 0; s < 5; s++) { MFB_CUDA (cudaEventCreate (&c->evStart[s])); MFB_CUDA (cudaEventCreate (&c->evStop[s])); }
     MFB_CUDA (cudaEventCreateWithFlags (&c->evIntfDone, cudaEventDisableTiming));
     MFB_CUDA (cudaEventCreateWithFlags (&c->evCommDone, cudaEventDisableTiming));
