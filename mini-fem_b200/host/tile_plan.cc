@@ -134,9 +134,14 @@ void order_diag_half_warp (std::vector<uint16_t> *rowLists, int nbRows, int stri
         int cnt[16] = {0};
         for (int r = 0; r < nbRows; r++) {
             for (int sub = 0; sub < 4 && !rest[r].empty (); sub++) {
+                // free bank first; among free banks the one this row still has most codes in
+                // (keeps rare banks for the late steps, when choice runs out)
+                int have[16] = {0};
+                for (uint16_t c : rest[r]) have[bank_of (c & 3, c >> 2, stride)]++;
                 int best = 0, bestCost = 1 << 30;
                 for (size_t k = 0; k < rest[r].size (); k++) {
-                    const int cost = cnt[bank_of (rest[r][k] & 3, rest[r][k] >> 2, stride)];
+                    const int b = bank_of (rest[r][k] & 3, rest[r][k] >> 2, stride);
+                    const int cost = cnt[b] * 1024 - have[b];
                     if (cost < bestCost) { bestCost = cost; best = (int)k; }
                 }
                 const uint16_t code = rest[r][best];
