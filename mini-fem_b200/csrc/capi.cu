@@ -304,6 +304,7 @@ int build_device_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options *o)
     lim.maxNodesRef = std::min (65535, std::max (lim.maxElems, 64));   // 24 B of staging per referenced node
     lim.maxEntries = 65535;
     lim.bankAware = !(o && o->bankAware < 0);
+    lim.laplacian = p->operatorID == 0;
     TilePlan hp;
     std::string err;
     if (build_tile_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn,

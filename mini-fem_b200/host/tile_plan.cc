@@ -430,7 +430,10 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                         for (int l = 0; l < half[h]->nbLanes && pad == zeroPad; l++) {
                             const uint16_t code = half[h]->codes[(size_t)t * 16 + l];
                             if (code != 0xFFFF) {
-                                const int freeBank = (4 * ((code >> 2) & 3) + (code >> 4)) & 15;   // row-side slot's bank
+                                // ela: the bank of the live lane's row-side slot; lap (one dot product
+                                // per contribution, banks {c, c+4, c+8} of the class): c + 12
+                                const int freeBank = lim.laplacian ? (((code >> 4) & 3) + 12)
+                                                                   : ((4 * ((code >> 2) & 3) + (code >> 4)) & 15);
                                 const int ez = nbIds + ((freeBank - nbIds) & 15);                  // ez = freeBank (mod 16)
                                 pad = (uint16_t)((ez << 4) | (1 << 2) | 0);
                             }

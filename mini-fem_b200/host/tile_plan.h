@@ -79,6 +79,7 @@ struct TilePlanLimits {
     int maxElems = 384;      // <= 4064 (12-bit element field, slack for numbering holes + padding slot)
     int maxNodesRef = 384;   // shared-memory coordinate staging
     int maxEntries = 2048;   // <= 65535
+    bool laplacian = false;  // scalar operator: the kernel keeps dot products, padding goes to bank c+12
     bool bankAware = true;   // coset numbering + conflict-aware step schedule (false: element order)
 };
 
