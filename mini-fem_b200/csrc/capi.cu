@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -274,6 +275,7 @@ struct mfb_ctx {
     TilePlan hostPlanStats;       // counters only (vectors released after upload)
     size_t tiledSmem = 0;
     int tiledCtas = 1;
+    bool tiledPrefetch = false;
     int64_t meshBytes = 0, planBytes = 0, launches = 0, graphLaunches = 0;
 
     NcclComm comm = nullptr;
@@ -313,17 +315,26 @@ int build_device_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options *o)
     }
     if (hp.blob.empty ()) hp.blob.resize (16);
     MFB_CUDA (put_plan (c, &c->plan.blob, hp.blob));
-    MFB_CUDA (put_plan (c, &c->plan.tileOffset, hp.tileOffset));
+    {   // device table: byte offset in the low 48 bits, (head bytes / 16) above
+        std::vector<uint64_t> packed (hp.tileOffset);
+        for (int t = 0; t < hp.nbTiles; t++) packed[t] |= (uint64_t)(hp.header (t)->offEntryRow >> 4) << 48;
+        MFB_CUDA (put_plan (c, &c->plan.tileOffset, packed));
+    }
     c->plan.nbTiles = hp.nbTiles; c->plan.nbInterfaceTiles = hp.nbInterfaceTiles;
     c->plan.maxRows = std::max (hp.maxRows, 1); c->plan.elemStride = hp.elemStride;
     c->plan.maxNodesRef = std::max (hp.maxNodesRef, 4); c->plan.maxBlobBytes = std::max (hp.maxBlobBytes, 16u);
+    c->plan.maxHeadBytes = std::max (hp.maxHeadBytes, 16u); c->plan.maxTailBytes = std::max (hp.maxTailBytes, 16u);
     c->hostPlanStats.nbTiles = hp.nbTiles; c->hostPlanStats.nbTileElems = hp.nbTileElems;
     c->hostPlanStats.nbContributions = hp.nbContributions; c->hostPlanStats.maxRows = hp.maxRows;
     c->hostPlanStats.maxElems = hp.maxElems; c->hostPlanStats.nbPaddedSteps = hp.nbPaddedSteps;
     c->hostPlanStats.maxBlobBytes = hp.maxBlobBytes;
     const bool pipelined = c->threads == tiled_pipeline_threads ();
+    // kernel variant: 0 / default = prefetching kernel, MFB_TILED_VARIANT=plain selects the simpler one
+    const char *variant = getenv ("MFB_TILED_VARIANT");
+    c->tiledPrefetch = !pipelined && c->threads == 256 && !(variant && std::string (variant) == "plain");
     c->tiledSmem = pipelined ? tiled_pipeline_smem_bytes (c->operatorID, c->plan)
-                             : tiled_smem_bytes (c->operatorID, c->plan, c->threads);
+                 : c->tiledPrefetch ? tiled_prefetch_smem_bytes (c->operatorID, c->plan, c->threads)
+                                    : tiled_smem_bytes (c->operatorID, c->plan, c->threads);
     if (c->tiledSmem > 227 * 1024) return fail (MFB_ERR_ARG, "tile plan needs more than 227 KB of shared memory per CTA; lower tileElems");
     MFB_CUDA (tiled_configure (c->operatorID, c->tiledSmem));
     // persistent grid: as many CTAs as fit on the device at once, each walking tiles with that stride
@@ -360,7 +371,7 @@ int do_assembly (mfb_ctx *c, int fusePrec)
 {
     if (c->path == MFB_PATH_TILED) {
         MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, c->plan.nbTiles, c->tiledCtas, c->threads, c->tiledSmem,
-                                c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, c->stream));
+                                c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, c->stream, c->tiledPrefetch));
         if (c->plan.nbTiles > 0) c->launches++;
         return MFB_OK;
     }
@@ -430,13 +441,13 @@ int do_iteration (mfb_ctx *c)
     // interface tiles first; their raw diagonal blocks travel while the interior assembles
     const int nIntfTiles = c->plan.nbInterfaceTiles;
     MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, c->tiledCtas, c->threads, c->tiledSmem, c->dCoord,
-                            c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream));
+                            c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
     if (nIntfTiles > 0) c->launches++;
     MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));
     // one CTA per interior tile (not a persistent grid): SM resources free up continuously, so
     // the higher-priority halo kernels are scheduled as soon as their inputs are ready
     MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, 1 << 30, c->threads,
-                            c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream));
+                            c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
     if (c->plan.nbTiles - nIntfTiles > 0) c->launches++;
     MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
     if ((rc = do_halo (c, c->commStream))) return rc;

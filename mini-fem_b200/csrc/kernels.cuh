@@ -37,7 +37,7 @@ struct DeviceTilePlan {
     const uint64_t *tileOffset = nullptr;     // nbTiles + 1
     int nbTiles = 0, nbInterfaceTiles = 0;
     int maxRows = 0, elemStride = 0, maxNodesRef = 0;
-    unsigned maxBlobBytes = 0;
+    unsigned maxBlobBytes = 0, maxHeadBytes = 0, maxTailBytes = 0;
 };
 
 // fusePrec: 0 = values only; 1 = also write prec: the raw diagonal block for interface
@@ -45,13 +45,16 @@ struct DeviceTilePlan {
 size_t tiled_smem_bytes (int operatorID, const DeviceTilePlan &plan, int threads);
 // Pipelined variant (one persistent 512-thread CTA per SM, warps specialised by role).
 size_t tiled_pipeline_smem_bytes (int operatorID, const DeviceTilePlan &plan);
+// Prefetching variant (default when it fits): next tile's head record and coordinates land while the
+// current tile is in its off-diagonal pass.  Selected with threads = 0 / 256 and prefetch = true.
+size_t tiled_prefetch_smem_bytes (int operatorID, const DeviceTilePlan &plan, int threads);
 int tiled_pipeline_threads ();
 cudaError_t tiled_configure (int operatorID, size_t smemBytes);
 // `ctas` CTAs walk the tiles [firstTile, firstTile + nbTiles) with stride `ctas`.
 cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstTile, int nbTiles, int ctas,
                           int threads, size_t smemBytes, const double *coord, double *values,
                           double *prec, const int *checkBounds, int nbNodes, int fusePrec,
-                          cudaStream_t stream);
+                          cudaStream_t stream, bool prefetch = false);
 
 }  // namespace mfb
 

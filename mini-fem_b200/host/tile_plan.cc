@@ -10,6 +10,8 @@
 
 namespace mfb {
 
+// smallest s = 4 (mod 16) such that s - 4 (the Laplacian's plane pitch) holds maxElems + 3 ids
+// and the 16 zero slots
 int tile_plan_stride (int maxElems) { return ((maxElems + 3 + 16 + 15) / 16) * 16 + 4; }
 
 namespace {
@@ -40,7 +42,7 @@ struct TileScratch {
     std::vector<uint16_t> pairCodes, diagCodes;
     int64_t contributions = 0, paddedSteps = 0;
     bool bad = false, hasInterface = false;
-    uint32_t blobBytes = 0;
+    uint32_t blobBytes = 0, headBytes = 0;
 };
 
 // Shared-memory bank pair (8-byte words, 16 per 128-byte line) of coefficient slot
@@ -412,7 +414,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
             // live lane in that step, the slot is picked so that the padding lands in banks the
             // live lanes leave free: on the column side the bank of a live element's row-side
             // slot, on the row side a column-side bank of that element.
-            const uint16_t zeroPad = (uint16_t)(nbIds << 4);
+            const uint16_t zeroPad = (uint16_t)((nbIds << 4) | (1 << 2) | 0);   // local nodes 1 / 0 like every padding code
             for (size_t c = 0; c < byLength.size (); c += 2) {
                 const Chunk *half[2] = { &chunks[byLength[c]], c + 1 < byLength.size () ? &chunks[byLength[c + 1]] : nullptr };
                 const int steps = half[0]->steps;            // sorted: the first is the longer one
@@ -448,7 +450,9 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
             }
             uint32_t bytes = (uint32_t)sizeof (TileBlobHeader) + (uint32_t)(s.rows.size () * sizeof (TileRow));
             bytes = align16 (bytes) + align16 ((uint32_t)(s.nodes.size () * 4));
-            bytes += align16 ((uint32_t)(s.elemNodes.size () * 2)) + align16 ((uint32_t)s.entryRow.size ());
+            bytes += align16 ((uint32_t)(s.elemNodes.size () * 2));
+            s.headBytes = bytes;
+            bytes += align16 ((uint32_t)s.entryRow.size ());
             bytes += align16 ((uint32_t)(s.laneEntry.size () * 2));
             bytes += align16 ((uint32_t)(s.batches.size () * sizeof (TileBatch)));
             bytes += align16 ((uint32_t)(s.diagCodes.size () * 2)) + align16 ((uint32_t)(s.pairCodes.size () * 2));
@@ -470,6 +474,8 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         if (s.bad) { error = "CSR lacks a node pair of an element (tile " + std::to_string (execOrder[k]) + ")"; return -1; }
         plan.tileOffset[k + 1] = plan.tileOffset[k] + s.blobBytes;
         plan.maxBlobBytes = std::max (plan.maxBlobBytes, s.blobBytes);
+        plan.maxHeadBytes = std::max (plan.maxHeadBytes, s.headBytes);
+        plan.maxTailBytes = std::max (plan.maxTailBytes, s.blobBytes - s.headBytes);
         plan.maxRows = std::max (plan.maxRows, (int)s.rows.size () - 1);
         plan.maxElems = std::max (plan.maxElems, s.nbIds);
         plan.maxNodesRef = std::max (plan.maxNodesRef, (int)s.nodes.size ());
@@ -611,7 +617,9 @@ int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *
                     const int code = pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
                     const int el = code >> 4, a = (code >> 2) & 3, bb = code & 3;
                     if (el >= h.nbElems) {                           // padding: one of the 16 zero slots
-                        if (el >= h.nbElems + 16 || (el + 16) > plan.elemStride) { error = "bad padding code"; return -1; }
+                        // local nodes must be (1, 0): the kernels zero exactly those slots (and the
+                        // Laplacian's pair plane of (1, 0))
+                        if (el >= h.nbElems + 16 || el >= plan.elemStride - 4 || a != 1 || bb != 0) { error = "bad padding code"; return -1; }
                         continue;
                     }
                     if (el >= h.nbElems || q == 0xFFFF || globalElem[el] < 0) { error = "pair code out of range"; return -1; }

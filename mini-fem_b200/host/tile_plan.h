@@ -67,6 +67,7 @@ struct TilePlan {
     int elemStride = 0;                  // shared-memory stride between the 4 local-node planes
     int64_t nbTileElems = 0, nbContributions = 0, nbPaddedSteps = 0;
     uint32_t maxBlobBytes = 0;
+    uint32_t maxHeadBytes = 0, maxTailBytes = 0;   // head = header..elements (bytes [0, offEntryRow)), tail = the rest
     std::vector<uint64_t> tileOffset;    // nbTiles + 1 byte offsets into `blob`
     std::vector<uint8_t> blob;
     int64_t bytes () const { return (int64_t)blob.size () + (int64_t)tileOffset.size () * 8; }
