@@ -134,8 +134,17 @@ void order_diag_half_warp (std::vector<uint16_t> *rowLists, int nbRows, int stri
     std::vector<std::vector<uint16_t>> rest (rowLists, rowLists + nbRows);
     for (size_t t = 0; t < steps; t++) {
         int cnt[16] = {0};
-        for (int r = 0; r < nbRows; r++) {
-            for (int sub = 0; sub < 4 && !rest[r].empty (); sub++) {
+        // one code per (row, sub-lane); the row with the fewest codes left chooses first
+        int orderRows[4] = {0, 1, 2, 3};
+        for (int i = 1; i < nbRows; i++) {                       // insertion sort of <= 4 rows
+            for (int j = i; j > 0 && rest[orderRows[j]].size () < rest[orderRows[j - 1]].size (); j--) std::swap (orderRows[j], orderRows[j - 1]);
+        }
+        uint16_t picked[4][4];
+        int nPicked[4] = {0, 0, 0, 0};
+        for (int sub = 0; sub < 4; sub++) {
+            for (int oi = 0; oi < nbRows; oi++) {
+                const int r = orderRows[oi];
+                if (rest[r].empty ()) continue;
                 // free bank first; among free banks the one this row still has most codes in
                 // (keeps rare banks for the late steps, when choice runs out)
                 int have[16] = {0};
@@ -148,10 +157,11 @@ void order_diag_half_warp (std::vector<uint16_t> *rowLists, int nbRows, int stri
                 }
                 const uint16_t code = rest[r][best];
                 rest[r].erase (rest[r].begin () + best);
-                out[r].push_back (code);
+                picked[r][nPicked[r]++] = code;
                 cnt[bank_of (code & 3, code >> 2, stride)]++;
             }
         }
+        for (int r = 0; r < nbRows; r++) for (int k = 0; k < nPicked[r]; k++) out[r].push_back (picked[r][k]);
     }
     for (int r = 0; r < nbRows; r++) rowLists[r].swap (out[r]);
 }
@@ -393,6 +403,50 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                 }
             }
             s.nbIds = nbIds;
+
+            // -- halo node numbering against bank conflicts of the coefficient phase: thread e reads
+            //    the coordinates of its 4 nodes from planes indexed by local node id, 16 consecutive
+            //    element ids per half-warp; owned nodes keep id = row, every other referenced node
+            //    gets the residue (id mod 16) least used by the nodes it shares such a read with
+            if (lim.bankAware && nbIds > 0) {
+                const int nbRef = (int)s.nodes.size ();
+                const int nbSets = ((nbIds + 15) / 16) * 4;
+                std::vector<std::vector<int>> setsOfNode ((size_t)nbRef);
+                for (int id = 0; id < nbIds; id++) {
+                    if (s.elemNodes[(size_t)id * 4] == 0xFFFF) continue;
+                    for (int k = 0; k < 4; k++) {
+                        std::vector<int> &v = setsOfNode[s.elemNodes[(size_t)id * 4 + k]];
+                        const int set = (id / 16) * 4 + k;
+                        if (std::find (v.begin (), v.end (), set) == v.end ()) v.push_back (set);
+                    }
+                }
+                std::vector<uint8_t> used ((size_t)nbSets * 16, 0);
+                std::vector<int> newNode ((size_t)nbRef, -1), nextFree (16);
+                for (int n = 0; n < nbRows; n++) {
+                    newNode[n] = n;
+                    for (int set : setsOfNode[n]) used[(size_t)set * 16 + (n & 15)]++;
+                }
+                for (int r = 0; r < 16; r++) { nextFree[r] = nbRows + ((r - nbRows) & 15); }
+                int maxId = nbRows - 1;
+                for (int n = nbRows; n < nbRef; n++) {
+                    int bestRes = 0, bestCost = 1 << 30;
+                    for (int r = 0; r < 16; r++) {
+                        if (nextFree[r] >= lim.maxNodesRef) continue;
+                        int cost = 0;
+                        for (int set : setsOfNode[n]) cost += used[(size_t)set * 16 + r];
+                        cost = cost * 65536 + nextFree[r];
+                        if (cost < bestCost) { bestCost = cost; bestRes = r; }
+                    }
+                    newNode[n] = nextFree[bestRes];
+                    nextFree[bestRes] += 16;
+                    maxId = std::max (maxId, newNode[n]);
+                    for (int set : setsOfNode[n]) used[(size_t)set * 16 + bestRes]++;
+                }
+                std::vector<int> renumNodes ((size_t)maxId + 1, s.nodes.empty () ? 0 : s.nodes[0]);   // holes: any valid node
+                for (int n = 0; n < nbRef; n++) renumNodes[newNode[n]] = s.nodes[n];
+                s.nodes.swap (renumNodes);
+                for (uint16_t &ln : s.elemNodes) if (ln != 0xFFFF) ln = (uint16_t)newNode[ln];
+            }
 
             // diagonal codes, 4 rows (= one half-warp of the diagonal pass) at a time
             for (int r0 = 0; r0 < nbRows; r0 += 4) {
