@@ -94,3 +94,41 @@ def test_nccl_halo_under_torchrun(nranks, tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "nccl_worker.py")]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0 and res.stdout.count("NCCL_WORKER_OK") == nranks, res.stdout[-3000:]
+
+
+def test_driver_two_ranks(tmp_path):
+    """minifem_b200 as two processes (RANK / WORLD_SIZE like mpirun -np 2): per-rank input files,
+    NCCL id and timer reduction through the rendezvous directory, numerical check per rank."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    grid, blocks = (12, 8, 8), (2, 1, 1)
+    data, rdv = str(tmp_path / "data"), str(tmp_path / "rdv")
+    os.makedirs(rdv)
+    oracle = Oracle()
+    meshes = [mfb.Mesh.generate(*grid, blocks=blocks, rank=r, seed=6) for r in range(2)]
+    for op in ("ela",):
+        setups = [mfb.Setup(m, op) for m in meshes]
+        results = [oracle.fem_iteration(s) for s in setups]
+        precs = [np.ascontiguousarray(res[1]) for res in results]
+        oracle.halo_exchange(precs, [m.intfIndex for m in meshes], [m.intfNodes for m in meshes],
+                             [m.neighborsList for m in meshes], 9)
+        for r, s in enumerate(setups):
+            mfb.Mesh.generate_to_file(os.path.join(data, "EIB", "inputs", f"{op}_2_{r}"), *grid, blocks=blocks, rank=r, seed=6)
+            p = oracle.prec_inversion(precs[r], s.row, s.col, s.checkBounds, s.mesh.nbNodes, 1)
+            path = os.path.join(data, "EIB", "checkings", f"{op}_2_{r}").encode()
+            assert mfb.lib.mfb_checking_write(path, oracle.norm(results[r][0]), oracle.norm(p)) == 0
+        exe = os.path.join(ROOT, "mini-fem_b200", "minifem_b200")
+        procs = []
+        for r in range(2):
+            env = dict(os.environ, MINIFEM_DATA_PATH=data, MINIFEM_RENDEZVOUS=rdv, RANK=str(r), WORLD_SIZE="2",
+                       LOCAL_RANK=str(r), MINIFEM_FUSED=str(r % 2 * 0 + 1))
+            procs.append(subprocess.Popen([exe, "EIB", op, "3"], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=300)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+        assert "Average cycles" in outs[0] and "Average cycles" not in outs[1]          # rank 0 prints (FEM.cc:125)
+        for r in range(2):
+            report = open(tmp_path / f"numerical_results_{r}").read()
+            diffs = [float(l.split(":")[1]) for l in report.splitlines() if "difference" in l]
+            assert len(diffs) == 2 and max(diffs) < 1e-13, report

@@ -115,6 +115,19 @@ def test_tile_shapes(oracle, rows, elems, threads):
         ctx.close()
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_mesh_without_elements(oracle, path):
+    """Nodes but no element: empty CSR rows, lap prec = 1/0 = inf, ela prec = masked zero block."""
+    mesh = ArrayMesh(np.arange(15, dtype=np.float64), np.zeros(0, np.int32), 5, np.array([0, 52, 10, 0, 54], np.int32))
+    for op in ("lap", "ela"):
+        setup = mfb.Setup(mesh, op, coloring=(path == "color"))
+        assert setup.nbEdges == 0
+        ctx = mfb.Context(setup, path=path)
+        check_against_oracle(oracle, setup, ctx, fused=True)
+        check_against_oracle(oracle, setup, ctx, fused=False)
+        ctx.close()
+
+
 def test_element_interval_callback(oracle):
     """assembly_{lap,ela}_seq(userArgs, first, last) — inclusive interval, no zeroing."""
     mesh = mfb.Mesh.generate(6, 5, 7, seed=6)
