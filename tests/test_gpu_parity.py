@@ -128,6 +128,26 @@ def test_mesh_without_elements(oracle, path):
         ctx.close()
 
 
+@pytest.mark.parametrize("variant", ["plain", "pipeline"])
+@pytest.mark.parametrize("op", ["lap", "ela"])
+def test_tiled_kernel_variants(oracle, op, variant, monkeypatch):
+    """The two non-default TILED kernels stay parity-green: the same phases without prefetch
+    (MFB_TILED_VARIANT=plain) and the warp-specialised pipelined kernel (768-thread CTAs)."""
+    if variant == "plain":
+        monkeypatch.setenv("MFB_TILED_VARIANT", "plain")
+    for grid, seed in (((3, 2, 2), 1), ((14, 11, 9), 2)):
+        mesh = mfb.Mesh.generate(*grid, seed=seed)
+        setup = mfb.Setup(mesh, op)
+        ctx = mfb.Context(setup, path="tiled", threads=768 if variant == "pipeline" else 0)
+        check_against_oracle(oracle, setup, ctx, fused=True)
+        check_against_oracle(oracle, setup, ctx, fused=False)
+        v1, p1 = ctx.download()
+        ctx.iteration()
+        v2, p2 = ctx.download()
+        assert np.array_equal(v1, v2) and np.array_equal(p1, p2, equal_nan=True)
+        ctx.close()
+
+
 def test_element_interval_callback(oracle):
     """assembly_{lap,ela}_seq(userArgs, first, last) — inclusive interval, no zeroing."""
     mesh = mfb.Mesh.generate(6, 5, 7, seed=6)
