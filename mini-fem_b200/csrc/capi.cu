@@ -438,18 +438,20 @@ int do_iteration (mfb_ctx *c)
     const bool exchange = c->nbBlocks > 1 && c->nbIntf > 0;
     if (!exchange) return do_assembly (c, 1);
     if (!c->comm) return fail (MFB_ERR_STATE, "mfb_ctx_iteration: call mfb_ctx_comm_init first (nbBlocks > 1)");
-    // interface tiles first; their raw diagonal blocks travel while the interior assembles
+    // Two co-resident kernels.  The high-priority stream takes the tiles that own interface
+    // nodes on a small persistent grid, then packs their raw diagonal blocks, exchanges them
+    // (NCCL), adds and inverts; the main stream assembles the interior tiles on the rest of the
+    // device.  The two kernels write disjoint rows; the streams join at the end.
     const int nIntfTiles = c->plan.nbInterfaceTiles;
-    MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, c->tiledCtas, c->threads, c->tiledSmem, c->dCoord,
-                            c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
+    const int intfCtas = std::max (c->tiledCtas / 16, 1), interiorCtas = std::max (c->tiledCtas - intfCtas, 1);
+    MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));                 // everything queued so far
+    MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
+    MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, intfCtas, c->threads, c->tiledSmem, c->dCoord,
+                            c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->commStream, c->tiledPrefetch));
     if (nIntfTiles > 0) c->launches++;
-    MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));
-    // one CTA per interior tile (not a persistent grid): SM resources free up continuously, so
-    // the higher-priority halo kernels are scheduled as soon as their inputs are ready
-    MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, 1 << 30, c->threads,
+    MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, interiorCtas, c->threads,
                             c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
     if (c->plan.nbTiles - nIntfTiles > 0) c->launches++;
-    MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
     if ((rc = do_halo (c, c->commStream))) return rc;
     MFB_CUDA (launch_prec_inversion_list (c->operatorID, c->dPrec, c->dDiagIndex, c->dCheckBounds, c->nbNodes,
                                           c->dUniqNodes, c->nbUniqIntf, c->commStream));
