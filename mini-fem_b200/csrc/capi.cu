@@ -896,6 +896,7 @@ extern "C" int mfb_tile_plan_selfcheck (const mfb_problem *p, int tileRows, int 
     if (tileElems > 0) lim.maxElems = tileElems;
     lim.maxNodesRef = std::min (65535, std::max (lim.maxElems, 64));
     lim.maxEntries = 65535;
+    lim.laplacian = p->operatorID == 0;
     std::vector<uint8_t> isIntf;
     if (p->nbBlocks > 1 && p->nbIntfNodes > 0) {
         isIntf.assign ((size_t)p->nbNodes, 0);

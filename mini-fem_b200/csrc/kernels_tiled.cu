@@ -77,19 +77,8 @@ __device__ __forceinline__ void bulk_load (void *dst, const void *src, unsigned 
                   :: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
 }
 
-// Laplacian tiles keep, per element, the 10 distinct dot products of its gradient rows instead
-// of the rows themselves (one shared-memory load per contribution instead of six).  Plane of
-// the pair (a,b), a != b: 2*colour + (a && b), colour = (a ^ b) - 1 — the proper 3-edge-colouring
-// of K4 ({01,23}, {02,13}, {03,12}), so the three pairs of one local node get three different
-// colours; plane of (a,a): 6 + a.  Plane p starts at p*PS + 4*residue (PS = stride - 4, a
-// multiple of 16; residue = colour, or a for the diagonal planes): with the coset numbering an
-// element of class c then keeps its off-diagonal dots in banks {c, c+4, c+8}.
-__device__ __forceinline__ int lap_pair_slot (int a, int b, int e, int PS)
-{
-    const int colour = (a ^ b) - 1;
-    return (2 * colour + ((a && b) ? 1 : 0)) * PS + 4 * colour + e;
-}
-__device__ __forceinline__ int lap_diag_slot (int a, int e, int PS) { return (6 + a) * PS + 4 * a + e; }
+// Laplacian: lap_pair_slot / lap_diag_slot (host/tile_plan.h) place the 10 dot products of an element;
+// the plan's codes already are those slots.
 
 template <int OPDIM, int MINB, int STRIDE>
 __global__ void __launch_bounds__(256, MINB)
@@ -188,7 +177,7 @@ tiled_assembly_kernel (const TiledArgs args)
             double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
             for (int k = begin + sub; k < end; k += 4) {
                 const int code = diagCodes[k];
-                if (OPDIM == 1) { a00 += cX[lap_diag_slot (code & 3, code >> 2, strideE - 4)]; continue; }
+                if (OPDIM == 1) { a00 += cX[code]; continue; }
                 const int v = (code & 3) * strideE + (code >> 2);
                 const double x = cX[v], y = cY[v], z = cZ[v];
                 a00 += x * x; a01 += x * y; a02 += x * z; a11 += y * y; a12 += y * z; a22 += z * z;
@@ -235,7 +224,7 @@ tiled_assembly_kernel (const TiledArgs args)
             for (int t = 0; t < tb.steps; t++) {
                 const int code = codes[t * 32];
                 const int e = code >> 4;
-                if (OPDIM == 1) { acc[0] += cX[lap_pair_slot ((code >> 2) & 3, code & 3, e, strideE - 4)]; continue; }
+                if (OPDIM == 1) { acc[0] += cX[code]; continue; }
                 const int va = ((code >> 2) & 3) * strideE + e, vb = (code & 3) * strideE + e;
                 const double ax = cX[va], ay = cY[va], az = cZ[va];
                 const double bx = cX[vb], by = cY[vb], bz = cZ[vb];
@@ -466,7 +455,7 @@ tiled_prefetch_kernel (const TiledArgs args)
             double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
             for (int q = begin + sub; q < end; q += 4) {
                 const int code = diagCodes[q];
-                if (OPDIM == 1) { a00 += cX[lap_diag_slot (code & 3, code >> 2, strideE - 4)]; continue; }
+                if (OPDIM == 1) { a00 += cX[code]; continue; }
                 const int v = (code & 3) * strideE + (code >> 2);
                 const double x = cX[v], y = cY[v], z = cZ[v];
                 a00 += x * x; a01 += x * y; a02 += x * z; a11 += y * y; a12 += y * z; a22 += z * z;
@@ -519,7 +508,7 @@ tiled_prefetch_kernel (const TiledArgs args)
             for (int t = 0; t < tb.steps; t++) {
                 const int code = codes[t * 32];
                 const int e = code >> 4;
-                if (OPDIM == 1) { acc[0] += cX[lap_pair_slot ((code >> 2) & 3, code & 3, e, strideE - 4)]; continue; }
+                if (OPDIM == 1) { acc[0] += cX[code]; continue; }
                 const int va = ((code >> 2) & 3) * strideE + e, vb = (code & 3) * strideE + e;
                 const double ax = cX[va], ay = cY[va], az = cZ[va];
                 const double bx = cX[vb], by = cY[vb], bz = cZ[vb];
@@ -740,9 +729,22 @@ tiled_pipeline_kernel (const TiledArgs args)
                 #pragma unroll
                 for (int i = 0; i < 4; i++) { p[3 * i] = S.sX[ids[i]]; p[3 * i + 1] = S.sY[ids[i]]; p[3 * i + 2] = S.sZ[ids[i]]; }
                 elem_coef (p, c);
-                #pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    S.cX[a * strideE + e] = c[3 * a]; S.cY[a * strideE + e] = c[3 * a + 1]; S.cZ[a * strideE + e] = c[3 * a + 2];
+                if (OPDIM == 1) {                         // the 10 dot products (assembly.cc:539-541)
+                    const int PS = strideE - 4;
+                    #pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        #pragma unroll
+                        for (int b = a; b < 4; b++) {
+                            const double dot = c[3 * a] * c[3 * b] + c[3 * a + 1] * c[3 * b + 1] + c[3 * a + 2] * c[3 * b + 2];
+                            S.cX[a == b ? lap_diag_slot (a, e, PS) : lap_pair_slot (a, b, e, PS)] = dot;
+                        }
+                    }
+                }
+                else {
+                    #pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        S.cX[a * strideE + e] = c[3 * a]; S.cY[a * strideE + e] = c[3 * a + 1]; S.cZ[a * strideE + e] = c[3 * a + 2];
+                    }
                 }
             }
             mbar_arrive (S.coefFull);
@@ -778,10 +780,10 @@ tiled_pipeline_kernel (const TiledArgs args)
                 double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
                 for (int q = begin + sub; q < end; q += 4) {
                     const int code = diagCodes[q];
+                    if (OPDIM == 1) { a00 += cX[code]; continue; }
                     const int v = (code & 3) * strideE + (code >> 2);
                     const double x = cX[v], y = cY[v], z = cZ[v];
-                    if (OPDIM == 1) { a00 += x * x + y * y + z * z; }
-                    else { a00 += x * x; a01 += x * y; a02 += x * z; a11 += y * y; a12 += y * z; a22 += z * z; }
+                    a00 += x * x; a01 += x * y; a02 += x * z; a11 += y * y; a12 += y * z; a22 += z * z;
                 }
                 #pragma unroll
                 for (int off = 1; off <= 2; off <<= 1) {
@@ -848,14 +850,12 @@ tiled_pipeline_kernel (const TiledArgs args)
                 #pragma unroll 2
                 for (int t = 0; t < tb.steps; t++) {
                     const int code = codes[t * 32];
+                    if (OPDIM == 1) { acc[0] += cX[code]; continue; }
                     const int e = code >> 4;
                     const int va = ((code >> 2) & 3) * strideE + e, vb = (code & 3) * strideE + e;
                     const double ax = cX[va], ay = cY[va], az = cZ[va];
                     const double bx = cX[vb], by = cY[vb], bz = cZ[vb];
-                    if (OPDIM == 1) {
-                        acc[0] += ax * bx + ay * by + az * bz;
-                    }
-                    else {
+                    {
                         acc[0] += ax * bx; acc[1] += ax * by; acc[2] += ax * bz;
                         acc[3] += ay * bx; acc[4] += ay * by; acc[5] += ay * bz;
                         acc[6] += az * bx; acc[7] += az * by; acc[8] += az * bz;

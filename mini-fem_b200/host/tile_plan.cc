@@ -183,6 +183,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
     // coset numbering's holes) and for the 16 all-zero slots the padding codes point at
     const int stride = tile_plan_stride (lim.maxElems);
     plan.elemStride = stride;
+    plan.laplacian = lim.laplacian;
 
     std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
     node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
@@ -502,6 +503,11 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                 }
                 s.paddedSteps += steps;
             }
+            if (lim.laplacian) {                 // codes -> shared-memory slots of the dot products
+                const int PS = stride - 4;
+                for (uint16_t &code : s.pairCodes) code = (uint16_t)lap_pair_slot ((code >> 2) & 3, code & 3, code >> 4, PS);
+                for (uint16_t &code : s.diagCodes) code = (uint16_t)lap_diag_slot (code & 3, code >> 2, PS);
+            }
             uint32_t bytes = (uint32_t)sizeof (TileBlobHeader) + (uint32_t)(s.rows.size () * sizeof (TileRow));
             bytes = align16 (bytes) + align16 ((uint32_t)(s.nodes.size () * 4));
             bytes += align16 ((uint32_t)(s.elemNodes.size () * 2));
@@ -645,7 +651,13 @@ int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *
                 error = "diagLocal is not the diagonal entry"; return -1;
             }
             for (int k = tr.diagCodeBase; k < rows[r + 1].diagCodeBase; k++) {
-                const int code = diagCodes[k], el = code >> 2, a = code & 3;
+                int code = diagCodes[k];
+                if (plan.laplacian) {                                // slot -> (element << 2 | a)
+                    const int PS = plan.elemStride - 4, a = code / PS - 6;
+                    if (a < 0 || a > 3) { error = "diagonal slot outside the diagonal planes"; return -1; }
+                    code = ((code - (6 + a) * PS - 4 * a) << 2) | a;
+                }
+                const int el = code >> 2, a = code & 3;
                 if (el >= h.nbElems || globalElem[el] < 0) { error = "diagonal code names a foreign element"; return -1; }
                 if (tileNodes[tileElems[(size_t)el * 4 + a]] != n) { error = "diagonal code: wrong local node"; return -1; }
                 if (tr.diagLocal == 0xFFFF) { error = "diagonal contribution on a row without diagonal entry"; return -1; }
@@ -668,7 +680,18 @@ int verify_tile_plan (const TilePlan &plan, int nbNodes, int nbElem, const int *
                     }
                 }
                 for (int s = 0; s < tb.steps; s++) {
-                    const int code = pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
+                    int code = pairCodes[(size_t)tb.codeBase + (size_t)s * 32 + lane];
+                    if (plan.laplacian) {                            // slot -> (element << 4 | a << 2 | b)
+                        static const int kPair[6][2] = {{0, 1}, {2, 3}, {0, 2}, {1, 3}, {0, 3}, {1, 2}};
+                        const int PS = plan.elemStride - 4, pl = code / PS;
+                        if (pl > 5) { error = "pair slot outside the pair planes"; return -1; }
+                        const int el = code - pl * PS - 4 * (pl / 2);
+                        int a = kPair[pl][0], b = kPair[pl][1];
+                        if (el >= h.nbElems) { a = 1; b = 0; }       // padding slots live in plane 0 = pair (1,0)
+                        else if (q != 0xFFFF && globalElem[el] >= 0 &&
+                                 tileNodes[tileElems[(size_t)el * 4 + a]] != (rows[entryRow[q]].node & 0x7fffffff)) std::swap (a, b);
+                        code = (el << 4) | (a << 2) | b;
+                    }
                     const int el = code >> 4, a = (code >> 2) & 3, bb = code & 3;
                     if (el >= h.nbElems) {                           // padding: one of the 16 zero slots
                         // local nodes must be (1, 0): the kernels zero exactly those slots (and the

@@ -65,6 +65,7 @@ struct TilePlan {
     int nbTiles = 0, maxRows = 0, maxElems = 0, maxNodesRef = 0, maxEntries = 0;
     int nbInterfaceTiles = 0;            // tiles owning >= 1 interface node come first
     int elemStride = 0;                  // shared-memory stride between the 4 local-node planes
+    bool laplacian = false;              // codes are shared-memory slots of dot products (see lap_pair_slot)
     int64_t nbTileElems = 0, nbContributions = 0, nbPaddedSteps = 0;
     uint32_t maxBlobBytes = 0;
     uint32_t maxHeadBytes = 0, maxTailBytes = 0;   // head = header..elements (bytes [0, offEntryRow)), tail = the rest
@@ -80,13 +81,33 @@ struct TilePlanLimits {
     int maxElems = 384;      // <= 4064 (12-bit element field, slack for numbering holes + padding slot)
     int maxNodesRef = 384;   // shared-memory coordinate staging
     int maxEntries = 2048;   // <= 65535
-    bool laplacian = false;  // scalar operator: the kernel keeps dot products, padding goes to bank c+12
+    bool laplacian = false;  // scalar operator: codes become dot-product slots, padding goes to bank c+12
     bool bankAware = true;   // coset numbering + conflict-aware step schedule (false: element order)
 };
 
 // Padding codes name an element id in [nbElems, nbElems + 16): the kernel keeps all-zero
 // coefficient vectors there, so padded steps need neither a branch nor a select.
 int tile_plan_stride (int maxElems);   // shared-memory stride between the 4 local-node planes
+
+// Laplacian tiles keep, per element, the 10 distinct dot products of its gradient rows instead
+// of the rows themselves (one shared-memory load per contribution instead of six), and their
+// codes ARE the shared-memory slots.  Plane of the pair (a,b), a != b: 2*colour + (a && b),
+// colour = (a ^ b) - 1 — the proper 3-edge-colouring of K4 ({01,23}, {02,13}, {03,12}), so the
+// three pairs of one local node get three different colours; plane of (a,a): 6 + a.  Plane p
+// starts at p*PS + 4*residue (PS = stride - 4, a multiple of 16; residue = colour, or a for the
+// diagonal planes): with the coset numbering an element of class c keeps its off-diagonal
+// dots in banks {c, c+4, c+8}.
+#ifdef __CUDACC__
+#define MFB_HD __host__ __device__ __forceinline__
+#else
+#define MFB_HD inline
+#endif
+MFB_HD int lap_pair_slot (int a, int b, int e, int PS)
+{
+    const int colour = (a ^ b) - 1;
+    return (2 * colour + ((a && b) ? 1 : 0)) * PS + 4 * colour + e;
+}
+MFB_HD int lap_diag_slot (int a, int e, int PS) { return (6 + a) * PS + 4 * a + e; }
 //
 // isInterface may be null.  Returns 0, or -1 with `error` set (e.g. one node alone
 // exceeds a cap, or the CSR lacks a pair).

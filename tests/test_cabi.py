@@ -60,13 +60,15 @@ def test_argument_validation_happens_before_cuda():
         mfb.Context(setup, path="color")
 
 
+@pytest.mark.parametrize("operatorID", [0, 1])
 @pytest.mark.parametrize("grid,rows,elems", [((6, 5, 4), 0, 0), ((6, 5, 4), 16, 200), ((9, 9, 9), 64, 704), ((3, 2, 2), 1, 64)])
-def test_tile_plan_selfcheck(grid, rows, elems):
-    """Host replay of the TILED plan against the reference's (element, j, k) loop."""
+def test_tile_plan_selfcheck(grid, rows, elems, operatorID):
+    """Host replay of the TILED plan against the reference's (element, j, k) loop (the Laplacian
+    plan stores shared-memory slots of dot products, the elasticity plan (element, a, b) codes)."""
     mesh = mfb.Mesh.generate(*grid, seed=4)
-    s = mfb.Setup(mesh, "ela")
+    s = mfb.Setup(mesh, "ela" if operatorID else "lap")
     keep = [np.ascontiguousarray(mesh.coord), s.elemToNode, s.row, s.col]
-    p = mfb.Problem(1, mesh.nbElem, mesh.nbNodes, s.nbEdges, *[k.ctypes.data for k in keep], None, None, None, 0,
+    p = mfb.Problem(operatorID, mesh.nbElem, mesh.nbNodes, s.nbEdges, *[k.ctypes.data for k in keep], None, None, None, 0,
                     1, 0, 0, 0, None, None, None)
     stats = (C.c_int64 * 6)()
     rc = mfb.lib.mfb_tile_plan_selfcheck(C.byref(p), rows, elems, stats)
