@@ -158,6 +158,22 @@ def run_reference_cpu(op, grid, nb_iter, ranks):
     return elements / seconds, n, kind, detail, elements, blocks
 
 
+def run_reference_coloring(op, grid, nb_iter):
+    """The reference's COLORING build (MPI + OpenMP, one rank, OMP_NUM_THREADS = host cores) as
+    shipped: the per-colour `#pragma omp parallel for` is commented out in the reference
+    (src/assembly.cc:362,516), so only the zero-fill and the preconditioner loops are threaded."""
+    import minifem_b200 as mfb
+    from oracle_lib import Reference, ref_available
+    if not ref_available("coloring"):
+        return None
+    mesh = mfb.Mesh.generate(*grid, seed=1)
+    setup = mfb.Setup(mesh, op, coloring=True)          # colours + permutation: bit-identical to coloring.cc (tested)
+    ref = Reference("coloring")
+    ref.set_colors(setup.colorToElem)
+    _, _, cycles, hz = ref.fem_loop([setup], nb_iter)
+    return mesh.nbElem / (sum(cycles) / hz), setup.nbTotalColors
+
+
 def reference_main(args, rank, world):
     if rank != 0:
         return
@@ -314,6 +330,12 @@ def main():
             line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": n, "kind": kind,
                                     "sample": f"whole {elements}-element mesh in {cb[0]}x{cb[1]}x{cb[2]} subdomains (one rank thread each), "
                                               f"2 timed iterations after 1 untimed; {detail}"}
+            col = run_reference_coloring(args.op, tuple(args.grid), 2)
+            if col:
+                line["cpu_baseline_coloring"] = {
+                    "value": col[0], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+                    "sample": f"whole mesh, one rank, OMP_NUM_THREADS = host cores, {col[1]} colours, 1 timed iteration after 1 untimed; "
+                              "oracle/_ref libminifem_ref_coloring.so as shipped (per-colour omp pragma disabled in the reference, assembly.cc:362)"}
         except Exception as e:                                   # the bench line must still appear
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
     print(json.dumps(line), flush=True)

@@ -100,6 +100,20 @@ int mref_coloring (int *elemToNode, int nbElem, int nbNodes, int *colorPermOut,
 #endif
 }
 
+// Installs colours computed elsewhere into the globals coloring_assembly reads (globals.h:43-44;
+// assembly.cc:593-611), for callers that permuted elemToNode themselves.  REF build: no-op.
+void mref_set_colors (const int *colorToElemIn, int nbColors)
+{
+#ifdef COLORING
+    delete[] colorToElem;
+    colorToElem = new int [nbColors + 1];
+    memcpy (colorToElem, colorToElemIn, sizeof (int) * (nbColors + 1));
+    nbTotalColors = nbColors;
+#else
+    (void)colorToElemIn; (void)nbColors;
+#endif
+}
+
 // main.cc:340-346.
 int mref_boundary_mask (int *boundNodesCode, int nbNodes, int nbBoundNodes,
                         int *checkBounds)

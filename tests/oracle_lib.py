@@ -185,6 +185,10 @@ class Reference:
         assert nb > 0, "mref_coloring needs a COLORING build"
         return e2n, perm[:nbElem], c2e[:nb + 1].copy(), nb
 
+    def set_colors(self, colorToElem):
+        c2e = _i32(colorToElem)
+        self.lib.mref_set_colors(_p(c2e), len(c2e) - 1)
+
     def boundary_mask(self, codes):
         codes = _i32(codes).copy()
         out = np.zeros(max(codes.size * 3, 1), np.int32)

@@ -69,3 +69,20 @@ def test_multi_rank_halo(oracle):
         for r, s in enumerate(setups):
             out = oracle.prec_inversion(precs[r], s.row, s.col, s.checkBounds, s.mesh.nbNodes, s.operatorID)
             assert np.array_equal(out, rp[r])
+
+
+def test_coloring_build_with_installed_colours(oracle):
+    """bench.py times the COLORING build with colours and permutation computed by this repository's
+    host code and installed through mref_set_colors: same result as the reference colouring itself."""
+    mesh = mfb.Mesh.generate(6, 5, 4, seed=8)
+    refc = Reference("coloring")
+    for op in ("lap", "ela"):
+        s = mfb.Setup(mesh, op, coloring=True)
+        refc.set_colors(s.colorToElem)
+        v1, p1, _, _ = refc.fem_loop([s], 2)
+        e2n, perm, c2e, nb = refc.coloring(mesh.elemToNode, mesh.nbNodes)       # the reference's own colouring
+        assert np.array_equal(e2n, s.elemToNode) and np.array_equal(c2e, s.colorToElem)
+        v2, p2, _, _ = refc.fem_loop([s], 2)
+        assert np.array_equal(v1[0], v2[0]) and np.array_equal(p1[0], p2[0])
+        want_v, _, want_p = oracle.fem_iteration(s)
+        assert np.array_equal(v1[0], want_v) and np.array_equal(p1[0], want_p)
