@@ -101,6 +101,24 @@ def test_unstructured_random(oracle, op, seed):
         ctx.close()
 
 
+@pytest.mark.parametrize("op", ["lap", "ela"])
+def test_arbitrary_input_numbering(oracle, op):
+    """The same mesh with random node and element numbering (what an unstructured mesh generator
+    hands over): the CSR layout follows the new ids, the tile plan only looks at coordinates."""
+    mesh = mfb.Mesh.generate(11, 9, 10, seed=9)
+    rng = np.random.default_rng(17)
+    nperm, eperm = rng.permutation(mesh.nbNodes), rng.permutation(mesh.nbElem)
+    coord = np.empty((mesh.nbNodes, 3)); coord[nperm] = mesh.coord.reshape(-1, 3)
+    codes = np.empty_like(mesh.boundNodesCode); codes[nperm] = mesh.boundNodesCode
+    e2n = (nperm[mesh.elemToNode.reshape(-1, 4) - 1] + 1)[eperm]
+    shuffled = ArrayMesh(coord.ravel(), e2n.ravel(), mesh.nbNodes, codes)
+    for path in PATHS:
+        setup = mfb.Setup(shuffled, op, coloring=(path == "color"))
+        ctx = mfb.Context(setup, path=path)
+        check_against_oracle(oracle, setup, ctx, fused=True)
+        ctx.close()
+
+
 @pytest.mark.parametrize("rows,elems,threads", [(1, 64, 32), (7, 120, 64), (32, 400, 128), (64, 640, 256), (128, 1200, 256)])
 def test_tile_shapes(oracle, rows, elems, threads):
     """Ragged tiles: one row per tile, tiles far below a warp batch, tiles near the caps."""

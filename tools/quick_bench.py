@@ -15,11 +15,20 @@ ap.add_argument("--tile-elems", type=int, default=0)
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--ctas", type=int, default=0)
 ap.add_argument("--no-bank-aware", action="store_true")
+ap.add_argument("--shuffle", action="store_true", help="random node and element numbering (unstructured-like input order)")
 a = ap.parse_args()
 
 t0 = time.time()
 mesh = mfb.Mesh.generate(*a.grid, seed=1)
 print(f"mesh {a.grid}: E={mesh.nbElem} N={mesh.nbNodes} Z={mesh.nbEdges}  ({time.time()-t0:.1f}s)", flush=True)
+if a.shuffle:
+    rng = np.random.default_rng(5)
+    nperm = rng.permutation(mesh.nbNodes)                  # old node -> new node
+    eperm = rng.permutation(mesh.nbElem)
+    coord = np.empty_like(mesh.coord.reshape(-1, 3)); coord[nperm] = mesh.coord.reshape(-1, 3)
+    codes = np.empty_like(mesh.boundNodesCode); codes[nperm] = mesh.boundNodesCode
+    e2n = (nperm[mesh.elemToNode.reshape(-1, 4) - 1] + 1)[eperm]
+    mesh.coord, mesh.boundNodesCode, mesh.elemToNode = coord.ravel(), codes, np.ascontiguousarray(e2n, np.int32).ravel()
 E, N, Z = mesh.nbElem, mesh.nbNodes, mesh.nbEdges
 alg = (16 * E + 76 * Z + 112 * N) if a.op == "ela" else (16 * E + 12 * Z + 36 * N)
 ref = None
