@@ -14,6 +14,8 @@
 //                       multithreaded-comm build reports (FEM.cc:179-180: everything under
 //                       "Matrix assembly")                     (default 0: four timed stages)
 //   MINIFEM_DEVICE      CUDA device ordinal                    (default LOCAL_RANK or 0)
+//   MINIFEM_STORE_CHECKINGS  1 = write the checkings file from this run's norms instead of
+//                       comparing with it (the role of store_ref_assembly_, src/IO.cc:42-58)
 //   RANK / WORLD_SIZE   MPI rank / size of the reference (one process per GPU);
 //   MINIFEM_RENDEZVOUS  directory shared by the ranks (NCCL id + timer reduction)
 #include <chrono>
@@ -224,9 +226,14 @@ void check_results (const double *prec, const double *values, int nbEdges, int n
     double refMatrixNorm, refPrecNorm;
     const string file = dataPath + "/" + meshName + "/checkings/" + operatorName + "_" + to_string (nbBlocks) +
                         "_" + to_string (rank);
-    if (mfb_checking_read (file.c_str (), &refMatrixNorm, &refPrecNorm) != MFB_OK) die (mfb_last_error ());
     const double matrixNorm = mfb_double_norm (values, (int64_t)nbEdges * operatorDim);
     const double precNorm = mfb_double_norm (prec, (int64_t)nbNodes * operatorDim);
+    if (env_int ("MINIFEM_STORE_CHECKINGS", 0)) {              // store_ref_assembly_, IO.cc:42-58
+        if (mfb_checking_write (file.c_str (), matrixNorm, precNorm) != MFB_OK) die (mfb_last_error ());
+        if (rank == 0) cout << "Stored reference checking: " << file << endl << endl;
+        return;
+    }
+    if (mfb_checking_read (file.c_str (), &refMatrixNorm, &refPrecNorm) != MFB_OK) die (mfb_last_error ());
     auto report = [&] (ostream &o, int r) {
         o << "Numerical stability of rank " << r << endl
           << "----------------------------------------------" << endl

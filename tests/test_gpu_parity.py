@@ -280,6 +280,15 @@ def test_driver_cli(tmp_path, oracle):
         report = open(tmp_path / "numerical_results_0").read()
         diffs = [float(l.split(":")[1]) for l in report.splitlines() if "difference" in l]
         assert len(diffs) == 2 and max(diffs) < 1e-13, report
+    # MINIFEM_STORE_CHECKINGS=1 writes the checkings file (store_ref_assembly_, IO.cc:42-58) ...
+    os.remove(os.path.join(data, "LM6", "checkings", "ela_1_0"))
+    env = dict(os.environ, MINIFEM_DATA_PATH=data, MINIFEM_STORE_CHECKINGS="1")
+    res = subprocess.run([exe, "LM6", "ela", "2"], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0 and "Stored reference checking" in res.stdout, res.stdout
+    # ... and the next run compares against it
+    env.pop("MINIFEM_STORE_CHECKINGS")
+    res = subprocess.run([exe, "LM6", "ela", "2"], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0 and "difference : 0.0e+00" in res.stdout, res.stdout
     res = subprocess.run([exe, "LM6", "foo", "4"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode != 0 and 'Incorrect argument "foo"' in res.stdout
     res = subprocess.run([exe, "EIB", "ela"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

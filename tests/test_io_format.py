@@ -84,3 +84,21 @@ def test_reference_driver_accepts_our_files(tmp_path, kind, op):
     # REF sums in element order like the oracle (difference exactly 0); COLORING sums colour
     # by colour, so its norm moves in the last bits
     assert all(d <= (0.0 if kind.startswith("ref") else 1e-14) for d in diffs), report
+
+
+def test_meshgen_cli(tmp_path):
+    """minifem_meshgen writes the per-rank input files of a block partition (both operators)."""
+    exe = os.path.join(ROOT, "mini-fem_b200", "minifem_meshgen")
+    data = str(tmp_path / "data")
+    res = subprocess.run([exe, data, "EIB", "6", "4", "5", "4", "3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    blocks = mfb.choose_blocks(6, 4, 5, 4)
+    for r in range(4):
+        want = mfb.Mesh.generate(6, 4, 5, blocks=blocks, rank=r, seed=3)
+        for op in ("lap", "ela"):
+            got = mfb.Mesh.read(os.path.join(data, "EIB", "inputs", f"{op}_4_{r}"))
+            for f in mfb.Mesh.FIELDS:
+                assert np.array_equal(getattr(got, f), getattr(want, f))
+    res = subprocess.run([exe, data, "EIB", "6", "4", "5", "7"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode != 0 and "cannot cut" in res.stdout
+    assert subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT).returncode != 0
