@@ -1,0 +1,20 @@
+"""Small all-paths run for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "mini-fem_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import minifem_b200 as mfb
+from helpers import row_scaled_error, block_scaled_error
+from oracle_lib import Oracle
+orc = Oracle()
+mesh = mfb.Mesh.generate(9, 8, 7, seed=3)
+for op in ("ela", "lap"):
+    for path, kw in (("tiled", {}), ("tiled", {"threads": 768}), ("atomic", {}), ("color", {})):
+        setup = mfb.Setup(mesh, op, coloring=(path == "color"))
+        want_v, _, want_p = orc.fem_iteration(setup)
+        ctx = mfb.Context(setup, path=path, **kw)
+        ctx.iteration(); ctx.stages(); ctx.iteration()
+        v, p = ctx.download()
+        print(op, path, kw, row_scaled_error(v, want_v, setup.row, setup.operatorDim), block_scaled_error(p, want_p, setup.operatorDim), flush=True)
+        ctx.close()
+print("SANITIZE_CASE_DONE")
