@@ -341,14 +341,13 @@ tiled_prefetch_kernel (const TiledArgs args)
     const int lane = tid & 31, warp = tid >> 5, nWarps = nThreads >> 5;
     const int strideE = STRIDE ? STRIDE : P.elemStride;
 
-    // shared memory: [head 0][head 1][tail][cX cY cZ][sDiag][coordinates][half-warp slabs][3 mbarriers]
+    // shared memory: [head 0][head 1][tail][cX cY cZ][coordinates][half-warp slabs][3 mbarriers]
     const unsigned headBytes = (P.maxHeadBytes + 127u) & ~127u, tailBytes = (P.maxTailBytes + 127u) & ~127u;
     unsigned char *sHead0 = smemRaw, *sTail = smemRaw + 2 * headBytes;
     double *cX = reinterpret_cast<double*> (sTail + tailBytes);
     double *cY = cX + 4 * strideE;
     double *cZ = cY + 4 * strideE;
-    double *sDiag = cZ + 4 * strideE;
-    double *sX = sDiag + P.maxRows * OPDIM, *sY = sX + P.maxNodesRef, *sZ = sY + P.maxNodesRef;
+    double *sX = cZ + 4 * strideE, *sY = sX + P.maxNodesRef, *sZ = sY + P.maxNodesRef;
     double *slabs = sZ + P.maxNodesRef;
     double *slab = slabs + warp * 144;
     uint64_t *bars = reinterpret_cast<uint64_t*> (slabs + (OPDIM == 9 ? nWarps * 144 : 0));
@@ -471,17 +470,51 @@ tiled_prefetch_kernel (const TiledArgs args)
                     a22 += __shfl_xor_sync (0xffffffffu, a22, off);
                 }
             }
-            if (live && sub == 0) {
-                if (OPDIM == 1) sDiag[r] = a00;
+            // every lane of the quad now holds the row's sums: the diagonal entry and the node's
+            // preconditioner block (prec_init + prec_inversion, src/preconditioner.cc:25-87,
+            // src/Fortran/elasclpr.f:19-53) leave from here, lane `sub` storing components
+            // sub, sub + 4 (and 8)
+            if (live) {
+                const TileRow tr = sRows[r];
+                const int node = tr.node & 0x7fffffff;
+                const bool isInterface = tr.node < 0, hasDiag = tr.diagLocal != 0xFFFF;
+                const size_t gd = (size_t)(tr.valueStart + ((int)tr.diagLocal - (int)tr.localStart));
+                if (OPDIM == 1) {
+                    if (sub == 0) {
+                        if (hasDiag) args.values[gd] = a00;
+                        if (args.fusePrec) args.prec[node] = isInterface ? a00 : 1.0 / a00;
+                    }
+                }
                 else {
-                    const double tr = a00 + a11 + a22;
-                    sDiag[r * 9 + 0] = 1.25 * a00 + tr; sDiag[r * 9 + 1] = 1.25 * a01; sDiag[r * 9 + 2] = 1.25 * a02;
-                    sDiag[r * 9 + 3] = 1.25 * a01; sDiag[r * 9 + 4] = 1.25 * a11 + tr; sDiag[r * 9 + 5] = 1.25 * a12;
-                    sDiag[r * 9 + 6] = 1.25 * a02; sDiag[r * 9 + 7] = 1.25 * a12; sDiag[r * 9 + 8] = 1.25 * a22 + tr;
+                    const double tr3 = a00 + a11 + a22;
+                    double b[9] = {1.25 * a00 + tr3, 1.25 * a01, 1.25 * a02, 1.25 * a01, 1.25 * a11 + tr3, 1.25 * a12,
+                                   1.25 * a02, 1.25 * a12, 1.25 * a22 + tr3};
+                    if (hasDiag) {
+                        double *dst = args.values + gd * 9;
+                        dst[sub] = sub == 0 ? b[0] : sub == 1 ? b[1] : sub == 2 ? b[2] : b[3];
+                        dst[sub + 4] = sub == 0 ? b[4] : sub == 1 ? b[5] : sub == 2 ? b[6] : b[7];
+                        if (sub == 0) dst[8] = b[8];
+                    }
+                    if (args.fusePrec) {
+                        if (!isInterface) {
+                            int mx = 0, my = 0, mz = 0;
+                            if (args.checkBounds) {
+                                mx = __ldg (args.checkBounds + node);
+                                my = __ldg (args.checkBounds + (size_t)args.nbNodes + node);
+                                mz = __ldg (args.checkBounds + 2 * (size_t)args.nbNodes + node);
+                            }
+                            mask_block (b, mx, my, mz);
+                            if (hasDiag) invert3_lu (b);
+                        }
+                        double *dst = args.prec + (size_t)node * 9;
+                        dst[sub] = sub == 0 ? b[0] : sub == 1 ? b[1] : sub == 2 ? b[2] : b[3];
+                        dst[sub + 4] = sub == 0 ? b[4] : sub == 1 ? b[5] : sub == 2 ? b[6] : b[7];
+                        if (sub == 0) dst[8] = b[8];
+                    }
                 }
             }
         }
-        __syncthreads ();      // sDiag complete
+        // no barrier: the off-diagonal pass reads nothing the diagonal pass wrote
 
         // ---- next tile's coordinates start travelling ---------------------------------------------
         if (hasNext) {
@@ -491,7 +524,7 @@ tiled_prefetch_kernel (const TiledArgs args)
 
         // ---- 4. off-diagonal blocks, one lane per CSR entry ----------------------------------------
         const int nbBatches = hdr.nbBatches;
-        for (int b = warp; b < nbBatches; b += nWarps) {
+        for (int b = nWarps - 1 - warp; b < nbBatches; b += nWarps) {   // the low warps ran the diagonal pass
             const TileBatch tb = batches[b];
             const int q = laneEntry[b * 32 + lane];
             const bool live = q != 0xFFFF;
@@ -518,7 +551,7 @@ tiled_prefetch_kernel (const TiledArgs args)
             }
 
             if (OPDIM == 1) {
-                if (live) args.values[g] = isDiag ? sDiag[r] : acc[0];
+                if (live && !isDiag) args.values[g] = acc[0];
             }
             else {
                 const double trA = acc[0] + acc[4 % OPDIM] + acc[8 % OPDIM];
@@ -526,11 +559,12 @@ tiled_prefetch_kernel (const TiledArgs args)
                 #pragma unroll
                 for (int i = 0; i < 9; i++) {
                     blk[i] = 1.25 * acc[i % OPDIM] + ((i == 0 || i == 4 || i == 8) ? trA : 0.0);
-                    if (isDiag) blk[i] = sDiag[r * 9 + i];
                 }
                 // each half-warp holds consecutive entries of one row: one contiguous run each,
-                // streamed out through a 144-double slab, half-warp after half-warp
+                // streamed out through a 144-double slab, half-warp after half-warp; the 9 slots of
+                // the row's diagonal entry (written by the diagonal pass) are stepped over
                 const unsigned liveMask = __ballot_sync (0xffffffffu, live);
+                const unsigned diagMask = __ballot_sync (0xffffffffu, isDiag);
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     if ((lane >> 4) == h) {
@@ -539,47 +573,19 @@ tiled_prefetch_kernel (const TiledArgs args)
                     }
                     __syncwarp ();
                     const int run = __popc ((liveMask >> (16 * h)) & 0xffffu) * 9;
+                    const unsigned dm = (diagMask >> (16 * h)) & 0xffffu;
+                    const int dlo = dm ? (__ffs (dm) - 1) * 9 : -16;
                     double *out = args.values + (size_t)__shfl_sync (0xffffffffu, g, 16 * h) * 9;
                     #pragma unroll
                     for (int i = 0; i < 5; i++) {
                         const int m = i * 32 + lane;
-                        if (m < run) out[m] = slab[m];
+                        if (m < run && (unsigned)(m - dlo) >= 9u) out[m] = slab[m];
                     }
                     __syncwarp ();
                 }
             }
         }
 
-        // ---- 5. fused preconditioner: one thread per owned row --------------------------------------
-        if (args.fusePrec) {
-            for (int r = nThreads - 1 - tid; r < nbRows; r += nThreads) {
-                const int nodeField = sRows[r].node;
-                const int node = nodeField & 0x7fffffff;
-                const bool isInterface = nodeField < 0;
-                if (OPDIM == 1) {
-                    const double d = sDiag[r];
-                    args.prec[node] = isInterface ? d : 1.0 / d;
-                }
-                else {
-                    double b[9];
-                    #pragma unroll
-                    for (int q = 0; q < 9; q++) b[q] = sDiag[r * 9 + q];
-                    if (!isInterface) {
-                        int mx = 0, my = 0, mz = 0;
-                        if (args.checkBounds) {
-                            mx = __ldg (args.checkBounds + node);
-                            my = __ldg (args.checkBounds + (size_t)args.nbNodes + node);
-                            mz = __ldg (args.checkBounds + 2 * (size_t)args.nbNodes + node);
-                        }
-                        mask_block (b, mx, my, mz);
-                        if (sRows[r].diagLocal != 0xFFFF) invert3_lu (b);
-                    }
-                    double *dst = args.prec + (size_t)node * 9;
-                    #pragma unroll
-                    for (int q = 0; q < 9; q++) dst[q] = b[q];
-                }
-            }
-        }
         offCur = offNext; offNext = offAfter;
         cp_async_wait_all ();  // next tile's coordinates are in
         __syncthreads ();      // every reader of this tile's records / coefficients is done
@@ -917,7 +923,7 @@ size_t tiled_prefetch_smem_bytes (int operatorID, const DeviceTilePlan &plan, in
 {
     const int opDim = operatorID == 0 ? 1 : 9;
     const size_t headBytes = ((size_t)plan.maxHeadBytes + 127) & ~(size_t)127, tailBytes = ((size_t)plan.maxTailBytes + 127) & ~(size_t)127;
-    const size_t doubles = 12 * (size_t)plan.elemStride + (size_t)plan.maxRows * opDim + 3 * (size_t)plan.maxNodesRef +
+    const size_t doubles = 12 * (size_t)plan.elemStride + 3 * (size_t)plan.maxNodesRef +
                            (opDim == 9 ? (size_t)(threads / 32) * 144 : 0);
     return 2 * headBytes + tailBytes + doubles * sizeof (double) + 3 * sizeof (uint64_t);
 }
