@@ -227,6 +227,27 @@ void mfb_host_free (void *ptr);
 
 int mfb_device_count (void);
 
+/* ------------------------------------------------------------------------------
+ * The layout builders on the GPU.  HOST pointers in and
+ * out, results bit-identical to the host builders above and therefore to the reference:
+ * create_nodeToNode matrix.cc:55-91 (columns in first-seen order), create_elemToEdge
+ * matrix.cc:25-52, coloring_creation coloring.cc:46-109 (greedy first-fit in element order,
+ * evaluated front by front) + the stable permutation of coloring.cc:107.
+ * ------------------------------------------------------------------------------ */
+
+/* nodeToNodeColumn may be NULL (count only).  *nbEdgesOut always receives the entry count;
+ * MFB_ERR_ARG if columnCapacity is smaller. */
+int mfb_device_create_nodeToNode (const int *elemToNode, int nbElem, int nbNodes,
+                                  int *nodeToNodeRow, int *nodeToNodeColumn,
+                                  int64_t columnCapacity, int *nbEdgesOut, int device);
+int mfb_device_create_elemToEdge (const int *nodeToNodeRow, const int *nodeToNodeColumn,
+                                  const int *elemToNode, int *elemToEdge, int nbElem,
+                                  int nbNodes, int device);
+/* colorPart[nbElem], colorToElem[129], colorPerm[nbElem] as mfb_coloring_creation. */
+int mfb_device_coloring_creation (const int *elemToNode, int nbElem, int nbNodes,
+                                  int *colorPart, int *colorToElem, int *colorPerm,
+                                  int *nbTotalColors, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -924,3 +924,119 @@ extern "C" int mfb_host_alloc (void **ptr, int64_t bytes)
 }
 
 extern "C" void mfb_host_free (void *ptr) { if (ptr) cudaFreeHost (ptr); }
+
+// ------------------------------------------------------------- layout builders on the GPU
+
+namespace {
+
+struct DevArray {
+    void *p = nullptr;
+    ~DevArray () { if (p) cudaFree (p); }
+    template <class T> T *as () { return static_cast<T*> (p); }
+};
+
+int upload_ints (DevArray &dst, const int *src, size_t count)
+{
+    MFB_CUDA (cudaMalloc (&dst.p, sizeof (int) * std::max<size_t> (count, 1)));
+    if (count) MFB_CUDA (cudaMemcpy (dst.p, src, sizeof (int) * count, cudaMemcpyHostToDevice));
+    return MFB_OK;
+}
+
+// elemToNode on the device plus its node -> element lists
+struct DeviceIncidence {
+    DevArray elemToNode, index, value;
+    int build (const char *who, const int *hostElemToNode, int nbElem, int nbNodes, int device)
+    {
+        if (mfb_device_count () <= device || device < 0) return fail (MFB_ERR_CUDA, std::string (who) + ": no such CUDA device");
+        MFB_CUDA (cudaSetDevice (device));
+        int rc = upload_ints (elemToNode, hostElemToNode, (size_t)nbElem * 4);
+        if (rc != MFB_OK) return rc;
+        MFB_CUDA (cudaMalloc (&index.p, sizeof (int) * ((size_t)nbNodes + 1)));
+        MFB_CUDA (cudaMalloc (&value.p, sizeof (int) * std::max<size_t> ((size_t)nbElem * 4, 1)));
+        int badIds = 0;
+        MFB_CUDA (device_node_to_elem (elemToNode.as<int> (), nbElem, nbNodes, index.as<int> (), value.as<int> (), &badIds, 0));
+        if (badIds) return fail (MFB_ERR_ARG, std::string (who) + ": elemToNode holds ids outside [1, nbNodes]");
+        return MFB_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" int mfb_device_create_nodeToNode (const int *elemToNode, int nbElem, int nbNodes,
+                                             int *nodeToNodeRow, int *nodeToNodeColumn,
+                                             int64_t columnCapacity, int *nbEdgesOut, int device)
+{
+    if ((!elemToNode && nbElem > 0) || !nodeToNodeRow || !nbEdgesOut || nbElem < 0 || nbNodes < 0) {
+        return fail (MFB_ERR_ARG, "mfb_device_create_nodeToNode: bad argument");
+    }
+    DeviceIncidence inc;
+    int rc = inc.build ("mfb_device_create_nodeToNode", elemToNode, nbElem, nbNodes, device);
+    if (rc != MFB_OK) return rc;
+    DevArray row, col;
+    MFB_CUDA (cudaMalloc (&row.p, sizeof (int) * ((size_t)nbNodes + 1)));
+    int *dCol = nullptr;
+    int64_t total = 0;
+    MFB_CUDA (device_build_csr (inc.elemToNode.as<int> (), inc.index.as<int> (), inc.value.as<int> (), nbElem, nbNodes,
+                                row.as<int> (), &dCol, &total, 0));
+    col.p = dCol;
+    *nbEdgesOut = (int)total;
+    MFB_CUDA (cudaMemcpy (nodeToNodeRow, row.p, sizeof (int) * ((size_t)nbNodes + 1), cudaMemcpyDeviceToHost));
+    if (!nodeToNodeColumn) return MFB_OK;
+    if (columnCapacity < total) return fail (MFB_ERR_ARG, "mfb_device_create_nodeToNode: nodeToNodeColumn is too small");
+    if (total) MFB_CUDA (cudaMemcpy (nodeToNodeColumn, col.p, sizeof (int) * (size_t)total, cudaMemcpyDeviceToHost));
+    return MFB_OK;
+}
+
+extern "C" int mfb_device_create_elemToEdge (const int *nodeToNodeRow, const int *nodeToNodeColumn,
+                                             const int *elemToNode, int *elemToEdge, int nbElem,
+                                             int nbNodes, int device)
+{
+    if (!nodeToNodeRow || !nodeToNodeColumn || !elemToNode || !elemToEdge || nbElem < 0 || nbNodes < 0) {
+        return fail (MFB_ERR_ARG, "mfb_device_create_elemToEdge: bad argument");
+    }
+    if (mfb_device_count () <= device || device < 0) return fail (MFB_ERR_CUDA, "mfb_device_create_elemToEdge: no such CUDA device");
+    MFB_CUDA (cudaSetDevice (device));
+    for (int64_t k = 0; k < (int64_t)nbElem * 4; k++) {
+        if (elemToNode[k] < 1 || elemToNode[k] > nbNodes) return fail (MFB_ERR_ARG, "mfb_device_create_elemToEdge: elemToNode holds ids outside [1, nbNodes]");
+    }
+    DevArray row, col, conn, out, missing;
+    int rc;
+    if ((rc = upload_ints (row, nodeToNodeRow, (size_t)nbNodes + 1)) != MFB_OK) return rc;
+    if ((rc = upload_ints (col, nodeToNodeColumn, (size_t)nodeToNodeRow[nbNodes])) != MFB_OK) return rc;
+    if ((rc = upload_ints (conn, elemToNode, (size_t)nbElem * 4)) != MFB_OK) return rc;
+    MFB_CUDA (cudaMalloc (&out.p, sizeof (int) * std::max<size_t> ((size_t)nbElem * 16, 1)));
+    MFB_CUDA (cudaMalloc (&missing.p, sizeof (int)));
+    MFB_CUDA (cudaMemset (missing.p, 0, sizeof (int)));
+    if (nbElem > 0) MFB_CUDA (launch_elem_to_edge (row.as<int> (), col.as<int> (), conn.as<int> (), out.as<int> (), nbElem, missing.as<int> (), 0));
+    int nbMissing = 0;
+    MFB_CUDA (cudaMemcpy (&nbMissing, missing.p, sizeof (int), cudaMemcpyDeviceToHost));
+    if (nbElem > 0) MFB_CUDA (cudaMemcpy (elemToEdge, out.p, sizeof (int) * (size_t)nbElem * 16, cudaMemcpyDeviceToHost));
+    if (nbMissing) return fail (MFB_ERR_ARG, "mfb_device_create_elemToEdge: a node pair is missing from the CSR");
+    return MFB_OK;
+}
+
+extern "C" int mfb_device_coloring_creation (const int *elemToNode, int nbElem, int nbNodes,
+                                             int *colorPart, int *colorToElem, int *colorPerm,
+                                             int *nbTotalColors, int device)
+{
+    if (!elemToNode || !colorPart || !colorToElem || !colorPerm || !nbTotalColors || nbElem < 0 || nbNodes < 0) {
+        return fail (MFB_ERR_ARG, "mfb_device_coloring_creation: bad argument");
+    }
+    DeviceIncidence inc;
+    int rc = inc.build ("mfb_device_coloring_creation", elemToNode, nbElem, nbNodes, device);
+    if (rc != MFB_OK) return rc;
+    DevArray part, perm;
+    MFB_CUDA (cudaMalloc (&part.p, sizeof (int) * std::max<size_t> (nbElem, 1)));
+    MFB_CUDA (cudaMalloc (&perm.p, sizeof (int) * std::max<size_t> (nbElem, 1)));
+    int colors = 0;
+    MFB_CUDA (device_color_elements (inc.elemToNode.as<int> (), inc.index.as<int> (), inc.value.as<int> (), nbElem, nbNodes,
+                                     part.as<int> (), perm.as<int> (), colorToElem, &colors, 0));
+    if (colors == -1) return fail (MFB_ERR_COLORS, "Error: Not enough colors.");
+    if (colors < 0) return fail (MFB_ERR_ARG, "mfb_device_coloring_creation: an element names the same node twice");
+    if (nbElem > 0) {
+        MFB_CUDA (cudaMemcpy (colorPart, part.p, sizeof (int) * (size_t)nbElem, cudaMemcpyDeviceToHost));
+        MFB_CUDA (cudaMemcpy (colorPerm, perm.p, sizeof (int) * (size_t)nbElem, cudaMemcpyDeviceToHost));
+    }
+    *nbTotalColors = colors;
+    return MFB_OK;
+}

@@ -31,6 +31,19 @@ cudaError_t launch_halo_add (double *prec, const double *recvBuf, const int *uni
                              const int *slotIndex, const int *slots, int dim, int nbUniq,
                              cudaStream_t stream);
 
+// GPU layout builders (kernels_topology.cu); every pointer is a device pointer unless noted.
+// *badIds = node ids outside [1, nbNodes] (nothing else is written then).
+cudaError_t device_node_to_elem (const int *dElemToNode, int nbElem, int nbNodes, int *dIndex, int *dValue,
+                                 int *badIds, cudaStream_t stream);
+// dRow holds nbNodes+1 ints; *dColOut is cudaMalloc'ed here (the count is not known before).
+cudaError_t device_build_csr (const int *dElemToNode, const int *dIndex, const int *dValue, int nbElem,
+                              int nbNodes, int *dRow, int **dColOut, int64_t *nbEdges, cudaStream_t stream);
+// colorToElem: HOST array of 129 ints.  *nbColors = -1: more than 128 colours; -2: an element
+// names a node twice.
+cudaError_t device_color_elements (const int *dElemToNode, const int *dIndex, const int *dValue, int nbElem,
+                                   int nbNodes, int *dColorPart, int *dColorPerm, int *colorToElem,
+                                   int *nbColors, cudaStream_t stream);
+
 // Device copy of a TilePlan (host/tile_plan.h): one blob per tile.
 struct DeviceTilePlan {
     const uint8_t *blob = nullptr;

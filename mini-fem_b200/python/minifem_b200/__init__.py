@@ -99,6 +99,11 @@ lib.mfb_checking_write.argtypes = [C.c_char_p, C.c_double, C.c_double]
 lib.mfb_checking_read.argtypes = [C.c_char_p, _f64p, _f64p]
 lib.mfb_choose_blocks.argtypes = [C.c_int] * 4 + [_i32p] * 3
 lib.mfb_choose_blocks.restype = None
+lib.mfb_device_create_nodeToNode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                             _i32p, C.c_int]
+lib.mfb_device_create_elemToEdge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+lib.mfb_device_coloring_creation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             _i32p, C.c_int]
 
 # Every symbol include/minifem_b200.h declares (tests check that the library exports them).
 DECLARED_SYMBOLS = [
@@ -115,6 +120,7 @@ DECLARED_SYMBOLS = [
     "mfb_ctx_halo_add_host", "mfb_ctx_assembly_fused", "mfb_ctx_prec_inversion_interface", "mfb_ctx_run_timed",
     "mfb_tile_plan_selfcheck", "mfb_host_alloc",
     "mfb_host_free", "mfb_device_count",
+    "mfb_device_create_nodeToNode", "mfb_device_create_elemToEdge", "mfb_device_coloring_creation",
 ]
 
 
@@ -182,6 +188,43 @@ def coloring_creation(elemToNode, nbNodes):
     nb = C.c_int(0)
     _check(lib.mfb_coloring_creation(_ptr(e2n), nbElem, nbNodes, _ptr(part), _ptr(c2e), _ptr(perm),
                                      C.byref(nb)), "mfb_coloring_creation")
+    return part[:nbElem], c2e[:nb.value + 1].copy(), perm[:nbElem], nb.value
+
+
+# ---------------------------------------------------------------- the same builders on the GPU
+
+def device_create_nodeToNode(elemToNode, nbNodes, device=0):
+    """create_nodeToNode (matrix.cc:55-91) built on the GPU; bit-identical to create_nodeToNode()."""
+    e2n = _i32(elemToNode).ravel()
+    nbElem = e2n.size // 4
+    row = np.zeros(nbNodes + 1, np.int32)
+    col = np.zeros(max(nbElem * 12 + nbNodes, 1), np.int32)       # upper bound of the entry count
+    out = C.c_int(0)
+    _check(lib.mfb_device_create_nodeToNode(_ptr(e2n), nbElem, nbNodes, _ptr(row), _ptr(col), col.size,
+                                            C.byref(out), device), "mfb_device_create_nodeToNode")
+    return row, col[:out.value].copy()
+
+
+def device_create_elemToEdge(row, col, elemToNode, device=0):
+    e2n = _i32(elemToNode).ravel()
+    nbElem = e2n.size // 4
+    row = _i32(row)
+    out = np.zeros(max(nbElem * 16, 1), np.int32)
+    _check(lib.mfb_device_create_elemToEdge(_ptr(row), _ptr(_i32(col)), _ptr(e2n), _ptr(out), nbElem,
+                                            row.size - 1, device), "mfb_device_create_elemToEdge")
+    return out[:nbElem * 16]
+
+
+def device_coloring_creation(elemToNode, nbNodes, device=0):
+    """coloring_creation (coloring.cc:84-109) evaluated front by front on the GPU; same colours."""
+    e2n = _i32(elemToNode).ravel()
+    nbElem = e2n.size // 4
+    part = np.zeros(max(nbElem, 1), np.int32)
+    c2e = np.zeros(129, np.int32)
+    perm = np.zeros(max(nbElem, 1), np.int32)
+    nb = C.c_int(0)
+    _check(lib.mfb_device_coloring_creation(_ptr(e2n), nbElem, nbNodes, _ptr(part), _ptr(c2e), _ptr(perm),
+                                            C.byref(nb), device), "mfb_device_coloring_creation")
     return part[:nbElem], c2e[:nb.value + 1].copy(), perm[:nbElem], nb.value
 
 
@@ -262,18 +305,28 @@ class Setup:
     """What main.cc builds between read_input_data and FEM_loop (main.cc:209-351):
     optional colouring + permutation, CSR, optional elemToEdge, Dirichlet mask."""
 
-    def __init__(self, mesh, operator="ela", coloring=False, elem_to_edge=False):
+    def __init__(self, mesh, operator="ela", coloring=False, elem_to_edge=False, builder="host", device=0):
         self.mesh = mesh
         self.operatorID = {"lap": 0, "ela": 1}[operator]
         self.operatorDim = 1 if self.operatorID == 0 else 9
         self.elemToNode = mesh.elemToNode.copy()
         self.colorToElem, self.nbTotalColors, self.colorPerm = None, 0, None
+        if builder not in ("host", "gpu"):
+            raise ValueError("builder must be 'host' or 'gpu'")
+        gpu = builder == "gpu"           # same layouts, built by the kernels of csrc/kernels_topology.cu
         if coloring:
-            _, self.colorToElem, self.colorPerm, self.nbTotalColors = coloring_creation(self.elemToNode, mesh.nbNodes)
+            color = (lambda e, n: device_coloring_creation(e, n, device)) if gpu else coloring_creation
+            _, self.colorToElem, self.colorPerm, self.nbTotalColors = color(self.elemToNode, mesh.nbNodes)
             self.elemToNode = permute_int_2d(self.elemToNode, self.colorPerm, 4)
-        self.row, self.col = create_nodeToNode(self.elemToNode, mesh.nbNodes)
+        if gpu:
+            self.row, self.col = device_create_nodeToNode(self.elemToNode, mesh.nbNodes, device)
+        else:
+            self.row, self.col = create_nodeToNode(self.elemToNode, mesh.nbNodes)
         self.nbEdges = int(self.row[-1])
-        self.elemToEdge = create_elemToEdge(self.row, self.col, self.elemToNode) if elem_to_edge else None
+        self.elemToEdge = None
+        if elem_to_edge:
+            self.elemToEdge = (device_create_elemToEdge(self.row, self.col, self.elemToNode, device) if gpu
+                               else create_elemToEdge(self.row, self.col, self.elemToNode))
         self.checkBounds, _ = boundary_mask(mesh.boundNodesCode)
 
 
