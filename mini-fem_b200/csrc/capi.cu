@@ -276,6 +276,8 @@ struct mfb_ctx {
     size_t tiledSmem = 0;
     int tiledCtas = 1;
     bool tiledPrefetch = false;
+    int haloCoresident = 0;         // multi-GPU overlap scheme, see do_iteration
+    int interiorTilesPerCta = 4;   // measured at N=2: 1 -> 0.71 ms, 4 -> 0.645, 8 -> 0.647 (kernel alone 0.636 in that build)
     int64_t meshBytes = 0, planBytes = 0, launches = 0, graphLaunches = 0;
 
     NcclComm comm = nullptr;
@@ -332,6 +334,8 @@ int build_device_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options *o)
     // kernel variant: 0 / default = prefetching kernel, MFB_TILED_VARIANT=plain selects the simpler one
     const char *variant = getenv ("MFB_TILED_VARIANT");
     c->tiledPrefetch = !pipelined && c->threads == 256 && !(variant && std::string (variant) == "plain");
+    if (const char *v = getenv ("MFB_HALO_OVERLAP")) c->haloCoresident = std::string (v) == "coresident";
+    if (const char *v = getenv ("MFB_INTERIOR_TILES_PER_CTA")) c->interiorTilesPerCta = std::max (atoi (v), 1);
     c->tiledSmem = pipelined ? tiled_pipeline_smem_bytes (c->operatorID, c->plan)
                  : c->tiledPrefetch ? tiled_prefetch_smem_bytes (c->operatorID, c->plan, c->threads)
                                     : tiled_smem_bytes (c->operatorID, c->plan, c->threads);
@@ -438,20 +442,39 @@ int do_iteration (mfb_ctx *c)
     const bool exchange = c->nbBlocks > 1 && c->nbIntf > 0;
     if (!exchange) return do_assembly (c, 1);
     if (!c->comm) return fail (MFB_ERR_STATE, "mfb_ctx_iteration: call mfb_ctx_comm_init first (nbBlocks > 1)");
-    // Two co-resident kernels.  The high-priority stream takes the tiles that own interface
-    // nodes on a small persistent grid, then packs their raw diagonal blocks, exchanges them
-    // (NCCL), adds and inverts; the main stream assembles the interior tiles on the rest of the
-    // device.  The two kernels write disjoint rows; the streams join at the end.
-    const int nIntfTiles = c->plan.nbInterfaceTiles;
-    const int intfCtas = std::max (c->tiledCtas / 16, 1), interiorCtas = std::max (c->tiledCtas - intfCtas, 1);
-    MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));                 // everything queued so far
-    MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
-    MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, intfCtas, c->threads, c->tiledSmem, c->dCoord,
-                            c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->commStream, c->tiledPrefetch));
-    if (nIntfTiles > 0) c->launches++;
-    MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, c->plan.nbTiles - nIntfTiles, interiorCtas, c->threads,
-                            c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
-    if (c->plan.nbTiles - nIntfTiles > 0) c->launches++;
+    const int nIntfTiles = c->plan.nbInterfaceTiles, nInterior = c->plan.nbTiles - nIntfTiles;
+    if (c->haloCoresident) {
+        // MFB_HALO_OVERLAP=coresident: two co-resident kernels.  The high-priority stream takes the
+        // tiles that own interface nodes on a small persistent grid, the main stream the interior
+        // tiles on the rest of the device.  Fastest with one neighbour (N=2: 0.59 ms per EIB block);
+        // with 7 neighbours NCCL's kernel needs more room than the interface CTAs leave and waits
+        // for the interior kernel to end (N=8: 0.96 ms) — not the default.
+        const int intfCtas = std::max (c->tiledCtas / 16, 1), interiorCtas = std::max (c->tiledCtas - intfCtas, 1);
+        MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));                 // everything queued so far
+        MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
+        MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, intfCtas, c->threads, c->tiledSmem, c->dCoord,
+                                c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->commStream, c->tiledPrefetch));
+        if (nIntfTiles > 0) c->launches++;
+        MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, nInterior, interiorCtas, c->threads,
+                                c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
+        if (nInterior > 0) c->launches++;
+    }
+    else {
+        // Default: the tiles that own interface nodes come first, on the whole device; their raw
+        // diagonal blocks then travel on the high-priority stream (pack, NCCL, add, invert) while
+        // the interior tiles assemble.  The interior launch is NOT one persistent grid: its CTAs
+        // take a few tiles each, so SM resources free up continuously and the halo kernels are
+        // scheduled as soon as their inputs are ready, however many CTAs NCCL asks for.
+        MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, c->tiledCtas, c->threads, c->tiledSmem, c->dCoord,
+                                c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
+        if (nIntfTiles > 0) c->launches++;
+        MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));
+        const int interiorCtas = std::max ((nInterior + c->interiorTilesPerCta - 1) / c->interiorTilesPerCta, 1);
+        MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, nInterior, interiorCtas, c->threads,
+                                c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
+        if (nInterior > 0) c->launches++;
+        MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
+    }
     if ((rc = do_halo (c, c->commStream))) return rc;
     MFB_CUDA (launch_prec_inversion_list (c->operatorID, c->dPrec, c->dDiagIndex, c->dCheckBounds, c->nbNodes,
                                           c->dUniqNodes, c->nbUniqIntf, c->commStream));
