@@ -258,7 +258,7 @@ def main():
     value = total_elements / (ms_step * 1e-3)
 
     # end to end through the host-buffer entry point: H2D coord, iteration, D2H values + prec
-    e2e = None
+    e2e, e2e_resident = None, None
     if args.e2e_steps > 0:
         pins = [mfb.PinnedArray(N * 3), mfb.PinnedArray(ctx.nbValues), mfb.PinnedArray(ctx.nbPrec)]
         pins[0].array[:] = mesh.coord
@@ -274,6 +274,21 @@ def main():
                "d2h_bytes_per_step": int(pins[1].bytes + pins[2].bytes), "ms_per_step": 1e3 * e2e_s,
                "steps": args.e2e_steps, "note": "per GPU: pinned coord -> device, fused iteration, values + prec -> pinned host",
                "prec_checksum": checksum}
+        # The same step for a caller that keeps the matrix on the device (a solver on the GPU): coord
+        # H2D, fused iteration, the two norms check_results looks at reduced on the device, 16 bytes
+        # D2H.  Reported beside `e2e`, not instead of it.
+        ctx.iteration_norms_host(pins[0].ptr)
+        mdist.barrier(); torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            norms = ctx.iteration_norms_host(pins[0].ptr)
+        torch.cuda.synchronize(); mdist.barrier()
+        res_s = mdist.max_over_ranks((time.perf_counter() - t1) / args.e2e_steps)
+        e2e_resident = {"value": total_elements / res_s, "unit": UNIT, "h2d_bytes_per_step": int(pins[0].bytes),
+                        "d2h_bytes_per_step": 16, "ms_per_step": 1e3 * res_s, "steps": args.e2e_steps,
+                        "note": "per GPU: pinned coord -> device, fused iteration, matrix and prec norms reduced on the "
+                                "device (mfb_ctx_iteration_norms_host); the matrix stays in HBM",
+                        "norms": [float(norms[0]), float(norms[1])]}
         for p in pins:
             p.free()
     if sampler and sampler.ok:
@@ -321,7 +336,7 @@ def main():
                          "traffic": load_traffic(f"{args.op}_{args.path}_{args.grid[0]}"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg,
                          "note": "one fused kernel launch per step at N=1; duration = CUDA events over the timed region / steps"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
+            "e2e": e2e, "e2e_device_resident": e2e_resident, "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
             "other_paths": other}
     if world == 1 and not args.no_cpu_baseline:
         cores = args.cpu_ranks or (os.cpu_count() or 1)

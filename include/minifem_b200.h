@@ -175,6 +175,14 @@ int mfb_ctx_upload_coord (mfb_ctx *ctx, const double *coord);
 int mfb_ctx_iteration_host (mfb_ctx *ctx, const double *coord, double *nodeToNodeValue,
                             double *prec);
 
+/* check_results' two norms (FEM.cc:68-76: compute_double_norm of nodeToNodeValue and of prec)
+ * computed on the device; only 16 bytes travel.  The summation order differs from the
+ * reference's serial loop (relative difference ~1e-15). */
+int mfb_ctx_norms (mfb_ctx *ctx, double *matrixNorm, double *precNorm);
+/* Device-resident step for callers that consume the matrix on the GPU: upload coord, run one
+ * iteration, return the two norms.  norms[0] = matrix, norms[1] = prec. */
+int mfb_ctx_iteration_norms_host (mfb_ctx *ctx, const double *coord, double norms[2]);
+
 /* Device pointers of the results (for callers that keep working on the GPU). */
 int mfb_ctx_device_ptrs (mfb_ctx *ctx, void **values, void **prec);
 /* The stream the stages are launched on (cudaStream_t as void*). */

@@ -276,6 +276,7 @@ struct mfb_ctx {
     size_t tiledSmem = 0;
     int tiledCtas = 1;
     bool tiledPrefetch = false;
+    double *dNorm = nullptr;        // [partials][2 results], allocated by the first mfb_ctx_norms
     int haloCoresident = 0;         // multi-GPU overlap scheme, see do_iteration
     int interiorTilesPerCta = 4;   // measured at N=2: 1 -> 0.71 ms, 4 -> 0.645, 8 -> 0.647 (kernel alone 0.636 in that build)
     int64_t meshBytes = 0, planBytes = 0, launches = 0, graphLaunches = 0;
@@ -503,7 +504,7 @@ extern "C" void mfb_ctx_destroy (mfb_ctx *c)
     if (c->graphExec) cudaGraphExecDestroy (c->graphExec);
     void *ptrs[] = {c->dCoord, c->dValues, c->dPrec, c->dSend, c->dRecv, c->dElemToNode, c->dRow, c->dCol,
                     c->dElemToEdge, c->dCheckBounds, c->dDiagIndex, c->dIntfNodes, c->dUniqNodes,
-                    c->dSlotIndex, c->dSlots};
+                    c->dSlotIndex, c->dSlots, c->dNorm};
     for (void *p : ptrs) if (p) cudaFree (p);
     for (void *p : c->planAllocs) if (p) cudaFree (p);
     for (int s = 0; s < 5; s++) {
@@ -769,6 +770,33 @@ extern "C" int mfb_ctx_iteration_host (mfb_ctx *c, const double *coord, double *
     int rc = mfb_ctx_upload_coord (c, coord);
     if (!rc) rc = mfb_ctx_iteration (c);
     if (!rc) rc = mfb_ctx_download (c, nodeToNodeValue, prec);
+    return rc;
+}
+
+// check_results' two norms (FEM.cc:68-76) without moving the arrays to the host.
+extern "C" int mfb_ctx_norms (mfb_ctx *c, double *matrixNorm, double *precNorm)
+{
+    CTX_ENTER (c);
+    if (!matrixNorm || !precNorm) return fail (MFB_ERR_ARG, "mfb_ctx_norms: NULL");
+    const int scratch = double_norm_scratch_doubles ();
+    if (!c->dNorm) MFB_CUDA (cudaMalloc (&c->dNorm, sizeof (double) * (size_t)(scratch + 2)));
+    MFB_CUDA (launch_double_norm (c->dValues, (int64_t)c->nbEdges * c->operatorDim, c->dNorm, c->dNorm + scratch, c->stream));
+    MFB_CUDA (launch_double_norm (c->dPrec, (int64_t)c->nbNodes * c->operatorDim, c->dNorm, c->dNorm + scratch + 1, c->stream));
+    c->launches += 4;
+    double host[2];
+    MFB_CUDA (cudaMemcpyAsync (host, c->dNorm + scratch, sizeof (host), cudaMemcpyDeviceToHost, c->stream));
+    MFB_CUDA (cudaStreamSynchronize (c->stream));
+    *matrixNorm = host[0];
+    *precNorm = host[1];
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_iteration_norms_host (mfb_ctx *c, const double *coord, double norms[2])
+{
+    if (!norms) return fail (MFB_ERR_ARG, "mfb_ctx_iteration_norms_host: NULL");
+    int rc = mfb_ctx_upload_coord (c, coord);
+    if (!rc) rc = mfb_ctx_iteration (c);
+    if (!rc) rc = mfb_ctx_norms (c, &norms[0], &norms[1]);
     return rc;
 }
 

@@ -31,6 +31,10 @@ cudaError_t launch_halo_add (double *prec, const double *recvBuf, const int *uni
                              const int *slotIndex, const int *slots, int dim, int nbUniq,
                              cudaStream_t stream);
 
+// compute_double_norm (FEM.cc:48-56) of a device array; `partials` holds double_norm_scratch_doubles().
+int double_norm_scratch_doubles ();
+cudaError_t launch_double_norm (const double *x, int64_t n, double *partials, double *out, cudaStream_t stream);
+
 // GPU layout builders (kernels_topology.cu); every pointer is a device pointer unless noted.
 // *badIds = node ids outside [1, nbNodes] (nothing else is written then).
 cudaError_t device_node_to_elem (const int *dElemToNode, int nbElem, int nbNodes, int *dIndex, int *dValue,

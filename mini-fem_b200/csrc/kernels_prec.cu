@@ -173,4 +173,50 @@ cudaError_t launch_halo_add (double *prec, const double *recvBuf, const int *uni
     return cudaGetLastError ();
 }
 
+// compute_double_norm (src/FEM.cc:48-56) on the device: sqrt of the sum of squares, summed in
+// two levels whose order depends only on the (fixed) launch shape, so the result is
+// reproducible run to run.
+namespace {
+constexpr int kNormBlocks = 592, kNormThreads = 256;
+
+__global__ void __launch_bounds__(kNormThreads)
+sum_squares_kernel (const double *__restrict__ x, int64_t n, double *partials)
+{
+    __shared__ double warpSums[kNormThreads / 32];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kNormThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kNormThreads) {
+        const double v = x[i];
+        acc += v * v;
+    }
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync (0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = acc;
+    __syncthreads ();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int w = 0; w < kNormThreads / 32; w++) total += warpSums[w];
+        partials[blockIdx.x] = total;
+    }
+}
+
+__global__ void finish_norm_kernel (const double *partials, double *out)
+{
+    if (threadIdx.x != 0) return;
+    double total = 0.0;
+    for (int b = 0; b < kNormBlocks; b++) total += partials[b];
+    *out = sqrt (total);
+}
+}  // namespace
+
+int double_norm_scratch_doubles () { return kNormBlocks; }
+
+cudaError_t launch_double_norm (const double *x, int64_t n, double *partials, double *out, cudaStream_t stream)
+{
+    sum_squares_kernel<<<kNormBlocks, kNormThreads, 0, stream>>> (x, n, partials);
+    cudaError_t e = cudaGetLastError ();
+    if (e != cudaSuccess) return e;
+    finish_norm_kernel<<<1, 32, 0, stream>>> (partials, out);
+    return cudaGetLastError ();
+}
+
 }  // namespace mfb

@@ -117,7 +117,7 @@ tiled_assembly_kernel (const TiledArgs args)
         mbar_wait (bar, parity);
         parity ^= 1;
         const TileBlobHeader &hdr = *reinterpret_cast<const TileBlobHeader*> (sBlob);
-        const int nbRows = hdr.nbRows, nbElems = hdr.nbElems, nbEntries = hdr.nbEntries, nbNodesRef = hdr.nbNodesRef;
+        const int nbRows = hdr.nbRows, nbElems = hdr.nbElems, nbNodesRef = hdr.nbNodesRef;
         const TileRow *sRows = reinterpret_cast<const TileRow*> (sBlob + sizeof (TileBlobHeader));
         const int *tileNodes = reinterpret_cast<const int*> (sBlob + hdr.offNodes);
         const ushort4 *tileElems = reinterpret_cast<const ushort4*> (sBlob + hdr.offElems);
@@ -767,8 +767,7 @@ tiled_pipeline_kernel (const TiledArgs args)
             mbar_wait_bounded (S.blobFull, use & 1);
             mbar_wait_bounded (S.coefFull, use & 1);
             const TileBlobHeader &hdr = *reinterpret_cast<const TileBlobHeader*> (S.blob);
-            const int nbRows = hdr.nbRows, nbElems = hdr.nbElems, nbEntries = hdr.nbEntries;
-            (void)nbElems;
+            const int nbRows = hdr.nbRows;
             const TileRow *sRows = reinterpret_cast<const TileRow*> (S.blob + sizeof (TileBlobHeader));
             const uint8_t *entryRow = S.blob + hdr.offEntryRow;
             const uint16_t *laneEntry = reinterpret_cast<const uint16_t*> (S.blob + hdr.offLaneEntry);

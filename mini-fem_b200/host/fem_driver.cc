@@ -14,6 +14,8 @@
 //                       multithreaded-comm build reports (FEM.cc:179-180: everything under
 //                       "Matrix assembly")                     (default 0: four timed stages)
 //   MINIFEM_DEVICE      CUDA device ordinal                    (default LOCAL_RANK or 0)
+//   MINIFEM_GPU_SETUP   1 = colouring and CSR built on the device (same layouts, bit for bit)
+//   MINIFEM_DEVICE_NORMS 1 = the two check norms are reduced on the device (default: host, serial sum)
 //   MINIFEM_STORE_CHECKINGS  1 = write the checkings file from this run's norms instead of
 //                       comparing with it (the role of store_ref_assembly_, src/IO.cc:42-58)
 //   RANK / WORLD_SIZE   MPI rank / size of the reference (one process per GPU);
@@ -220,14 +222,11 @@ void FEM_loop (mfb_ctx *ctx, int nbIter, int nbBlocks, int rank, bool fused, con
 }
 
 // FEM.cc:59-98
-void check_results (const double *prec, const double *values, int nbEdges, int nbNodes, int operatorDim,
-                    int nbBlocks, int rank, const string &dataPath)
+void check_results (double matrixNorm, double precNorm, int nbBlocks, int rank, const string &dataPath)
 {
     double refMatrixNorm, refPrecNorm;
     const string file = dataPath + "/" + meshName + "/checkings/" + operatorName + "_" + to_string (nbBlocks) +
                         "_" + to_string (rank);
-    const double matrixNorm = mfb_double_norm (values, (int64_t)nbEdges * operatorDim);
-    const double precNorm = mfb_double_norm (prec, (int64_t)nbNodes * operatorDim);
     if (env_int ("MINIFEM_STORE_CHECKINGS", 0)) {              // store_ref_assembly_, IO.cc:42-58
         if (mfb_checking_write (file.c_str (), matrixNorm, precNorm) != MFB_OK) die (mfb_last_error ());
         if (rank == 0) cout << "Stored reference checking: " << file << endl << endl;
@@ -265,6 +264,7 @@ int main (int argCount, char **argValue)
     const string rendezvous = env_str ("MINIFEM_RENDEZVOUS", ".");
     const bool fused = env_int ("MINIFEM_FUSED", 0) != 0;
     const int device = env_int ("MINIFEM_DEVICE", env_int ("LOCAL_RANK", 0));
+    const bool gpuSetup = env_int ("MINIFEM_GPU_SETUP", 0) != 0;
     int path = MFB_PATH_TILED;
     if (pathName == "atomic") path = MFB_PATH_ATOMIC;
     else if (pathName == "color") path = MFB_PATH_COLOR;
@@ -301,8 +301,12 @@ int main (int argCount, char **argValue)
     if (path == MFB_PATH_COLOR) {
         begin_step ("Coloring of the mesh...              ");
         vector<int> colorPerm (max (in.nbElem, 1)), colorPart (max (in.nbElem, 1));
-        if (mfb_coloring_creation (in.elemToNode, in.nbElem, in.nbNodes, colorPart.data (), colorToElem.data (),
-                                   colorPerm.data (), &nbTotalColors) != MFB_OK) die (mfb_last_error ());
+        const int rcColor = gpuSetup
+            ? mfb_device_coloring_creation (in.elemToNode, in.nbElem, in.nbNodes, colorPart.data (), colorToElem.data (),
+                                            colorPerm.data (), &nbTotalColors, device)
+            : mfb_coloring_creation (in.elemToNode, in.nbElem, in.nbNodes, colorPart.data (), colorToElem.data (),
+                                     colorPerm.data (), &nbTotalColors);
+        if (rcColor != MFB_OK) die (mfb_last_error ());
         end_step ();
         begin_step ("Applying permutation...              ");
         check (mfb_permute_int_2d (in.elemToNode, colorPerm.data (), in.nbElem, 4), "permutation");
@@ -311,14 +315,24 @@ int main (int argCount, char **argValue)
 
     // Create the CSR matrix (main.cc:238-255); nbEdges comes from the file header (IO.cc:77)
     begin_step ("Creating CSR matrix...               ");
-    const int64_t counted = mfb_count_edges (in.elemToNode, in.nbElem, in.nbNodes);
-    if (counted != in.nbEdges) {
-        die ("Error: the input file announces " + to_string (in.nbEdges) + " edges, the mesh has " + to_string (counted) + ".");
-    }
     vector<int> nodeToNodeRow ((size_t)in.nbNodes + 1), nodeToNodeColumn (max (in.nbEdges, 1));
     int nbEdges = 0;
-    check (mfb_create_nodeToNode (in.elemToNode, in.nbElem, in.nbNodes, nodeToNodeRow.data (),
-                                  nodeToNodeColumn.data (), &nbEdges), "create_nodeToNode");
+    if (gpuSetup) {                                            // MINIFEM_GPU_SETUP=1: the same layouts, built on the device
+        const int rcCsr = mfb_device_create_nodeToNode (in.elemToNode, in.nbElem, in.nbNodes, nodeToNodeRow.data (),
+                                                        nodeToNodeColumn.data (), in.nbEdges, &nbEdges, device);
+        if (nbEdges != in.nbEdges) {
+            die ("Error: the input file announces " + to_string (in.nbEdges) + " edges, the mesh has " + to_string (nbEdges) + ".");
+        }
+        check (rcCsr, "create_nodeToNode");
+    }
+    else {
+        const int64_t counted = mfb_count_edges (in.elemToNode, in.nbElem, in.nbNodes);
+        if (counted != in.nbEdges) {
+            die ("Error: the input file announces " + to_string (in.nbEdges) + " edges, the mesh has " + to_string (counted) + ".");
+        }
+        check (mfb_create_nodeToNode (in.elemToNode, in.nbElem, in.nbNodes, nodeToNodeRow.data (),
+                                      nodeToNodeColumn.data (), &nbEdges), "create_nodeToNode");
+    }
     end_step ();
 
     // Compute the boundary conditions (main.cc:335-351)
@@ -365,14 +379,24 @@ int main (int argCount, char **argValue)
 
     // Main loop with assembly, solver & update (main.cc:353-367)
     if (rank == 0) cout << "\nMain FEM loop\n";
-    vector<double> nodeToNodeValue ((size_t)max (nbEdges, 1) * operatorDim), prec ((size_t)max (in.nbNodes, 1) * operatorDim);
     FEM_loop (ctx, nbIter, nbBlocks, rank, fused, rendezvous);
-    check (mfb_ctx_download (ctx, nodeToNodeValue.data (), prec.data ()), "download");
-    const int nbNodes = in.nbNodes;
+    // The two norms check_results compares (FEM.cc:68-76).  Default: the arrays come back to the
+    // host and are summed serially like compute_double_norm, so that the figures agree with the
+    // reference's to the last digit; MINIFEM_DEVICE_NORMS=1 reduces them on the device instead.
+    double matrixNorm = 0, precNorm = 0;
+    if (env_int ("MINIFEM_DEVICE_NORMS", 0)) {
+        check (mfb_ctx_norms (ctx, &matrixNorm, &precNorm), "norms");
+    }
+    else {
+        vector<double> nodeToNodeValue ((size_t)max (nbEdges, 1) * operatorDim), prec ((size_t)max (in.nbNodes, 1) * operatorDim);
+        check (mfb_ctx_download (ctx, nodeToNodeValue.data (), prec.data ()), "download");
+        matrixNorm = mfb_double_norm (nodeToNodeValue.data (), (int64_t)nbEdges * operatorDim);
+        precNorm = mfb_double_norm (prec.data (), (int64_t)in.nbNodes * operatorDim);
+    }
     mfb_ctx_destroy (ctx);
     mfb_mesh_free (mesh);
 
     // Check matrix & prec arrays (main.cc:375-378)
-    check_results (prec.data (), nodeToNodeValue.data (), nbEdges, nbNodes, operatorDim, nbBlocks, rank, dataPath);
+    check_results (matrixNorm, precNorm, nbBlocks, rank, dataPath);
     return EXIT_SUCCESS;
 }

@@ -80,6 +80,8 @@ lib.mfb_ctx_assembly_interval.argtypes = [C.c_void_p, C.c_int, C.c_int]
 lib.mfb_ctx_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 lib.mfb_ctx_upload_coord.argtypes = [C.c_void_p, C.c_void_p]
 lib.mfb_ctx_iteration_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.mfb_ctx_norms.argtypes = [C.c_void_p, _f64p, _f64p]
+lib.mfb_ctx_iteration_norms_host.argtypes = [C.c_void_p, C.c_void_p, _f64p]
 lib.mfb_ctx_device_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
 lib.mfb_ctx_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
 lib.mfb_ctx_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -121,6 +123,7 @@ DECLARED_SYMBOLS = [
     "mfb_tile_plan_selfcheck", "mfb_host_alloc",
     "mfb_host_free", "mfb_device_count",
     "mfb_device_create_nodeToNode", "mfb_device_create_elemToEdge", "mfb_device_coloring_creation",
+    "mfb_ctx_norms", "mfb_ctx_iteration_norms_host",
 ]
 
 
@@ -384,6 +387,17 @@ class Context:
         p = np.empty(max(self.nbPrec, 1), np.float64) if prec else None
         _check(lib.mfb_ctx_download(self.handle, _ptr(v), _ptr(p)), "mfb_ctx_download")
         return (None if v is None else v[:self.nbValues]), (None if p is None else p[:self.nbPrec])
+
+    def norms(self):
+        """(matrix norm, prec norm) as check_results computes them (FEM.cc:68-76), on the device."""
+        a, b = C.c_double(0), C.c_double(0)
+        _check(lib.mfb_ctx_norms(self.handle, C.byref(a), C.byref(b)), "mfb_ctx_norms")
+        return a.value, b.value
+
+    def iteration_norms_host(self, coord_ptr):
+        out = (C.c_double * 2)()
+        _check(lib.mfb_ctx_iteration_norms_host(self.handle, coord_ptr, out), "mfb_ctx_iteration_norms_host")
+        return out[0], out[1]
 
     def iteration_host(self, coord_ptr, values_ptr, prec_ptr):
         _check(lib.mfb_ctx_iteration_host(self.handle, coord_ptr, values_ptr, prec_ptr), "mfb_ctx_iteration_host")

@@ -47,6 +47,15 @@ def test_no_cpu_fallback():
     for path in ("tiled", "atomic"):
         with pytest.raises(mfb.MfbError, match="no CUDA device"):
             mfb.Context(setup, path=path)
+    # the GPU layout builders do not quietly run on the host either
+    with pytest.raises(mfb.MfbError, match="no such CUDA device"):
+        mfb.device_create_nodeToNode(mesh.elemToNode, mesh.nbNodes)
+    with pytest.raises(mfb.MfbError, match="no such CUDA device"):
+        mfb.device_create_elemToEdge(setup.row, setup.col, mesh.elemToNode)
+    with pytest.raises(mfb.MfbError, match="no such CUDA device"):
+        mfb.device_coloring_creation(mesh.elemToNode, mesh.nbNodes)
+    with pytest.raises(mfb.MfbError, match="no such CUDA device"):
+        mfb.Setup(mesh, "ela", builder="gpu")
 
 
 def test_argument_validation_happens_before_cuda():

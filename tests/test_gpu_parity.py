@@ -211,6 +211,27 @@ def test_moving_coordinates(oracle):
 
 
 @pytest.mark.parametrize("op", ["lap", "ela"])
+def test_device_norms(oracle, op):
+    """mfb_ctx_norms = compute_double_norm (FEM.cc:48-56) of values and prec, reduced on the device."""
+    mesh = mfb.Mesh.generate(16, 9, 12, seed=3)
+    setup = mfb.Setup(mesh, op)
+    ctx = mfb.Context(setup, path="tiled")
+    ctx.iteration()
+    v, p = ctx.download()
+    got = ctx.norms()
+    assert got == ctx.norms()                                   # reproducible
+    want = (mfb.double_norm(v), mfb.double_norm(p))
+    assert abs(got[0] - want[0]) <= RTOL * want[0] and abs(got[1] - want[1]) <= RTOL * want[1]
+    want_v, _, want_p = oracle.fem_iteration(setup)
+    assert abs(got[0] - oracle.norm(want_v)) <= RTOL * got[0] and abs(got[1] - oracle.norm(want_p)) <= RTOL * got[1]
+    pinned = mfb.PinnedArray(mesh.coord.size)
+    pinned.array[:] = mesh.coord
+    assert ctx.iteration_norms_host(pinned.ptr) == got
+    pinned.free()
+    ctx.close()
+
+
+@pytest.mark.parametrize("op", ["lap", "ela"])
 def test_eib_size_properties(op):
     """BASELINE.json's EIB-like size (100^3 cubes: 1,030,301 nodes, 6,000,000 tets), where the
     oracle would take minutes: size-independent properties of the assembled operator.
@@ -280,6 +301,14 @@ def test_driver_cli(tmp_path, oracle):
         report = open(tmp_path / "numerical_results_0").read()
         diffs = [float(l.split(":")[1]) for l in report.splitlines() if "difference" in l]
         assert len(diffs) == 2 and max(diffs) < 1e-13, report
+    # the same case with the layouts built on the device and the two norms reduced there
+    env = dict(os.environ, MINIFEM_DATA_PATH=data, MINIFEM_PATH="color", MINIFEM_GPU_SETUP="1", MINIFEM_DEVICE_NORMS="1")
+    res = subprocess.run([exe, "LM6", "ela", "3"], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout
+    report = open(tmp_path / "numerical_results_0").read()
+    diffs = [float(l.split(":")[1]) for l in report.splitlines() if "difference" in l]
+    assert len(diffs) == 2 and max(diffs) < 1e-13, report
     # MINIFEM_STORE_CHECKINGS=1 writes the checkings file (store_ref_assembly_, IO.cc:42-58) ...
     os.remove(os.path.join(data, "LM6", "checkings", "ela_1_0"))
     env = dict(os.environ, MINIFEM_DATA_PATH=data, MINIFEM_STORE_CHECKINGS="1")
