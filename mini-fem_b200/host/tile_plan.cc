@@ -60,31 +60,42 @@ inline int bank_of (int a, int e, int stride) { return (a * stride + e) & 15; }
 int schedule_chunk (const std::vector<uint16_t> *lists, int nbLanes, bool bankAware, std::vector<uint16_t> &out)
 {
     int T = 0, remaining[16], total = 0;
-    std::vector<uint16_t> rest[16];
     for (int l = 0; l < nbLanes; l++) {
-        rest[l] = lists[l];
-        remaining[l] = (int)rest[l].size ();
+        remaining[l] = (int)lists[l].size ();
         T = std::max (T, remaining[l]);
         total += remaining[l];
     }
     out.clear ();
     if (!bankAware) {                               // plain element order, no gaps
         out.assign ((size_t)T * 16, 0xFFFF);
-        for (int l = 0; l < nbLanes; l++) for (size_t t = 0; t < rest[l].size (); t++) out[t * 16 + l] = rest[l][t];
+        for (int l = 0; l < nbLanes; l++) for (size_t t = 0; t < lists[l].size (); t++) out[t * 16 + l] = lists[l][t];
         return T;
     }
-    // contributions grouped by element: group g = (element, its remaining (lane, code) pairs)
-    struct Group { int elem; std::vector<std::pair<int, uint16_t>> pairs; };
-    std::vector<Group> groups;
+    // contributions grouped by element, groups in order of first appearance: group g owns the
+    // (lane, code) pairs gPairs[gStart[g] .. gStart[g] + gCount[g]) that are still to be placed
+    static thread_local std::vector<int> gElem, gStart, gCount;
+    static thread_local std::vector<std::pair<int, uint16_t>> gPairs;
+    static thread_local std::vector<int16_t> groupOf (4096, -1);      // element (12-bit field) -> group, -1 between calls
+    gElem.clear (); gCount.clear ();
     for (int l = 0; l < nbLanes; l++) {
-        for (uint16_t code : rest[l]) {
+        for (uint16_t code : lists[l]) {
             const int e = code >> 4;
-            size_t g = 0;
-            while (g < groups.size () && groups[g].elem != e) g++;
-            if (g == groups.size ()) groups.push_back ({e, {}});
-            groups[g].pairs.push_back ({l, code});
+            if (groupOf[e] < 0) { groupOf[e] = (int16_t)gElem.size (); gElem.push_back (e); gCount.push_back (0); }
+            gCount[groupOf[e]]++;
         }
     }
+    const int nbGroups = (int)gElem.size ();
+    gStart.assign ((size_t)nbGroups + 1, 0);
+    for (int g = 0; g < nbGroups; g++) { gStart[g + 1] = gStart[g] + gCount[g]; gCount[g] = 0; }
+    gPairs.resize ((size_t)total);
+    for (int l = 0; l < nbLanes; l++) {
+        for (uint16_t code : lists[l]) {
+            const int g = groupOf[code >> 4];
+            gPairs[(size_t)gStart[g] + gCount[g]++] = {l, code};
+        }
+    }
+    for (int e : gElem) groupOf[e] = -1;
+    out.reserve ((size_t)(T + 2) * 16);
     int step = 0;
     while (total > 0) {
         out.resize ((size_t)(step + 1) * 16, 0xFFFF);
@@ -97,26 +108,28 @@ int schedule_chunk (const std::vector<uint16_t> *lists, int nbLanes, bool bankAw
             // element covering the most lanes that cannot wait, then the most free lanes,
             // in a bank class this step does not use yet
             int best = -1, bestScore = 0;
-            for (size_t g = 0; g < groups.size (); g++) {
+            for (int g = 0; g < nbGroups; g++) {
+                const std::pair<int, uint16_t> *pairs = &gPairs[(size_t)gStart[g]];
                 int nMust = 0, nFree = 0;
-                for (auto &pr : groups[g].pairs) if (!busy[pr.first]) { nFree++; nMust += must[pr.first]; }
+                for (int k = 0; k < gCount[g]; k++) if (!busy[pairs[k].first]) { nFree++; nMust += must[pairs[k].first]; }
                 if (nFree == 0) continue;
                 if (nChosen >= 4 && nMust == 0) continue;            // four bank classes per step
                 if (nMustOpen == 0 && nFree < 2 && nChosen > 0) continue;   // do not open an element for one idle lane
-                const int score = nMust * 64 + nFree * 4 + (int)groups[g].pairs.size ();
-                if (score > bestScore) { bestScore = score; best = (int)g; }
+                const int score = nMust * 64 + nFree * 4 + gCount[g];
+                if (score > bestScore) { bestScore = score; best = g; }
             }
             if (best < 0) break;
-            Group &G = groups[best];
+            std::pair<int, uint16_t> *pairs = &gPairs[(size_t)gStart[best]];
             nChosen++;
-            for (size_t k = 0; k < G.pairs.size ();) {
-                const int l = G.pairs[k].first;
-                if (busy[l]) { k++; continue; }
-                cur[l] = G.pairs[k].second;
+            int kept = 0;
+            for (int k = 0; k < gCount[best]; k++) {
+                const int l = pairs[k].first;
+                if (busy[l]) { pairs[kept++] = pairs[k]; continue; }
+                cur[l] = pairs[k].second;
                 busy[l] = true; remaining[l]--; total--;
                 if (must[l]) nMustOpen--;
-                G.pairs.erase (G.pairs.begin () + k);
             }
+            gCount[best] = kept;
         }
         step++;
         if (step > 4096) break;                     // cannot happen: every step places >= 1 code
@@ -268,6 +281,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
     {
         std::vector<int> nodeLocal ((size_t)nbNodes, -1), elemLocal ((size_t)nbElem, -1);
         std::vector<std::vector<uint16_t>> lists, diagLists;
+        std::vector<int> meetStart, meetFill, meetList, setStart, setCount, setList;   // reused from tile to tile
         #pragma omp for schedule(dynamic, 16)
         for (int t = 0; t < nbTiles; t++) {
             TileScratch &s = scratch[t];
@@ -356,29 +370,42 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
             std::vector<int> newId ((size_t)nbTileElems);
             int nbIds = nbTileElems;
             if (lim.bankAware && nbTileElems > 0) {
-                std::vector<std::vector<int>> meets ((size_t)nbTileElems);
-                for (const Chunk &ch : chunks) {
-                    for (int t = 0; t < ch.steps; t++) {
-                        int present[16], nPresent = 0;
-                        for (int l = 0; l < ch.nbLanes; l++) {
-                            const uint16_t code = ch.codes[(size_t)t * 16 + l];
-                            if (code == 0xFFFF) continue;
-                            const int e = code >> 4;
-                            bool known = false;
-                            for (int u = 0; u < nPresent; u++) known |= present[u] == e;
-                            if (!known) present[nPresent++] = e;
+                // meets: CSR over the elements, filled in two sweeps over the scheduled steps
+                meetStart.assign ((size_t)nbTileElems + 1, 0);
+                auto for_each_step = [&] (auto &&visit) {
+                    for (const Chunk &ch : chunks) {
+                        for (int t = 0; t < ch.steps; t++) {
+                            int present[16], nPresent = 0;
+                            for (int l = 0; l < ch.nbLanes; l++) {
+                                const uint16_t code = ch.codes[(size_t)t * 16 + l];
+                                if (code == 0xFFFF) continue;
+                                const int e = code >> 4;
+                                bool known = false;
+                                for (int u = 0; u < nPresent; u++) known |= present[u] == e;
+                                if (!known) present[nPresent++] = e;
+                            }
+                            visit (present, nPresent);
                         }
-                        for (int u = 0; u < nPresent; u++) for (int v = 0; v < nPresent; v++) if (u != v) meets[present[u]].push_back (present[v]);
                     }
-                }
+                };
+                for_each_step ([&] (const int *present, int nPresent) {
+                    for (int u = 0; u < nPresent; u++) meetStart[(size_t)present[u] + 1] += nPresent - 1;
+                });
+                for (int el = 0; el < nbTileElems; el++) meetStart[(size_t)el + 1] += meetStart[el];
+                meetFill.assign (meetStart.begin (), meetStart.end () - 1);
+                meetList.resize ((size_t)meetStart[nbTileElems]);
+                for_each_step ([&] (const int *present, int nPresent) {
+                    for (int u = 0; u < nPresent; u++) for (int v = 0; v < nPresent; v++) if (u != v) meetList[(size_t)meetFill[present[u]]++] = present[v];
+                });
+                auto degree = [&] (int el) { return meetStart[(size_t)el + 1] - meetStart[el]; };
                 std::vector<int> cls ((size_t)nbTileElems, -1), byDegree ((size_t)nbTileElems);
                 for (int el = 0; el < nbTileElems; el++) byDegree[el] = el;
-                std::stable_sort (byDegree.begin (), byDegree.end (), [&] (int x, int y) { return meets[x].size () > meets[y].size (); });
+                std::stable_sort (byDegree.begin (), byDegree.end (), [&] (int x, int y) { return degree (x) > degree (y); });
                 int classSize[4] = {0, 0, 0, 0};
                 const int classCap = (nbTileElems + 3) / 4;
                 for (int el : byDegree) {
                     int clash[4] = {0, 0, 0, 0};
-                    for (int other : meets[el]) if (cls[other] >= 0) clash[cls[other]]++;
+                    for (int q = meetStart[el]; q < meetStart[(size_t)el + 1]; q++) if (cls[meetList[q]] >= 0) clash[cls[meetList[q]]]++;
                     int bestClass = -1, bestCost = 1 << 30;
                     for (int c = 0; c < 4; c++) {
                         if (classSize[c] >= classCap) continue;
@@ -412,20 +439,32 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
             if (lim.bankAware && nbIds > 0) {
                 const int nbRef = (int)s.nodes.size ();
                 const int nbSets = ((nbIds + 15) / 16) * 4;
-                std::vector<std::vector<int>> setsOfNode ((size_t)nbRef);
+                // setList[setStart[n] .. + setCount[n]): the distinct read sets node n takes part in
+                setStart.assign ((size_t)nbRef + 1, 0);
+                for (int id = 0; id < nbIds; id++) {
+                    if (s.elemNodes[(size_t)id * 4] == 0xFFFF) continue;
+                    for (int k = 0; k < 4; k++) setStart[(size_t)s.elemNodes[(size_t)id * 4 + k] + 1]++;
+                }
+                for (int n = 0; n < nbRef; n++) setStart[(size_t)n + 1] += setStart[n];
+                setCount.assign ((size_t)nbRef, 0);
+                setList.resize ((size_t)setStart[nbRef]);
                 for (int id = 0; id < nbIds; id++) {
                     if (s.elemNodes[(size_t)id * 4] == 0xFFFF) continue;
                     for (int k = 0; k < 4; k++) {
-                        std::vector<int> &v = setsOfNode[s.elemNodes[(size_t)id * 4 + k]];
-                        const int set = (id / 16) * 4 + k;
-                        if (std::find (v.begin (), v.end (), set) == v.end ()) v.push_back (set);
+                        const int n = s.elemNodes[(size_t)id * 4 + k], set = (id / 16) * 4 + k;
+                        int *v = &setList[(size_t)setStart[n]];
+                        if (std::find (v, v + setCount[n], set) == v + setCount[n]) v[setCount[n]++] = set;
                     }
                 }
+                auto sets_of = [&] (int n, auto &&visit) {
+                    const int *v = &setList[(size_t)setStart[n]];
+                    for (int q = 0; q < setCount[n]; q++) visit (v[q]);
+                };
                 std::vector<uint8_t> used ((size_t)nbSets * 16, 0);
                 std::vector<int> newNode ((size_t)nbRef, -1), nextFree (16);
                 for (int n = 0; n < nbRows; n++) {
                     newNode[n] = n;
-                    for (int set : setsOfNode[n]) used[(size_t)set * 16 + (n & 15)]++;
+                    sets_of (n, [&] (int set) { used[(size_t)set * 16 + (n & 15)]++; });
                 }
                 for (int r = 0; r < 16; r++) { nextFree[r] = nbRows + ((r - nbRows) & 15); }
                 int maxId = nbRows - 1;
@@ -434,14 +473,14 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                     for (int r = 0; r < 16; r++) {
                         if (nextFree[r] >= lim.maxNodesRef) continue;
                         int cost = 0;
-                        for (int set : setsOfNode[n]) cost += used[(size_t)set * 16 + r];
+                        sets_of (n, [&] (int set) { cost += used[(size_t)set * 16 + r]; });
                         cost = cost * 65536 + nextFree[r];
                         if (cost < bestCost) { bestCost = cost; bestRes = r; }
                     }
                     newNode[n] = nextFree[bestRes];
                     nextFree[bestRes] += 16;
                     maxId = std::max (maxId, newNode[n]);
-                    for (int set : setsOfNode[n]) used[(size_t)set * 16 + bestRes]++;
+                    sets_of (n, [&] (int set) { used[(size_t)set * 16 + bestRes]++; });
                 }
                 std::vector<int> renumNodes ((size_t)maxId + 1, s.nodes.empty () ? 0 : s.nodes[0]);   // holes: any valid node
                 for (int n = 0; n < nbRef; n++) renumNodes[newNode[n]] = s.nodes[n];
