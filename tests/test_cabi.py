@@ -107,3 +107,31 @@ def test_tile_plan_selfcheck_unstructured_and_multirank():
     p = mfb.Problem(1, mesh.nbElem, mesh.nbNodes, s.nbEdges, *[k.ctypes.data for k in keep[:4]], None, None, None, 0,
                     2, 1, mesh.nbIntf, mesh.nbIntfNodes, *[k.ctypes.data for k in keep[4:]])
     assert mfb.lib.mfb_tile_plan_selfcheck(C.byref(p), 16, 256, stats) == 0, mfb.lib.mfb_last_error()
+
+
+def test_tile_plan_selfcheck_property():
+    """Random unstructured connectivity, random caps, both operators: whenever a plan is built
+    it replays the reference's (element, j, k) loop exactly; caps are either met or reported."""
+    from hypothesis import given, settings, strategies as st
+    from helpers import random_tet_mesh, ArrayMesh
+
+    @settings(max_examples=40, deadline=None)
+    @given(seed=st.integers(0, 2**31 - 1), nbNodes=st.integers(4, 120), density=st.floats(0.5, 6.0),
+           rows=st.integers(1, 40), elems=st.integers(8, 400), operatorID=st.integers(0, 1))
+    def check(seed, nbNodes, density, rows, elems, operatorID):
+        rng = np.random.default_rng(seed)
+        nbElem = max(1, int(nbNodes * density))
+        coord, e2n = random_tet_mesh(rng, nbNodes, nbElem)
+        s = mfb.Setup(ArrayMesh(coord, e2n, nbNodes), "ela" if operatorID else "lap")
+        keep = [np.ascontiguousarray(coord), s.elemToNode, s.row, s.col]
+        p = mfb.Problem(operatorID, nbElem, nbNodes, s.nbEdges, *[k.ctypes.data for k in keep], None, None, None, 0,
+                        1, 0, 0, 0, None, None, None)
+        stats = (C.c_int64 * 6)()
+        rc = mfb.lib.mfb_tile_plan_selfcheck(C.byref(p), rows, elems, stats)
+        if rc != 0:
+            assert b"exceeds the tile caps" in mfb.lib.mfb_last_error(), mfb.lib.mfb_last_error()
+            return
+        assert stats[2] == 16 * nbElem
+        assert stats[3] <= rows and stats[4] <= elems + 3      # ids include the coset numbering's holes
+
+    check()
