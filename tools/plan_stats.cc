@@ -33,7 +33,10 @@ int main (int argc, char **argv)
     lim.maxNodesRef = lim.maxElems; lim.maxEntries = 65535;
     if (argc > 4) lim.bankAware = atoi (argv[4]) != 0;
     SubMesh m;
-    generate_block (g, g, g, 1, 1, 1, 0, 1, m);
+    if (argc > 1 && strchr (argv[1], '/')) {                  // an input file (src/IO.cc format), e.g. from tools/delaunay_mesh.py
+        if (read_input (argv[1], m)) { printf ("cannot read %s\n", argv[1]); return 1; }
+    }
+    else generate_block (g, g, g, 1, 1, 1, 0, 1, m);
     std::vector<int> row (m.nbNodes + 1), col (m.nbEdges);
     build_csr (m.elemToNode.data (), m.nbElem, m.nbNodes, row.data (), col.data ());
     TilePlan plan; std::string err;
@@ -88,7 +91,8 @@ int main (int argc, char **argv)
             }
         }
     }
-    printf ("grid %d^3: tiles %d tileElems %.3f x, padded steps %.3f x, blob max %u\n", g, plan.nbTiles,
+    printf ("%s: %d elements, tiles %d (%.1f rows, %.1f elements each) tileElems %.3f x, padded steps %.3f x, blob max %u\n", argc > 1 ? argv[1] : "40", m.nbElem, plan.nbTiles,
+            (double)m.nbNodes / plan.nbTiles, (double)plan.nbTileElems / plan.nbTiles,
             (double)plan.nbTileElems / m.nbElem, (double)plan.nbPaddedSteps * 32 / (12.0 * m.nbElem), plan.maxBlobBytes);
     printf ("per element: P4 %.1f wavefronts (%.2f per LDS.64), diag %.1f (%.2f), P2 reads %.1f (%.2f)\n",
             wfP4 / m.nbElem, wfP4 / instrP4, wfDiag / m.nbElem, wfDiag / instrDiag, wfP2 / m.nbElem, wfP2 / instrP2);

@@ -15,12 +15,13 @@ ap.add_argument("--tile-elems", type=int, default=0)
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--ctas", type=int, default=0)
 ap.add_argument("--no-bank-aware", action="store_true")
+ap.add_argument("--file", default=None, help="read the mesh from an input file (src/IO.cc format, e.g. tools/delaunay_mesh.py) instead of generating a Kuhn grid")
 ap.add_argument("--shuffle", action="store_true", help="random node and element numbering (unstructured-like input order)")
 a = ap.parse_args()
 
 t0 = time.time()
-mesh = mfb.Mesh.generate(*a.grid, seed=1)
-print(f"mesh {a.grid}: E={mesh.nbElem} N={mesh.nbNodes} Z={mesh.nbEdges}  ({time.time()-t0:.1f}s)", flush=True)
+mesh = mfb.Mesh.read(a.file) if a.file else mfb.Mesh.generate(*a.grid, seed=1)
+print(f"mesh {a.file or a.grid}: E={mesh.nbElem} N={mesh.nbNodes} Z={mesh.nbEdges}  ({time.time()-t0:.1f}s)", flush=True)
 if a.shuffle:
     rng = np.random.default_rng(5)
     nperm = rng.permutation(mesh.nbNodes)                  # old node -> new node
@@ -56,8 +57,8 @@ for path in a.paths.split(","):
         if ref is None:
             ref = (v, p)
         else:
-            dim = setup.operatorDim
-            sv = np.abs(ref[0].reshape(-1, dim)).max(axis=1, keepdims=True)
-            print("   vs first path: values", (np.abs(v - ref[0]).reshape(-1, dim) / sv).max(),
-                  "prec", np.nanmax(np.abs(p - ref[1]) / np.maximum(np.abs(ref[1]), 1e-300)))
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from helpers import row_scaled_error, block_scaled_error
+            print("   vs first path (row / block scaled): values", row_scaled_error(v, ref[0], setup.row, setup.operatorDim),
+                  "prec", block_scaled_error(p, ref[1], setup.operatorDim))
     ctx.close()
