@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))            # mini-fem_b200/
-LIB_PATH = os.path.join(PKG_ROOT, "libminifem_b200.so")
+LIB_PATH = os.environ.get("MFB_LIBRARY") or os.path.join(PKG_ROOT, "libminifem_b200.so")   # MFB_LIBRARY: an experimental build
 
 PATH_TILED, PATH_ATOMIC, PATH_COLOR = 0, 1, 2
 PATH_NAMES = {"tiled": PATH_TILED, "atomic": PATH_ATOMIC, "color": PATH_COLOR}
