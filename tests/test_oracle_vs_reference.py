@@ -86,3 +86,21 @@ def test_coloring_build_with_installed_colours(oracle):
         assert np.array_equal(v1[0], v2[0]) and np.array_equal(p1[0], p2[0])
         want_v, _, want_p = oracle.fem_iteration(s)
         assert np.array_equal(v1[0], want_v) and np.array_equal(p1[0], want_p)
+
+
+def test_modified_coloring_build_matches_the_shipped_one(oracle):
+    """oracle/_ref/libminifem_ref_coloring_omp.so restores the per-colour `#pragma omp parallel for`
+    the reference ships commented out (src/assembly.cc:362,516); bench.py reports it as the
+    "modified" CPU baseline.  Elements of one colour share no node, so the threaded loop must give
+    the same bits as the shipped serial one."""
+    mesh = mfb.Mesh.generate(9, 7, 6, seed=12)
+    shipped, modified = Reference("coloring"), Reference("coloring_omp")
+    for op in ("lap", "ela"):
+        s = mfb.Setup(mesh, op, coloring=True)
+        shipped.set_colors(s.colorToElem)
+        modified.set_colors(s.colorToElem)
+        v1, p1, _, _ = shipped.fem_loop([s], 2)
+        v2, p2, _, _ = modified.fem_loop([s], 2)
+        assert np.array_equal(v1[0], v2[0]) and np.array_equal(p1[0], p2[0])
+        want_v, _, want_p = oracle.fem_iteration(s)
+        assert np.array_equal(v2[0], want_v) and np.array_equal(p2[0], want_p)
