@@ -36,6 +36,11 @@ extern "C" {
 #define MFB_PATH_TILED    0   /* write-once gather over node tiles staged in shared memory */
 #define MFB_PATH_ATOMIC   1   /* memset + native FP64 atomicAdd per contribution            */
 #define MFB_PATH_COLOR    2   /* memset + one conflict-free launch per reference colour     */
+#define MFB_PATH_RING     3   /* write-once like TILED, but every mesh edge walks the ring of elements
+                                 around it from the node coordinates: no coefficient planes in shared
+                                 memory, interior edges computed once for both (i,j) and (j,i), the
+                                 diagonal block = minus the row sum.  Compiled and replayed on the host
+                                 (tools/ring_replay.cc); first GPU measurement pending */
 
 const char *mfb_last_error (void);
 const char *mfb_version (void);
@@ -132,7 +137,7 @@ typedef struct {
     int path;                       /* MFB_PATH_* */
     int device;                     /* CUDA device ordinal */
     int tileRows;                   /* TILED: max rows per tile (0 = default) */
-    int tileElems;                  /* TILED: max elements per tile (0 = default) */
+    int tileElems;                  /* TILED: max elements per tile; RING: max CSR entries per tile (0 = default) */
     int threads;                    /* TILED: threads per CTA (0 = default) */
     int useGraph;                   /* capture mfb_ctx_iteration in a CUDA graph */
     int ctas;                       /* TILED: CTAs walking the tiles (0 = default, -1 = one per tile) */
@@ -228,6 +233,16 @@ int mfb_ctx_run_timed (mfb_ctx *ctx, int steps, float *ms);
  * [2] contributions [3] max rows [4] max elems [5] plan bytes. */
 int mfb_tile_plan_selfcheck (const mfb_problem *problem, int tileRows, int tileElems,
                              int64_t stats[6]);
+
+/* Same for the RING plan (host/ring_plan.h): rows tile the CSR, every off-diagonal entry is written
+ * by exactly one job, the consecutive nodes of a job's chains name distinct elements around its edge,
+ * every element's 12 off-diagonal node pairs are covered exactly once.  tileRows / tileEntries 0 =
+ * defaults.  stats: [0] tiles [1] jobs [2] jobs that also write the transposed block [3] ring steps
+ * [4] padded lane-steps [5] chain breaks [6] modelled gather wavefronts [7] conflict-free count
+ * [8] modelled slab-store wavefronts per block component [9] conflict-free count [10] plan bytes
+ * [11] interface tiles. */
+int mfb_ring_plan_selfcheck (const mfb_problem *problem, int tileRows, int tileEntries,
+                             int64_t stats[12]);
 
 /* Pinned host memory for the *_host calls. */
 int mfb_host_alloc (void **ptr, int64_t bytes);

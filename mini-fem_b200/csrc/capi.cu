@@ -276,6 +276,9 @@ struct mfb_ctx {
     size_t tiledSmem = 0;
     int tiledCtas = 1;
     bool tiledPrefetch = false;
+    bool ring = false;              // MFB_PATH_RING: same iteration structure as TILED, other plan + kernel
+    DeviceRingPlan ringPlan;
+    RingPlan ringStats;             // counters only
     double *dNorm = nullptr;        // [partials][2 results], allocated by the first mfb_ctx_norms
     int haloCoresident = 0;         // multi-GPU overlap scheme, see do_iteration
     int interiorTilesPerCta = 4;   // measured at N=2: 1 -> 0.71 ms, 4 -> 0.645, 8 -> 0.647 (kernel alone 0.636 in that build)
@@ -350,6 +353,61 @@ int build_device_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options *o)
     return MFB_OK;
 }
 
+int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options *o)
+{
+    std::vector<uint8_t> isIntf;
+    if (p->nbBlocks > 1 && p->nbIntfNodes > 0) {
+        isIntf.assign ((size_t)p->nbNodes, 0);
+        for (int j = 0; j < p->nbIntfNodes; j++) isIntf[p->intfNodes[j] - 1] = 1;
+    }
+    RingPlanLimits lim;
+    if (o && o->tileRows > 0) lim.maxRows = o->tileRows;
+    if (o && o->tileElems > 0) lim.maxEntries = o->tileElems;          // RING: tileElems caps the CSR entries of a tile
+    lim.bankAware = !(o && o->bankAware < 0);
+    RingPlan hp;
+    std::string err;
+    if (build_ring_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, p->coord,
+                         isIntf.empty () ? nullptr : isIntf.data (), lim, hp, err) != 0) {
+        return fail (MFB_ERR_ARG, "ring plan: " + err);
+    }
+    if (hp.blob.empty ()) hp.blob.resize (16);
+    MFB_CUDA (put_plan (c, &c->ringPlan.blob, hp.blob));
+    {   // device table: byte offset in the low 48 bits, (head bytes / 16) above
+        std::vector<uint64_t> packed (hp.tileOffset);
+        for (int t = 0; t < hp.nbTiles; t++) packed[t] |= (uint64_t)(hp.header (t)->headBytes >> 4) << 48;
+        MFB_CUDA (put_plan (c, &c->ringPlan.tileOffset, packed));
+    }
+    c->ringPlan.nbTiles = hp.nbTiles; c->ringPlan.nbInterfaceTiles = hp.nbInterfaceTiles;
+    c->ringPlan.maxRows = std::max (hp.maxRows, 1); c->ringPlan.maxNodes = std::max (hp.maxNodes, 4);
+    c->ringPlan.maxEntries = std::max (hp.maxEntries, 1);
+    c->ringPlan.maxHeadBytes = std::max (hp.maxHeadBytes, 16u); c->ringPlan.maxTailBytes = std::max (hp.maxTailBytes, 16u);
+    c->plan.nbTiles = hp.nbTiles; c->plan.nbInterfaceTiles = hp.nbInterfaceTiles;     // do_iteration splits on these
+    std::vector<uint64_t> ().swap (hp.tileOffset);
+    std::vector<uint8_t> ().swap (hp.blob);
+    c->ringStats = hp;
+    if (const char *v = getenv ("MFB_HALO_OVERLAP")) c->haloCoresident = std::string (v) == "coresident";
+    if (const char *v = getenv ("MFB_INTERIOR_TILES_PER_CTA")) c->interiorTilesPerCta = std::max (atoi (v), 1);
+    c->tiledSmem = ring_smem_bytes (c->operatorID, c->ringPlan);
+    if (c->tiledSmem > 227 * 1024) return fail (MFB_ERR_ARG, "ring plan needs more than 227 KB of shared memory per CTA; lower tileRows / tileElems");
+    MFB_CUDA (ring_configure (c->operatorID));
+    cudaDeviceProp prop;
+    MFB_CUDA (cudaGetDeviceProperties (&prop, c->device));
+    const int perSM = std::max (1, std::min ((int)(prop.sharedMemPerMultiprocessor / (c->tiledSmem + 1024)), 2048 / c->threads));
+    c->tiledCtas = (o && o->ctas > 0) ? o->ctas : (o && o->ctas == -1) ? (1 << 30) : prop.multiProcessorCount * perSM;
+    return MFB_OK;
+}
+
+// The write-once kernel of the context (TILED or RING) over the tiles [firstTile, firstTile + nbTiles).
+cudaError_t launch_write_once (mfb_ctx *c, int firstTile, int nbTiles, int ctas, int fusePrec, cudaStream_t stream)
+{
+    if (c->ring) {
+        return launch_ring (c->operatorID, c->ringPlan, firstTile, nbTiles, ctas, c->threads, c->tiledSmem, c->dCoord,
+                            c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, stream);
+    }
+    return launch_tiled (c->operatorID, c->plan, firstTile, nbTiles, ctas, c->threads, c->tiledSmem, c->dCoord,
+                         c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, stream, c->tiledPrefetch);
+}
+
 int record (mfb_ctx *c, int stage, bool start)
 {
     MFB_CUDA (cudaEventRecord (start ? c->evStart[stage] : c->evStop[stage], c->stream));
@@ -375,8 +433,7 @@ int do_scatter_interval (mfb_ctx *c, int first, int count)
 int do_assembly (mfb_ctx *c, int fusePrec)
 {
     if (c->path == MFB_PATH_TILED) {
-        MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, c->plan.nbTiles, c->tiledCtas, c->threads, c->tiledSmem,
-                                c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, c->stream, c->tiledPrefetch));
+        MFB_CUDA (launch_write_once (c, 0, c->plan.nbTiles, c->tiledCtas, fusePrec, c->stream));
         if (c->plan.nbTiles > 0) c->launches++;
         return MFB_OK;
     }
@@ -453,11 +510,9 @@ int do_iteration (mfb_ctx *c)
         const int intfCtas = std::max (c->tiledCtas / 16, 1), interiorCtas = std::max (c->tiledCtas - intfCtas, 1);
         MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));                 // everything queued so far
         MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
-        MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, intfCtas, c->threads, c->tiledSmem, c->dCoord,
-                                c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->commStream, c->tiledPrefetch));
+        MFB_CUDA (launch_write_once (c, 0, nIntfTiles, intfCtas, 1, c->commStream));
         if (nIntfTiles > 0) c->launches++;
-        MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, nInterior, interiorCtas, c->threads,
-                                c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
+        MFB_CUDA (launch_write_once (c, nIntfTiles, nInterior, interiorCtas, 1, c->stream));
         if (nInterior > 0) c->launches++;
     }
     else {
@@ -466,13 +521,11 @@ int do_iteration (mfb_ctx *c)
         // the interior tiles assemble.  The interior launch is NOT one persistent grid: its CTAs
         // take a few tiles each, so SM resources free up continuously and the halo kernels are
         // scheduled as soon as their inputs are ready, however many CTAs NCCL asks for.
-        MFB_CUDA (launch_tiled (c->operatorID, c->plan, 0, nIntfTiles, c->tiledCtas, c->threads, c->tiledSmem, c->dCoord,
-                                c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
+        MFB_CUDA (launch_write_once (c, 0, nIntfTiles, c->tiledCtas, 1, c->stream));
         if (nIntfTiles > 0) c->launches++;
         MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));
         const int interiorCtas = std::max ((nInterior + c->interiorTilesPerCta - 1) / c->interiorTilesPerCta, 1);
-        MFB_CUDA (launch_tiled (c->operatorID, c->plan, nIntfTiles, nInterior, interiorCtas, c->threads,
-                                c->tiledSmem, c->dCoord, c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, 1, c->stream, c->tiledPrefetch));
+        MFB_CUDA (launch_write_once (c, nIntfTiles, nInterior, interiorCtas, 1, c->stream));
         if (nInterior > 0) c->launches++;
         MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
     }
@@ -524,7 +577,12 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     c->device = o ? o->device : 0;
     c->threads = (o && o->threads > 0) ? o->threads : 256;
     c->useGraph = o ? o->useGraph : 0;
-    if (c->path < MFB_PATH_TILED || c->path > MFB_PATH_COLOR) return fail (MFB_ERR_ARG, "mfb_ctx_create: unknown path");
+    if (c->path < MFB_PATH_TILED || c->path > MFB_PATH_RING) return fail (MFB_ERR_ARG, "mfb_ctx_create: unknown path");
+    if (c->path == MFB_PATH_RING) {          // a write-once path like TILED: same stages, same fused iteration
+        c->ring = true;
+        c->path = MFB_PATH_TILED;
+        if (c->threads != 256) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 256 threads per CTA");
+    }
     if (c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {
         return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256], or the pipelined kernel's CTA size");
     }
@@ -595,7 +653,7 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
         }
     }
     else {
-        int rc = build_device_plan (c, p, o);
+        int rc = c->ring ? build_device_ring_plan (c, p, o) : build_device_plan (c, p, o);
         if (rc) return rc;
     }
 
@@ -840,6 +898,12 @@ extern "C" int mfb_ctx_device_bytes (mfb_ctx *c, int64_t *meshBytes, int64_t *pl
 extern "C" int mfb_ctx_plan_stats (mfb_ctx *c, int64_t stats[8])
 {
     if (!c || !stats) return fail (MFB_ERR_ARG, "NULL argument");
+    if (c->ring) {              // RING: [1] jobs (mesh edges) [2] ring steps [4] max nodes [6] padded lane-steps
+        stats[0] = c->ringStats.nbTiles; stats[1] = c->ringStats.nbJobs; stats[2] = c->ringStats.nbRingSteps;
+        stats[3] = c->ringStats.maxRows; stats[4] = c->ringStats.maxNodes; stats[5] = (int64_t)c->tiledSmem;
+        stats[6] = c->ringStats.nbPaddedSteps; stats[7] = c->ringStats.maxBlobBytes;
+        return MFB_OK;
+    }
     stats[0] = c->hostPlanStats.nbTiles; stats[1] = c->hostPlanStats.nbTileElems;
     stats[2] = c->hostPlanStats.nbContributions; stats[3] = c->hostPlanStats.maxRows;
     stats[4] = c->hostPlanStats.maxElems; stats[5] = (int64_t)c->tiledSmem;
@@ -964,6 +1028,33 @@ extern "C" int mfb_tile_plan_selfcheck (const mfb_problem *p, int tileRows, int 
     }
     stats[0] = plan.nbTiles; stats[1] = plan.nbTileElems; stats[2] = plan.nbContributions;
     stats[3] = plan.maxRows; stats[4] = plan.maxElems; stats[5] = plan.bytes ();
+    return MFB_OK;
+}
+
+extern "C" int mfb_ring_plan_selfcheck (const mfb_problem *p, int tileRows, int tileEntries, int64_t stats[12])
+{
+    if (!p || !stats) return fail (MFB_ERR_ARG, "mfb_ring_plan_selfcheck: NULL argument");
+    RingPlanLimits lim;
+    if (tileRows > 0) lim.maxRows = tileRows;
+    if (tileEntries > 0) lim.maxEntries = tileEntries;
+    std::vector<uint8_t> isIntf;
+    if (p->nbBlocks > 1 && p->nbIntfNodes > 0) {
+        isIntf.assign ((size_t)p->nbNodes, 0);
+        for (int j = 0; j < p->nbIntfNodes; j++) isIntf[p->intfNodes[j] - 1] = 1;
+    }
+    RingPlan plan;
+    std::string err;
+    if (build_ring_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, p->coord,
+                         isIntf.empty () ? nullptr : isIntf.data (), lim, plan, err) != 0) {
+        return fail (MFB_ERR_ARG, "ring plan: " + err);
+    }
+    if (verify_ring_plan (plan, p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, err) != 0) {
+        return fail (MFB_ERR_STATE, "ring plan self-check: " + err);
+    }
+    stats[0] = plan.nbTiles; stats[1] = plan.nbJobs; stats[2] = plan.nbSymmetricJobs; stats[3] = plan.nbRingSteps;
+    stats[4] = plan.nbPaddedSteps; stats[5] = plan.nbBreaks; stats[6] = plan.gatherWavefronts; stats[7] = plan.gatherIdeal;
+    stats[8] = plan.slabWriteWavefronts; stats[9] = plan.slabWriteIdeal; stats[10] = (int64_t)plan.blob.size ();
+    stats[11] = plan.nbInterfaceTiles;
     return MFB_OK;
 }
 

@@ -2,6 +2,15 @@
 #ifndef MFB_DEVICE_MATH_CUH
 #define MFB_DEVICE_MATH_CUH
 
+#include <cmath>
+
+// __host__ too: tools/ring_replay.cc (a test aid) runs mask_block / invert3_lu on the host
+#if defined(__CUDACC__)
+#define MFB_DM __host__ __device__ __forceinline__
+#else
+#define MFB_DM inline
+#endif
+
 namespace mfb {
 
 // Gradient coefficients of one P1 tetrahedron — what elem_coef_seq computes
@@ -9,7 +18,7 @@ namespace mfb {
 // products, row 3 = minus the sum of rows 0..2, all scaled by 1/vol with
 // vol = a . row0 (no |vol|/6 weight; the sign of vol cancels in every product).
 // p = 4 nodes x (x,y,z); c = 4 rows x 3.
-__device__ __forceinline__ void elem_coef (const double p[12], double c[12])
+MFB_DM void elem_coef (const double p[12], double c[12])
 {
     const double xa = p[0] - p[9],  xb = p[6] - p[9],  xc = p[3] - p[9];
     const double ya = p[1] - p[10], yb = p[7] - p[10], yc = p[4] - p[10];
@@ -28,7 +37,7 @@ __device__ __forceinline__ void elem_coef (const double p[12], double c[12])
 
 // One elasticity node-pair block (src/assembly.cc:386-409), row-major 3x3:
 // K = (a.b) I + 1.25 a b^T, i.e. diagonal a_p b_p * 2.25 + the two other products.
-__device__ __forceinline__ void ela_block (const double a[3], const double b[3], double k[9])
+MFB_DM void ela_block (const double a[3], const double b[3], double k[9])
 {
     const double p00 = a[0] * b[0], p11 = a[1] * b[1], p22 = a[2] * b[2];
     k[0] = p00 * 2.25 + p11 + p22;
@@ -42,21 +51,21 @@ __device__ __forceinline__ void ela_block (const double a[3], const double b[3],
     k[8] = p00 + p11 + p22 * 2.25;
 }
 
-__device__ __forceinline__ void swap2 (double &x, double &y) { double t = x; x = y; y = t; }
+MFB_DM void swap2 (double &x, double &y) { double t = x; x = y; y = t; }
 
 // What ela_invert_prec does to one node's 3x3 block (src/Fortran/elasclpr.f:19-53):
 // Dirichlet components get their row and column zeroed and a unit diagonal, then the
 // block is inverted by LU with partial pivoting (DGETRF) and DGETRI's back-substitution.
 // The Fortran views the C block column-major (a(ki,kj) = blk[3*kj+ki]); the same view
 // is kept so that pivoting picks the same rows.  Registers only: every index is static.
-__device__ __forceinline__ void mask_block (double b[9], int mx, int my, int mz)
+MFB_DM void mask_block (double b[9], int mx, int my, int mz)
 {
     if (mx) { b[0] = 1.0; b[1] = b[2] = b[3] = b[6] = 0.0; }
     if (my) { b[4] = 1.0; b[1] = b[3] = b[5] = b[7] = 0.0; }
     if (mz) { b[8] = 1.0; b[2] = b[5] = b[6] = b[7] = 0.0; }
 }
 
-__device__ __forceinline__ void invert3_lu (double b[9])
+MFB_DM void invert3_lu (double b[9])
 {
     // rows of the column-major view: r_i = (a(i,0), a(i,1), a(i,2)) = (b[i], b[3+i], b[6+i])
     double a00 = b[0], a01 = b[3], a02 = b[6];

@@ -6,6 +6,7 @@
 #include <cstdint>
 
 #include "../host/tile_plan.h"
+#include "../host/ring_plan.h"
 
 namespace mfb {
 
@@ -72,6 +73,22 @@ cudaError_t launch_tiled (int operatorID, const DeviceTilePlan &plan, int firstT
                           int threads, size_t smemBytes, const double *coord, double *values,
                           double *prec, const int *checkBounds, int nbNodes, int fusePrec,
                           cudaStream_t stream, bool prefetch = false);
+
+// Device copy of a RingPlan (host/ring_plan.h) and the RING kernel (kernels_ring.cu): same
+// persistent-grid contract as launch_tiled.  tileOffset entries carry (head bytes / 16) in their
+// top 16 bits.
+struct DeviceRingPlan {
+    const uint8_t *blob = nullptr;
+    const uint64_t *tileOffset = nullptr;     // nbTiles + 1
+    int nbTiles = 0, nbInterfaceTiles = 0;
+    int maxRows = 0, maxNodes = 0, maxEntries = 0;
+    unsigned maxHeadBytes = 0, maxTailBytes = 0;
+};
+size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan);
+cudaError_t ring_configure (int operatorID);
+cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,
+                         int threads, size_t smemBytes, const double *coord, double *values, double *prec,
+                         const int *checkBounds, int nbNodes, int fusePrec, cudaStream_t stream);
 
 }  // namespace mfb
 

@@ -1,0 +1,343 @@
+// RING path: write-once assembly (+ fused preconditioner) that walks the ring of elements around
+// every mesh edge straight from the node coordinates (host/ring_plan.h, csrc/ring_math.h).
+//
+// The TILED kernel is bound by shared-memory bandwidth: 12 coefficients stored per tile element,
+// 48 bytes gathered per contribution, every border element recomputed in ~2.2 tiles.  Here a lane
+// owns a mesh EDGE {i, j}: it keeps x_i and d = x_j - x_i in registers, loads ONE node (24 bytes)
+// per element of the ring, rebuilds the two gradients from the coordinates (two cross products,
+// one reciprocal) and accumulates A_ij; an edge inside the tile yields both K_ij and K_ji = K_ij^T.
+// There are no coefficient planes and no diagonal pass: the diagonal block of a row is minus the sum
+// of the row's off-diagonal blocks (element matrices have zero row sums) and is formed while the row
+// streams out of the slab.
+//
+// Per tile:
+//   0. plan record by TMA (cp.async.bulk + mbarrier): the HEAD of tile t+1 (header, row table, node
+//      list) is fetched at the start of tile t, the TAIL (batches, jobs, ring codes) and the
+//      coordinates (cp.async) of tile t+1 while tile t is in its write-out;
+//   1. job phase: one lane per edge, 32 jobs per warp batch, ring codes 8 to a 64-bit word;
+//      finished 3x3 blocks go to the tile-wide slab at the slots of their CSR entries;
+//   2. write-out: one warp per row, 27 lanes = 3 entries x 9 components copy the row's slab run to
+//      global memory as contiguous 216-byte pieces and sum it; lanes 0..8 store the diagonal entry;
+//   3. fused mode: one lane per row of the warp masks / inverts the diagonal block into prec
+//      (prec_init + prec_inversion, src/preconditioner.cc:25-87, src/Fortran/elasclpr.f:19-53).
+// Every CSR entry is written exactly once by a plain store; the summation order is fixed by the plan.
+#include "kernels.cuh"
+#include "device_math.cuh"
+#include "ring_math.h"
+
+namespace mfb {
+
+namespace {
+
+static_assert (sizeof (RingTileHeader) == 32 && sizeof (RingRow) == 16 && sizeof (RingBatch) == 8,
+               "plan records are copied to the device verbatim");
+
+struct RingArgs {
+    DeviceRingPlan plan;
+    const double *coord;
+    double *values;
+    double *prec;
+    const int *checkBounds;
+    int nbNodes;
+    int fusePrec;
+    int firstTile, lastTile;      // [firstTile, lastTile)
+};
+
+// tileOffset entries: byte offset of the record in the low 48 bits, (head bytes / 16) above
+__device__ __forceinline__ uint64_t ring_record_offset (uint64_t packed) { return packed & 0xFFFFFFFFFFFFull; }
+__device__ __forceinline__ unsigned ring_record_head_bytes (uint64_t packed) { return (unsigned)(packed >> 48) << 4; }
+
+__device__ __forceinline__ unsigned ring_smem_u32 (const void *p) { return (unsigned)__cvta_generic_to_shared (p); }
+
+__device__ __forceinline__ void ring_mbar_init (uint64_t *bar, unsigned count)
+{
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ring_smem_u32 (bar)), "r"(count) : "memory");
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void ring_mbar_expect_tx (uint64_t *bar, unsigned bytes)
+{
+    asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ring_smem_u32 (bar)), "r"(bytes) : "memory");
+}
+
+// Bounded wait: a protocol bug must trap instead of hanging the device.
+__device__ __forceinline__ void ring_mbar_wait (uint64_t *bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (long spin = 0; spin < (1l << 22); spin++) {
+        asm volatile (
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(ring_smem_u32 (bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap ();
+}
+
+// TMA bulk copy global -> shared, completion counted on `bar` (SASS: UBLKCP).
+__device__ __forceinline__ void ring_bulk_load (void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                  :: "r"(ring_smem_u32 (dst)), "l"(src), "r"(bytes), "r"(ring_smem_u32 (bar)) : "memory");
+}
+
+__device__ __forceinline__ void ring_cp_async_f64 (double *dst, const double *src)
+{
+    asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(ring_smem_u32 (dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ring_cp_async_wait_all () { asm volatile ("cp.async.wait_all;" ::: "memory"); }
+
+__host__ __device__ __forceinline__ unsigned ring_align128 (unsigned x) { return (x + 127u) & ~127u; }
+
+template <int OPDIM>
+__global__ void __launch_bounds__(256, 3)
+ring_assembly_kernel (const RingArgs args)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const DeviceRingPlan &P = args.plan;
+    const int tid = threadIdx.x, nThreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nWarps = nThreads >> 5;
+
+    // shared memory: [head 0][head 1][tail][X Y Z][slab][diagonal blocks][3 mbarriers]
+    const unsigned headBytes = ring_align128 (P.maxHeadBytes), tailBytes = ring_align128 (P.maxTailBytes);
+    const int planeStride = (P.maxNodes + 15) & ~15;                  // planes start on a 128-byte line: bank = id mod 16
+    unsigned char *sHead0 = smemRaw, *sTail = smemRaw + 2 * headBytes;
+    double *sX = reinterpret_cast<double*> (sTail + tailBytes), *sY = sX + planeStride, *sZ = sY + planeStride;
+    double *slab = sZ + planeStride;
+    double *sDiag = slab + (((size_t)P.maxEntries * OPDIM + 15) & ~(size_t)15);
+    uint64_t *bars = reinterpret_cast<uint64_t*> (sDiag + (((size_t)P.maxRows * OPDIM + 1) & ~(size_t)1));
+    uint64_t *headFull = bars, *tailFull = bars + 2;                  // headFull[2], tailFull
+
+    if (tid == 0) { ring_mbar_init (headFull, 1); ring_mbar_init (headFull + 1, 1); ring_mbar_init (tailFull, 1); }
+    __syncthreads ();
+
+    const int firstTile = args.firstTile + blockIdx.x, tileStep = gridDim.x;
+    auto fetch_head = [&] (uint64_t packed, int k) {                  // thread 0 only
+        const unsigned bytes = ring_record_head_bytes (packed);
+        ring_mbar_expect_tx (headFull + (k & 1), bytes);
+        ring_bulk_load (sHead0 + (k & 1) * headBytes, P.blob + ring_record_offset (packed), bytes, headFull + (k & 1));
+    };
+    auto fetch_tail = [&] (uint64_t packed, const unsigned char *head) {   // thread 0 only, `head` has landed
+        const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
+        const unsigned bytes = h.blobBytes - h.headBytes;
+        ring_mbar_expect_tx (tailFull, bytes);                           // zero bytes: the phase completes at once
+        if (bytes) ring_bulk_load (sTail, P.blob + ring_record_offset (packed) + h.headBytes, bytes, tailFull);
+    };
+    auto gather_coords = [&] (const unsigned char *head) {            // all threads, asynchronous
+        const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
+        const int *nodes = reinterpret_cast<const int*> (head + h.offNodes);
+        for (int n = tid; n < h.nbNodes; n += nThreads) {
+            const double *q = args.coord + (size_t)nodes[n] * 3;
+            ring_cp_async_f64 (sX + n, q); ring_cp_async_f64 (sY + n, q + 1); ring_cp_async_f64 (sZ + n, q + 2);
+        }
+    };
+
+    // thread 0 keeps the packed offsets of this tile and the next in registers and loads the one after
+    // that a whole tile ahead, so that issuing the copies never waits on global memory
+    uint64_t offCur = 0, offNext = 0;
+    if (tid == 0 && firstTile < args.lastTile) {
+        offCur = P.tileOffset[firstTile];
+        if (firstTile + tileStep < args.lastTile) offNext = P.tileOffset[firstTile + tileStep];
+    }
+    // prologue: head, tail and coordinates of this CTA's first tile
+    if (firstTile < args.lastTile) {
+        if (tid == 0) fetch_head (offCur, 0);
+        ring_mbar_wait (headFull, 0);
+        if (tid == 0) fetch_tail (offCur, sHead0);
+        gather_coords (sHead0);
+        ring_cp_async_wait_all ();
+    }
+    __syncthreads ();
+
+    int k = 0;
+    for (int tile = firstTile; tile < args.lastTile; tile += tileStep, k++) {
+        const unsigned char *sHead = sHead0 + (k & 1) * headBytes;
+        const RingTileHeader &hdr = *reinterpret_cast<const RingTileHeader*> (sHead);
+        const bool hasNext = tile + tileStep < args.lastTile;
+        // ---- 0. the next tile's head starts travelling ----------------------------------------
+        uint64_t offAfter = 0;
+        if (tid == 0) {
+            if (tile + 2 * tileStep < args.lastTile) offAfter = P.tileOffset[tile + 2 * tileStep];   // used next iteration
+            if (hasNext) fetch_head (offNext, k + 1);
+        }
+        const int nbRows = hdr.nbRows, nbBatches = hdr.nbBatches;
+        const RingRow *sRows = reinterpret_cast<const RingRow*> (sHead + sizeof (RingTileHeader));
+        const RingBatch *batches = reinterpret_cast<const RingBatch*> (sTail);
+        const uint64_t *jobs = reinterpret_cast<const uint64_t*> (sTail + (hdr.offJobs - hdr.headBytes));
+        const uint64_t *codes = reinterpret_cast<const uint64_t*> (sTail + (hdr.offCodes - hdr.headBytes));
+
+        // ---- 1. job phase: one lane per mesh edge ----------------------------------------------
+        ring_mbar_wait (tailFull, k & 1);
+        for (int b = warp; b < nbBatches; b += nWarps) {
+            const RingBatch rb = batches[b];
+            const uint64_t job = jobs[b * 32 + lane];
+            const int i = (int)(job & 0xFF), j = (int)((job >> 8) & 0xFF);
+            const int sIJ = (int)((job >> 16) & 0xFFFF), sJI = (int)((job >> 32) & 0xFFFF);
+            const double xi[3] = {sX[i], sY[i], sZ[i]};
+            const double d[3] = {sX[j] - xi[0], sY[j] - xi[1], sZ[j] - xi[2]};
+            double acc[OPDIM], u[3] = {0.0, 0.0, 0.0};
+            #pragma unroll
+            for (int q = 0; q < OPDIM; q++) acc[q] = 0.0;
+            bool have = false;
+            const uint64_t *cw = codes + rb.codeBase + lane;
+            int remaining = rb.nbSteps;
+            for (int wd = 0; wd < rb.nbWords; wd++, remaining -= 8) {
+                uint64_t word = cw[wd * 32];
+                const int n = min (remaining, 8);
+                for (int q = 0; q < n; q++, word >>= 8) {
+                    const int id = (int)(word & 0xFF);
+                    if (id >= kRingBreak) {                 // idle step, or the chain of elements is interrupted
+                        if (id == kRingBreak) have = false;
+                        continue;
+                    }
+                    const double w[3] = {sX[id] - xi[0], sY[id] - xi[1], sZ[id] - xi[2]};
+                    if (have) ring_accumulate<OPDIM> (d, u, w, acc);
+                    u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
+                    have = true;
+                }
+            }
+            if (sIJ != 0xFFFF) {
+                if (OPDIM == 1) {
+                    slab[sIJ] = acc[0];
+                    if (sJI != 0xFFFF) slab[sJI] = acc[0];
+                }
+                else {
+                    double blk[9];
+                    ring_block (acc, blk);
+                    double *dst = slab + sIJ * 9;
+                    #pragma unroll
+                    for (int q = 0; q < 9; q++) dst[q] = blk[q];
+                    if (sJI != 0xFFFF) {
+                        double *dstT = slab + sJI * 9;
+                        #pragma unroll
+                        for (int q = 0; q < 9; q++) dstT[3 * (q % 3) + q / 3] = blk[q];
+                    }
+                }
+            }
+        }
+        __syncthreads ();      // the slab is complete; tail and coordinates of this tile are dead
+
+        // ---- 2. next tile's tail (TMA) and coordinates (cp.async) start travelling ---------------
+        if (hasNext) {
+            const unsigned char *nextHead = sHead0 + ((k + 1) & 1) * headBytes;
+            ring_mbar_wait (headFull + ((k + 1) & 1), ((k + 1) >> 1) & 1);
+            if (tid == 0) fetch_tail (offNext, nextHead);
+            gather_coords (nextHead);
+        }
+
+        // ---- 3. write-out: one warp per row, the diagonal entry is minus the sum of the run -------
+        for (int r = warp; r < nbRows; r += nWarps) {
+            const RingRow rr = sRows[r];
+            const int len = rr.len, diagOff = rr.diagOff;             // 0xFFFF never equals a position
+            double *out = args.values + (size_t)rr.valueStart * OPDIM;
+            const double *src = slab + (size_t)rr.localStart * OPDIM;
+            if (OPDIM == 1) {
+                double a = 0.0;
+                for (int q = lane; q < len; q += 32) {
+                    if (q != diagOff) { const double v = src[q]; a += v; out[q] = v; }
+                }
+                #pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync (0xffffffffu, a, off);
+                const double diag = 0.0 - a;
+                if (lane == 0) {
+                    if (diagOff != 0xFFFF) out[diagOff] = diag;
+                    sDiag[r] = diag;
+                }
+            }
+            else {
+                const int grp = lane / 9, comp = lane - 9 * grp;      // lanes 27..31 idle
+                double a = 0.0;
+                if (grp < 3) {
+                    for (int q = grp; q < len; q += 3) {
+                        if (q != diagOff) { const double v = src[q * 9 + comp]; a += v; out[q * 9 + comp] = v; }
+                    }
+                }
+                const double a1 = __shfl_down_sync (0xffffffffu, a, 9), a2 = __shfl_down_sync (0xffffffffu, a, 18);
+                const double diag = 0.0 - ((a + a1) + a2);
+                if (lane < 9) {
+                    if (diagOff != 0xFFFF) out[diagOff * 9 + lane] = diag;
+                    sDiag[r * 9 + lane] = diag;
+                }
+            }
+        }
+        // ---- 4. fused preconditioner: lane t of a warp takes the t-th row the warp wrote out ------
+        if (args.fusePrec) {
+            __syncwarp ();
+            const int r = warp + lane * nWarps;
+            if (r < nbRows) {
+                const RingRow rr = sRows[r];
+                const int node = rr.node & 0x7fffffff;
+                const bool isInterface = rr.node < 0, hasDiag = rr.diagOff != 0xFFFF;
+                if (OPDIM == 1) {
+                    const double dgl = sDiag[r];
+                    args.prec[node] = isInterface ? dgl : 1.0 / dgl;
+                }
+                else {
+                    double b[9];
+                    #pragma unroll
+                    for (int q = 0; q < 9; q++) b[q] = sDiag[r * 9 + q];
+                    if (!isInterface) {
+                        int mx = 0, my = 0, mz = 0;
+                        if (args.checkBounds) {
+                            mx = __ldg (args.checkBounds + node);
+                            my = __ldg (args.checkBounds + (size_t)args.nbNodes + node);
+                            mz = __ldg (args.checkBounds + 2 * (size_t)args.nbNodes + node);
+                        }
+                        mask_block (b, mx, my, mz);
+                        if (hasDiag) invert3_lu (b);
+                    }
+                    double *dst = args.prec + (size_t)node * 9;
+                    #pragma unroll
+                    for (int q = 0; q < 9; q++) dst[q] = b[q];
+                }
+            }
+        }
+
+        offCur = offNext; offNext = offAfter;
+        ring_cp_async_wait_all ();  // next tile's coordinates are in
+        __syncthreads ();           // every reader of this tile's slab / head is done
+    }
+}
+
+template <class K>
+cudaError_t ring_opt_in (K kernel)
+{
+    // The attribute belongs to the kernel, not to a context: always opt in to the device maximum.
+    return cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+}  // namespace
+
+size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
+{
+    const int opDim = operatorID == 0 ? 1 : 9;
+    const size_t planeStride = ((size_t)plan.maxNodes + 15) & ~(size_t)15;
+    const size_t doubles = 3 * planeStride + (((size_t)plan.maxEntries * opDim + 15) & ~(size_t)15) +
+                           (((size_t)plan.maxRows * opDim + 1) & ~(size_t)1);
+    return 2 * (size_t)ring_align128 (plan.maxHeadBytes) + ring_align128 (plan.maxTailBytes) + doubles * sizeof (double) +
+           3 * sizeof (uint64_t);
+}
+
+cudaError_t ring_configure (int operatorID)
+{
+    return operatorID == 0 ? ring_opt_in (ring_assembly_kernel<1>) : ring_opt_in (ring_assembly_kernel<9>);
+}
+
+cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,
+                         int threads, size_t smemBytes, const double *coord, double *values, double *prec,
+                         const int *checkBounds, int nbNodes, int fusePrec, cudaStream_t stream)
+{
+    if (nbTiles <= 0) return cudaSuccess;
+    RingArgs args;
+    args.plan = plan; args.coord = coord; args.values = values; args.prec = prec;
+    args.checkBounds = checkBounds; args.nbNodes = nbNodes; args.fusePrec = fusePrec;
+    args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
+    const int grid = std::max (1, std::min (ctas, nbTiles));
+    if (operatorID == 0) ring_assembly_kernel<1><<<grid, threads, smemBytes, stream>>> (args);
+    else                 ring_assembly_kernel<9><<<grid, threads, smemBytes, stream>>> (args);
+    return cudaGetLastError ();
+}
+
+}  // namespace mfb

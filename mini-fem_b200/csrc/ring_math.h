@@ -1,0 +1,96 @@
+// Arithmetic of the RING path (host/ring_plan.h), shared verbatim by the sm_100a kernel
+// (csrc/kernels_ring.cu) and by the host replay the tests run (tools/ring_replay.cc).
+#ifndef MFB_RING_MATH_H
+#define MFB_RING_MATH_H
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define MFB_RM __host__ __device__ __forceinline__
+#else
+#define MFB_RM inline
+#endif
+
+#ifndef MFB_RING_FAST_RCP
+#define MFB_RING_FAST_RCP 1
+#endif
+
+namespace mfb {
+
+// 1 / x for a normal, finite, non-zero x.  Device: MUFU.RCP64H seed (rcp.approx.ftz.f64, about
+// 20 good bits, low mantissa word zero) and two Newton steps, 4 DFMA instead of the ~10 FP64
+// instructions plus slow-path branch of an IEEE division; the result is within an ulp or two,
+// far inside the 1e-12 the values are held to.  The host replay starts from the same kind of
+// 20-bit seed so that the tests exercise the same iteration.
+MFB_RM double ring_rcp (double x)
+{
+#if MFB_RING_FAST_RCP
+    double r;
+#if defined(__CUDA_ARCH__)
+    asm ("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#else
+    r = 1.0 / x;
+    uint64_t bits;
+    memcpy (&bits, &r, 8);
+    bits &= 0xFFFFFFFF00000000ull;      // sign, exponent, upper 20 mantissa bits
+    memcpy (&r, &bits, 8);
+#endif
+    double e = fma (-x, r, 1.0);
+    r = fma (r, e, r);
+    e = fma (-x, r, 1.0);
+    r = fma (r, e, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// One element (i, j, p, q) of the ring around the mesh edge (i, j).  d = x_j - x_i, u = x_p - x_i,
+// w = x_q - x_i.  Face normals n_j = u x w (opposite j) and n_i = (u - d) x (w - d)
+// = n_j + (w - u) x d (opposite i); det = n_j . d = n_i . d = 6 V (signed).  The gradients the
+// reference computes in elem_coef_seq (src/assembly.cc:85-121) are grad_j = n_j / det and
+// grad_i = -n_i / det, so the element adds grad_i grad_j^T = -(n_i n_j^T) / det^2 to A_ij;
+// the order of p and q does not matter (both normals and det change sign).
+// OPDIM 9: acc = the 3x3 sum A_ij (row component from node i); OPDIM 1: acc[0] = sum of
+// grad_i . grad_j, the Laplacian entry (src/assembly.cc:539-541).
+template <int OPDIM>
+MFB_RM void ring_accumulate (const double d[3], const double u[3], const double w[3], double acc[OPDIM])
+{
+    const double njx = u[1] * w[2] - u[2] * w[1];
+    const double njy = u[2] * w[0] - u[0] * w[2];
+    const double njz = u[0] * w[1] - u[1] * w[0];
+    const double ex = w[0] - u[0], ey = w[1] - u[1], ez = w[2] - u[2];
+    const double nix = njx + (ey * d[2] - ez * d[1]);
+    const double niy = njy + (ez * d[0] - ex * d[2]);
+    const double niz = njz + (ex * d[1] - ey * d[0]);
+    const double det = njx * d[0] + njy * d[1] + njz * d[2];
+    const double r = -ring_rcp (det * det);
+    if (OPDIM == 1) {
+        acc[0] += r * (nix * njx + niy * njy + niz * njz);
+    }
+    else {
+        const double mx = r * nix, my = r * niy, mz = r * niz;
+        acc[0] += mx * njx; acc[1 % OPDIM] += mx * njy; acc[2 % OPDIM] += mx * njz;
+        acc[3 % OPDIM] += my * njx; acc[4 % OPDIM] += my * njy; acc[5 % OPDIM] += my * njz;
+        acc[6 % OPDIM] += mz * njx; acc[7 % OPDIM] += mz * njy; acc[8 % OPDIM] += mz * njz;
+    }
+}
+
+// CSR block of the elasticity operator from A = sum grad_i grad_j^T (src/assembly.cc:386-409):
+// K = 1.25 A + tr(A) I, row-major.
+MFB_RM void ring_block (const double acc[9], double k[9])
+{
+    const double tr = acc[0] + acc[4] + acc[8];
+    k[0] = 1.25 * acc[0] + tr; k[1] = 1.25 * acc[1]; k[2] = 1.25 * acc[2];
+    k[3] = 1.25 * acc[3]; k[4] = 1.25 * acc[4] + tr; k[5] = 1.25 * acc[5];
+    k[6] = 1.25 * acc[6]; k[7] = 1.25 * acc[7]; k[8] = 1.25 * acc[8] + tr;
+}
+
+// position of component k = 3a + b in the transposed block
+MFB_RM int ring_transposed (int k) { return 3 * (k % 3) + k / 3; }
+
+}  // namespace mfb
+
+#endif

@@ -1,0 +1,108 @@
+// Plan of the RING path: write-once assembly that walks the ring of elements around every
+// mesh edge straight from the node coordinates.
+//
+// The TILED path (tile_plan.h) computes the 12 gradient coefficients of every tile element into
+// shared-memory planes and lets one lane per CSR entry gather 48 bytes per contribution; ncu
+// shows it bound by shared-memory bandwidth.  The RING path keeps the tiles
+// (same Morton cut, cut_node_tiles) but removes the coefficient planes:
+//
+//   * a JOB is one mesh edge {i, j} with i owned by the tile.  Its lane walks the nodes of the
+//     edge's link (the polygon r_0, r_1, ... around the edge: element k = (i, j, r_k, r_k+1)),
+//     loading ONE node (24 bytes) per element, and rebuilds the two gradients it needs from the
+//     coordinates: with d = x_j - x_i, u = x_p - x_i, w = x_q - x_i,
+//         n_j = u x w,  n_i = n_j + (w - u) x d,  det = n_j . d  (= 6 V, signed),
+//         grad(lambda_j) = n_j / det,  grad(lambda_i) = -n_i / det      (src/assembly.cc:85-121
+//     computes exactly these gradients as cross products over vol), so the element adds
+//         A_ij += -(n_i n_j^T) / det^2                                   (src/assembly.cc:386-409)
+//     and the CSR entry is K_ij = 1.25 A_ij + tr(A_ij) I as on the TILED path;
+//   * when j is owned by the same tile the job also writes K_ji = K_ij^T: every interior edge
+//     is computed once;
+//   * jobs are independent of rows, so they are sorted by ring length and packed 32 to a warp;
+//   * finished blocks go to a tile-wide shared slab laid out like the tile's CSR rows; the
+//     write-out streams each row to global memory as one contiguous run and sums it on the way:
+//     the element matrices have zero row sums (the four gradients of an element add up to
+//     zero), hence K_ii = -sum_{j != i} K_ij — the diagonal entry and the preconditioner block
+//     come from the run that is being written anyway.
+//
+// Per tile the plan is one contiguous record: HEAD = header, row table, node list (needed one
+// tile ahead for the coordinate prefetch and during the write-out), TAIL = batches, jobs, ring
+// codes (needed by the job phase only).
+#ifndef MFB_RING_PLAN_H
+#define MFB_RING_PLAN_H
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mfb {
+
+constexpr int kRingIdle  = 0xFF;   // code byte: nothing to do in this step
+constexpr int kRingBreak = 0xFE;   // code byte: the chain of elements is interrupted, the next node starts a new one
+constexpr int kRingMaxNodes = 254; // tile-local node ids 0 .. 253
+
+struct RingTileHeader {            // 32 bytes
+    uint16_t nbRows, nbNodes, nbBatches, nbEntries, hasInterface, pad0;
+    uint32_t offNodes;             // int[nbNodes]: 0-based global ids by tile-local id (holes name a valid node)
+    uint32_t headBytes;            // bytes [0, headBytes) = header + rows + nodes; the tail starts here with RingBatch[nbBatches]
+    uint32_t offJobs;              // uint64[32 * nbBatches]
+    uint32_t offCodes;             // uint64[]: per batch [word][32 lanes], 8 code bytes per word, low byte first
+    uint32_t blobBytes;
+};
+
+struct RingRow {                   // 16 bytes per owned row, right after the header
+    int node;                      // 0-based global node id; bit 31 set = interface node
+    int valueStart;                // nodeToNodeRow[node]
+    uint16_t localStart;           // slab slot of the row's first entry
+    uint16_t len;                  // entries of the row
+    uint16_t diagOff;              // position of the diagonal entry inside the row, 0xFFFF = none
+    uint16_t pad0;
+};
+
+struct RingBatch {                 // 8 bytes per warp batch of 32 jobs
+    uint32_t codeBase;             // first code word of the batch (index into the codes section)
+    uint16_t nbSteps;              // code bytes to walk (longest job of the batch)
+    uint16_t nbWords;              // ceil (nbSteps / 8)
+};
+
+// job word: i | j << 8 | slotIJ << 16 | slotJI << 32; slots are tile-local entry indices
+// (slab position = slot * operatorDim), 0xFFFF = no such block; an idle lane has both 0xFFFF.
+inline uint64_t ring_job (int i, int j, int slotIJ, int slotJI)
+{
+    return (uint64_t)(i & 0xFF) | ((uint64_t)(j & 0xFF) << 8) | ((uint64_t)(slotIJ & 0xFFFF) << 16) | ((uint64_t)(slotJI & 0xFFFF) << 32);
+}
+
+struct RingPlanLimits {
+    int maxRows = 36;              // rows per tile (<= 255)
+    int maxEntries = 576;          // CSR entries per tile: the slab holds maxEntries * operatorDim doubles
+    int maxNodes = kRingMaxNodes;  // tile-local nodes (<= 254: one code byte per node)
+    bool bankAware = true;         // node numbering + ring rotation chosen against bank conflicts
+    int refinePasses = 2;          // renumber-and-rotate rounds after the first numbering
+};
+
+struct RingPlan {
+    int nbTiles = 0, nbInterfaceTiles = 0;
+    int maxRows = 0, maxNodes = 0, maxEntries = 0, maxBatches = 0;
+    uint32_t maxBlobBytes = 0, maxHeadBytes = 0, maxTailBytes = 0;
+    int64_t nbJobs = 0, nbSymmetricJobs = 0, nbRingSteps = 0, nbPaddedSteps = 0, nbBreaks = 0;
+    // shared-memory model (wavefronts of 128 bytes, one per half-warp LDS.64 / STS.64 without conflicts)
+    int64_t gatherWavefronts = 0, gatherIdeal = 0, slabWriteWavefronts = 0, slabWriteIdeal = 0;
+    std::vector<uint64_t> tileOffset;   // nbTiles + 1 byte offsets into `blob`
+    std::vector<uint8_t> blob;
+    const RingTileHeader *header (int t) const { return reinterpret_cast<const RingTileHeader*> (blob.data () + tileOffset[t]); }
+};
+
+// isInterface may be null.  Returns 0, or -1 with `error` set.
+int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *row, const int *col,
+                     const double *coord, const uint8_t *isInterface, const RingPlanLimits &limits,
+                     RingPlan &plan, std::string &error);
+
+// Structural replay: rows tile the CSR; every off-diagonal CSR entry is written by exactly one job
+// (as its (i,j) or its transposed (j,i) block); the consecutive node pairs of a job's chains are
+// distinct elements containing {i, j, p, q}; every element's 12 ordered off-diagonal node pairs
+// (src/assembly.cc:382-412) are covered exactly once.  Returns 0 or -1 with `error` set.
+int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *elemToNode,
+                      const int *row, const int *col, std::string &error);
+
+}  // namespace mfb
+
+#endif

@@ -181,26 +181,11 @@ void order_diag_half_warp (std::vector<uint16_t> *rowLists, int nbRows, int stri
 
 }  // namespace
 
-int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *row,
-                     const int *col, const double *coord, const uint8_t *isInterface,
-                     const TilePlanLimits &lim, TilePlan &plan, std::string &error)
+int cut_node_tiles (int nbNodes, int nbElem, const int *elemToNode, const int *row, const double *coord,
+                    const int *n2eIndexPtr, const int *n2eValuePtr, const TileCutLimits &lim,
+                    std::vector<int> &nodeOrder, std::vector<int> &tileStart, std::string &error)
 {
-    plan = TilePlan ();
-    if (lim.maxRows < 1 || lim.maxRows > 255 || lim.maxElems < 1 || lim.maxElems > 4064 ||
-        lim.maxNodesRef < 4 || lim.maxNodesRef > 65535 || lim.maxEntries < 1 || lim.maxEntries > 65535) {
-        error = "tile plan limits out of range";
-        return -1;
-    }
-    // plane stride = 4 (mod 16): the 4 local-node planes of element e occupy the 4 banks of the
-    // coset e mod 4 (8-byte words, 16 bank pairs); room for the ids (<= maxElems + 3 with the
-    // coset numbering's holes) and for the 16 all-zero slots the padding codes point at
-    const int stride = tile_plan_stride (lim.maxElems);
-    plan.elemStride = stride;
-    plan.laplacian = lim.laplacian;
-
-    std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
-    node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
-
+    const int *n2eIndex = n2eIndexPtr, *n2eValue = n2eValuePtr;
     // ---- 1. spatial order of the nodes -------------------------------------------
     double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
     if (nbNodes > 0) {
@@ -225,7 +210,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
     std::sort (order.begin (), order.end ());
 
     // ---- 2. greedy cut under the shared-memory caps -------------------------------
-    std::vector<int> tileStart;          // offsets into `order`
+    tileStart.clear ();
     {
         std::vector<int> elemStamp ((size_t)nbElem, -1), nodeStamp ((size_t)nbNodes, -1);
         int rows = 0, elems = 0, refs = 0, entries = 0, tile = 0;
@@ -270,6 +255,38 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         tileStart.push_back (nbNodes);
         if (nbNodes == 0) tileStart.assign (1, 0);
     }
+    nodeOrder.resize ((size_t)nbNodes);
+    for (int at = 0; at < nbNodes; at++) nodeOrder[at] = order[at].second;
+    return 0;
+}
+
+int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *row,
+                     const int *col, const double *coord, const uint8_t *isInterface,
+                     const TilePlanLimits &lim, TilePlan &plan, std::string &error)
+{
+    plan = TilePlan ();
+    if (lim.maxRows < 1 || lim.maxRows > 255 || lim.maxElems < 1 || lim.maxElems > 4064 ||
+        lim.maxNodesRef < 4 || lim.maxNodesRef > 65535 || lim.maxEntries < 1 || lim.maxEntries > 65535) {
+        error = "tile plan limits out of range";
+        return -1;
+    }
+    // plane stride = 4 (mod 16): the 4 local-node planes of element e occupy the 4 banks of the
+    // coset e mod 4 (8-byte words, 16 bank pairs); room for the ids (<= maxElems + 3 with the
+    // coset numbering's holes) and for the 16 all-zero slots the padding codes point at
+    const int stride = tile_plan_stride (lim.maxElems);
+    plan.elemStride = stride;
+    plan.laplacian = lim.laplacian;
+
+    std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
+    node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
+
+    // ---- 1 + 2. spatial order of the nodes, greedy cut under the shared-memory caps ----
+    std::vector<int> nodeOrder, tileStart;
+    {
+        TileCutLimits cut = { lim.maxRows, lim.maxElems, lim.maxNodesRef, lim.maxEntries };
+        if (cut_node_tiles (nbNodes, nbElem, elemToNode, row, coord, n2eIndex.data (), n2eValue.data (), cut,
+                            nodeOrder, tileStart, error) != 0) return -1;
+    }
     const int nbTiles = (int)tileStart.size () - 1;
 
     // ---- 3. per-tile tables (independent) ------------------------------------------
@@ -287,7 +304,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
             TileScratch &s = scratch[t];
             const int first = tileStart[t], nbRows = tileStart[t + 1] - first;
             for (int r = 0; r < nbRows; r++) {                       // owned rows first
-                const int n = order[first + r].second;
+                const int n = nodeOrder[first + r];
                 nodeLocal[n] = r;
                 s.nodes.push_back (n);
             }

@@ -108,6 +108,14 @@ MFB_HD int lap_pair_slot (int a, int b, int e, int PS)
     return (2 * colour + ((a && b) ? 1 : 0)) * PS + 4 * colour + e;
 }
 MFB_HD int lap_diag_slot (int a, int e, int PS) { return (6 + a) * PS + 4 * a + e; }
+// Steps 1-2 of every write-once plan: nodes in Morton order of their coordinates, cut greedily
+// into tiles under the caps.  nodeOrder[tileStart[t] .. tileStart[t+1]) = the rows tile t owns.
+// n2eIndex / n2eValue = node_to_elem (mesh_topology.h).
+struct TileCutLimits { int maxRows, maxElems, maxNodesRef, maxEntries; };
+int cut_node_tiles (int nbNodes, int nbElem, const int *elemToNode, const int *row, const double *coord,
+                    const int *n2eIndex, const int *n2eValue, const TileCutLimits &limits,
+                    std::vector<int> &nodeOrder, std::vector<int> &tileStart, std::string &error);
+
 //
 // isInterface may be null.  Returns 0, or -1 with `error` set (e.g. one node alone
 // exceeds a cap, or the CSR lacks a pair).

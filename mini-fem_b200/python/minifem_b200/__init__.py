@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))            # mini-fem_b200/
 LIB_PATH = os.environ.get("MFB_LIBRARY") or os.path.join(PKG_ROOT, "libminifem_b200.so")   # MFB_LIBRARY: an experimental build
 
-PATH_TILED, PATH_ATOMIC, PATH_COLOR = 0, 1, 2
-PATH_NAMES = {"tiled": PATH_TILED, "atomic": PATH_ATOMIC, "color": PATH_COLOR}
+PATH_TILED, PATH_ATOMIC, PATH_COLOR, PATH_RING = 0, 1, 2, 3
+PATH_NAMES = {"tiled": PATH_TILED, "atomic": PATH_ATOMIC, "color": PATH_COLOR, "ring": PATH_RING}
 COMM_ID_BYTES = 128
 
 
@@ -94,6 +94,7 @@ lib.mfb_ctx_halo_add_host.argtypes = [C.c_void_p, C.c_void_p]
 lib.mfb_ctx_prec_inversion_interface.argtypes = [C.c_void_p]
 lib.mfb_ctx_run_timed.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
 lib.mfb_tile_plan_selfcheck.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, C.POINTER(C.c_int64)]
+lib.mfb_ring_plan_selfcheck.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, C.POINTER(C.c_int64)]
 lib.mfb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
 lib.mfb_host_free.argtypes = [C.c_void_p]
 lib.mfb_host_free.restype = None
@@ -120,7 +121,7 @@ DECLARED_SYMBOLS = [
     "mfb_ctx_stream", "mfb_ctx_stage_ms", "mfb_ctx_launch_count", "mfb_ctx_device_bytes",
     "mfb_ctx_plan_stats", "mfb_comm_unique_id", "mfb_ctx_comm_init", "mfb_ctx_halo_pack_host",
     "mfb_ctx_halo_add_host", "mfb_ctx_assembly_fused", "mfb_ctx_prec_inversion_interface", "mfb_ctx_run_timed",
-    "mfb_tile_plan_selfcheck", "mfb_host_alloc",
+    "mfb_tile_plan_selfcheck", "mfb_ring_plan_selfcheck", "mfb_host_alloc",
     "mfb_host_free", "mfb_device_count",
     "mfb_device_create_nodeToNode", "mfb_device_create_elemToEdge", "mfb_device_coloring_creation",
     "mfb_ctx_norms", "mfb_ctx_iteration_norms_host",

@@ -1,0 +1,183 @@
+"""RING path without a GPU: the plan's structural self-check through the C ABI, and a host replay of
+the plan (tools/ring_replay.cc — lane by lane, in the kernel's order, with the arithmetic header
+the kernel compiles) against the oracle.  This pins the plan format, the edge-ring formulation
+(gradients rebuilt from coordinates, one node per element), the transposed block of interior
+edges and the row-sum diagonal to the reference's numbers; the kernel itself is covered by the
+`-m gpu` tests (test_gpu_parity.py, path "ring")."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import minifem_b200 as mfb
+from helpers import RTOL, ArrayMesh, block_scaled_error, random_tet_mesh, row_scaled_error
+from oracle_lib import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ringlib():
+    lib = C.CDLL(os.path.join(ROOT, "tools", "libmfb_ringcheck.so"))
+    lib.mfb_ring_replay_error.restype = C.c_char_p
+    lib.mfb_ring_replay.argtypes = [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p] * 3
+    return lib
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def replay(lib, setup, rows=0, entries=0, bank_aware=1, interface=None):
+    m = setup.mesh
+    dim = setup.operatorDim
+    values = np.full(setup.nbEdges * dim, np.nan)
+    prec = np.full(m.nbNodes * dim, np.nan)
+    stats = np.zeros(16, np.int64)
+    keep = [np.ascontiguousarray(setup.elemToNode, np.int32), np.ascontiguousarray(setup.row, np.int32),
+            np.ascontiguousarray(setup.col, np.int32), np.ascontiguousarray(m.coord, np.float64),
+            np.ascontiguousarray(setup.checkBounds, np.int32)]
+    rc = lib.mfb_ring_replay(setup.operatorID, m.nbNodes, keep[0].size // 4, _p(keep[0]), _p(keep[1]), _p(keep[2]),
+                             _p(keep[3]), _p(keep[4]), _p(interface), rows, entries, bank_aware,
+                             _p(values), _p(prec), _p(stats))
+    assert rc == 0, lib.mfb_ring_replay_error().decode()
+    return values, prec, stats
+
+
+def check_against_oracle(oracle, setup, values, prec, interface=None):
+    want_v, want_p0, want_p = oracle.fem_iteration(setup)
+    dim = setup.operatorDim
+    assert row_scaled_error(values, want_v, setup.row, dim) <= RTOL
+    if interface is None:
+        assert block_scaled_error(prec, want_p, dim) <= RTOL
+    else:          # interface rows keep the raw diagonal block for the halo sum, the others are inverted
+        intf = interface.astype(bool)
+        got, raw, inv = prec.reshape(-1, dim), want_p0.reshape(-1, dim), want_p.reshape(-1, dim)
+        assert block_scaled_error(got[intf], raw[intf], dim) <= RTOL
+        assert block_scaled_error(got[~intf], inv[~intf], dim) <= RTOL
+
+
+@pytest.mark.parametrize("op", ["ela", "lap"])
+@pytest.mark.parametrize("grid,rows,entries", [((12, 10, 9), 0, 0), ((7, 6, 5), 16, 200), ((9, 9, 9), 64, 960), ((3, 2, 2), 1, 32)])
+def test_ring_replay_matches_oracle(ringlib, oracle, op, grid, rows, entries):
+    mesh = mfb.Mesh.generate(*grid, seed=5)
+    setup = mfb.Setup(mesh, op)
+    values, prec, stats = replay(ringlib, setup, rows, entries)
+    check_against_oracle(oracle, setup, values, prec)
+    # every off-diagonal CSR entry comes from one job, as its own or its transposed block
+    nb_offdiag = setup.nbEdges - mesh.nbNodes
+    assert stats[1] + stats[2] == nb_offdiag
+    assert stats[5] == 0                                   # a conforming mesh: one chain per edge
+    if rows:
+        assert stats[11] <= rows and stats[13] <= entries
+
+
+@pytest.mark.parametrize("op", ["ela", "lap"])
+def test_ring_replay_plain_order_and_shuffled_numbering(ringlib, oracle, op):
+    mesh = mfb.Mesh.generate(8, 7, 6, seed=3)
+    rng = np.random.default_rng(1)
+    nperm, eperm = rng.permutation(mesh.nbNodes), rng.permutation(mesh.nbElem)
+    coord = np.empty_like(mesh.coord).reshape(-1, 3)
+    coord[nperm] = mesh.coord.reshape(-1, 3)
+    e2n = np.empty_like(mesh.elemToNode).reshape(-1, 4)
+    e2n[eperm] = nperm[mesh.elemToNode.reshape(-1, 4) - 1] + 1
+    codes = np.empty_like(mesh.boundNodesCode)
+    codes[nperm] = mesh.boundNodesCode
+    shuffled = mfb.Setup(ArrayMesh(coord.ravel(), e2n.ravel(), mesh.nbNodes, codes), op)
+    for setup, bank in ((mfb.Setup(mesh, op), 0), (shuffled, 1)):
+        values, prec, _ = replay(ringlib, setup, bank_aware=bank)
+        check_against_oracle(oracle, setup, values, prec)
+
+
+@pytest.mark.parametrize("op", ["ela", "lap"])
+def test_ring_replay_random_tets(ringlib, oracle, op):
+    """Random 4-subsets: edge links are arbitrary graphs (several chains per edge, breaks), rows are
+    long, nodes can be isolated."""
+    rng = np.random.default_rng(12)
+    coord, e2n = random_tet_mesh(rng, 60, 150)
+    codes = rng.choice([0, 0, 0, 52, 53, 54, 10], size=60).astype(np.int32)
+    setup = mfb.Setup(ArrayMesh(coord, e2n, 60, codes), op)
+    values, prec, stats = replay(ringlib, setup, rows=8, entries=400)
+    check_against_oracle(oracle, setup, values, prec)
+    assert 6 * 150 <= stats[3] <= 12 * 150                 # an (element, edge) pair is visited once, or once per tile when the edge crosses tiles
+    coord, e2n = random_tet_mesh(rng, 25, 400)             # dense: many elements around every edge, chains with breaks
+    setup = mfb.Setup(ArrayMesh(coord, e2n, 25), op)
+    values, prec, stats = replay(ringlib, setup, rows=25, entries=640)
+    check_against_oracle(oracle, setup, values, prec)
+    assert stats[0] == 1 and stats[3] == 6 * 400 and stats[5] > 0
+
+
+def test_ring_replay_interface_rows_keep_raw_blocks(ringlib, oracle):
+    mesh = mfb.Mesh.generate(6, 6, 6, blocks=(2, 1, 1), rank=1, seed=2)
+    setup = mfb.Setup(mesh, "ela")
+    interface = np.zeros(mesh.nbNodes, np.uint8)
+    interface[mesh.intfNodes - 1] = 1
+    values, prec, _ = replay(ringlib, setup, interface=interface)
+    check_against_oracle(oracle, setup, values, prec, interface)
+
+
+def test_ring_plan_selfcheck_cabi():
+    """The structural check of the plan through the product library (no GPU)."""
+    mesh = mfb.Mesh.generate(6, 6, 6, blocks=(2, 1, 1), rank=0, seed=2)
+    s = mfb.Setup(mesh, "ela")
+    keep = [np.ascontiguousarray(mesh.coord), s.elemToNode, s.row, s.col, mesh.intfIndex, mesh.intfNodes, mesh.neighborsList]
+    p = mfb.Problem(1, mesh.nbElem, mesh.nbNodes, s.nbEdges, *[k.ctypes.data for k in keep[:4]], None, None, None, 0,
+                    2, 0, mesh.nbIntf, mesh.nbIntfNodes, *[k.ctypes.data for k in keep[4:]])
+    stats = (C.c_int64 * 12)()
+    assert mfb.lib.mfb_ring_plan_selfcheck(C.byref(p), 0, 0, stats) == 0, mfb.lib.mfb_last_error()
+    assert stats[1] + stats[2] == s.nbEdges - mesh.nbNodes
+    assert 0 < stats[11] <= stats[0]                       # tiles that own interface nodes come first
+    assert stats[6] >= stats[7] > 0 and stats[8] >= stats[9] > 0
+    # caps that a single node cannot meet are reported, not silently exceeded
+    assert mfb.lib.mfb_ring_plan_selfcheck(C.byref(p), 4, 3, stats) != 0
+    assert b"exceeds the tile caps" in mfb.lib.mfb_last_error()
+
+
+def test_ring_plan_rejects_degenerate_elements():
+    coord = np.arange(15, dtype=np.float64) ** 1.5
+    e2n = np.array([1, 2, 3, 4, 2, 3, 3, 5], np.int32)      # the second element names node 3 twice
+    mesh = ArrayMesh(coord, e2n, 5)
+    s = mfb.Setup(mesh, "ela")
+    keep = [np.ascontiguousarray(coord), s.elemToNode, s.row, s.col]
+    p = mfb.Problem(1, 2, 5, s.nbEdges, *[k.ctypes.data for k in keep], None, None, None, 0, 1, 0, 0, 0, None, None, None)
+    stats = (C.c_int64 * 12)()
+    assert mfb.lib.mfb_ring_plan_selfcheck(C.byref(p), 0, 0, stats) != 0
+    assert b"names a node twice" in mfb.lib.mfb_last_error()
+
+
+def test_ring_plan_property(ringlib, oracle):
+    """Random unstructured connectivity and caps, both operators: a plan that builds verifies and its
+    replay reproduces the oracle; caps are met or reported."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=30, deadline=None)
+    @given(seed=st.integers(0, 2**31 - 1), nbNodes=st.integers(4, 90), density=st.floats(0.5, 5.0),
+           rows=st.integers(1, 40), entries=st.integers(16, 700), operatorID=st.integers(0, 1))
+    def check(seed, nbNodes, density, rows, entries, operatorID):
+        rng = np.random.default_rng(seed)
+        nbElem = max(1, int(nbNodes * density))
+        coord, e2n = random_tet_mesh(rng, nbNodes, nbElem)
+        setup = mfb.Setup(ArrayMesh(coord, e2n, nbNodes), "ela" if operatorID else "lap")
+        m = setup.mesh
+        stats = np.zeros(16, np.int64)
+        values = np.full(setup.nbEdges * setup.operatorDim, np.nan)
+        prec = np.full(nbNodes * setup.operatorDim, np.nan)
+        keep = [setup.elemToNode, setup.row, setup.col, np.ascontiguousarray(m.coord), setup.checkBounds]
+        rc = ringlib.mfb_ring_replay(operatorID, nbNodes, nbElem, *[_p(np.ascontiguousarray(k)) for k in keep], None,
+                                     rows, entries, 1, _p(values), _p(prec), _p(stats))
+        if rc != 0:
+            msg = ringlib.mfb_ring_replay_error()
+            assert rc == -1 and (b"exceeds the tile caps" in msg or b"more than 254 nodes" in msg), msg
+            return
+        assert stats[11] <= rows and stats[13] <= entries and stats[12] <= 254
+        want_v, _, want_p = oracle.fem_iteration(setup)
+        # random tetrahedra can be arbitrarily flat: compare where the reference's own numbers are finite
+        if np.all(np.isfinite(want_v)) and np.all(np.isfinite(want_p)) and np.abs(want_v).max() < 1e12:
+            assert row_scaled_error(values, want_v, setup.row, setup.operatorDim) <= 1e-9
+    check()

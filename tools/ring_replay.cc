@@ -1,0 +1,181 @@
+// TEST AID, not product code: replays a RING plan (mini-fem_b200/host/ring_plan.h) on the host,
+// lane by lane and in the kernel's order of operations, with the arithmetic header the kernel
+// itself compiles (csrc/ring_math.h, csrc/device_math.cuh).  tests/test_ring_plan.py compares
+// the result with the oracle, so the plan format, the edge-ring formulation and the row-sum
+// diagonal are checked without a GPU.  Nothing in libminifem_b200.so links or calls this file;
+// it is built into tools/libmfb_ringcheck.so by `make -C mini-fem_b200 ringcheck`.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../mini-fem_b200/csrc/device_math.cuh"
+#include "../mini-fem_b200/csrc/ring_math.h"
+#include "../mini-fem_b200/host/ring_plan.h"
+
+using namespace mfb;
+
+static std::string g_error;
+
+template <int OPDIM>
+static int replay (const RingPlan &plan, const double *coord, const int *checkBounds, int nbNodes, int fusePrec,
+                   double *values, double *prec)
+{
+    const double kNaN = std::numeric_limits<double>::quiet_NaN ();
+    std::vector<double> X, Y, Z, slab, sDiag;
+    for (int t = 0; t < plan.nbTiles; t++) {
+        const uint8_t *base = plan.blob.data () + plan.tileOffset[t];
+        const RingTileHeader &h = *plan.header (t);
+        const RingRow *rows = reinterpret_cast<const RingRow*> (base + sizeof (RingTileHeader));
+        const int *tileNodes = reinterpret_cast<const int*> (base + h.offNodes);
+        const RingBatch *batches = reinterpret_cast<const RingBatch*> (base + h.headBytes);
+        const uint64_t *jobs = reinterpret_cast<const uint64_t*> (base + h.offJobs);
+        const uint64_t *codes = reinterpret_cast<const uint64_t*> (base + h.offCodes);
+        X.resize (h.nbNodes); Y.resize (h.nbNodes); Z.resize (h.nbNodes);
+        for (int n = 0; n < h.nbNodes; n++) {
+            X[n] = coord[(size_t)tileNodes[n] * 3]; Y[n] = coord[(size_t)tileNodes[n] * 3 + 1]; Z[n] = coord[(size_t)tileNodes[n] * 3 + 2];
+        }
+        slab.assign ((size_t)h.nbEntries * OPDIM, kNaN);       // a slot nobody writes must show up
+        sDiag.assign ((size_t)h.nbRows * OPDIM, kNaN);
+        // ---- job phase: one lane per job ---------------------------------------------------
+        for (int b = 0; b < h.nbBatches; b++) {
+            const RingBatch rb = batches[b];
+            for (int lane = 0; lane < 32; lane++) {
+                const uint64_t job = jobs[(size_t)b * 32 + lane];
+                const int i = (int)(job & 0xFF), j = (int)((job >> 8) & 0xFF);
+                const int sIJ = (int)((job >> 16) & 0xFFFF), sJI = (int)((job >> 32) & 0xFFFF);
+                const double xi[3] = {X[i], Y[i], Z[i]};
+                const double d[3] = {X[j] - xi[0], Y[j] - xi[1], Z[j] - xi[2]};
+                double acc[OPDIM], u[3] = {0, 0, 0};
+                for (int k = 0; k < OPDIM; k++) acc[k] = 0.0;
+                bool have = false;
+                int remaining = rb.nbSteps;
+                for (int wd = 0; wd < rb.nbWords; wd++, remaining -= 8) {
+                    uint64_t word = codes[(size_t)rb.codeBase + (size_t)wd * 32 + lane];
+                    const int n = remaining < 8 ? remaining : 8;
+                    for (int q = 0; q < n; q++, word >>= 8) {
+                        const int id = (int)(word & 0xFF);
+                        if (id >= kRingBreak) { if (id == kRingBreak) have = false; continue; }
+                        const double w[3] = {X[id] - xi[0], Y[id] - xi[1], Z[id] - xi[2]};
+                        if (have) ring_accumulate<OPDIM> (d, u, w, acc);
+                        u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
+                        have = true;
+                    }
+                }
+                if (sIJ == 0xFFFF) continue;
+                if (OPDIM == 1) {
+                    slab[sIJ] = acc[0];
+                    if (sJI != 0xFFFF) slab[sJI] = acc[0];
+                }
+                else {
+                    double k9[9];
+                    ring_block (acc, k9);
+                    for (int k = 0; k < 9; k++) {
+                        slab[(size_t)sIJ * 9 + k] = k9[k];
+                        if (sJI != 0xFFFF) slab[(size_t)sJI * 9 + ring_transposed (k)] = k9[k];
+                    }
+                }
+            }
+        }
+        // ---- write-out: one warp per row; the diagonal entry is minus the sum of the run ----------
+        for (int r = 0; r < h.nbRows; r++) {
+            const RingRow rr = rows[r];
+            const int len = rr.len, diagOff = rr.diagOff;
+            double *out = values + (size_t)rr.valueStart * OPDIM;
+            const double *src = slab.data () + (size_t)rr.localStart * OPDIM;
+            if (OPDIM == 1) {
+                double lanes[32];
+                for (int lane = 0; lane < 32; lane++) {
+                    double a = 0.0;
+                    for (int k = lane; k < len; k += 32) if (k != diagOff) { a += src[k]; out[k] = src[k]; }
+                    lanes[lane] = a;
+                }
+                for (int off = 16; off >= 1; off >>= 1) {         // shfl_xor butterfly
+                    double next[32];
+                    for (int lane = 0; lane < 32; lane++) next[lane] = lanes[lane] + lanes[lane ^ off];
+                    memcpy (lanes, next, sizeof lanes);
+                }
+                const double diag = 0.0 - lanes[0];
+                if (diagOff != 0xFFFF) out[diagOff] = diag;
+                sDiag[r] = diag;
+            }
+            else {
+                double a[3][9];
+                for (int grp = 0; grp < 3; grp++) {
+                    for (int comp = 0; comp < 9; comp++) {
+                        double s = 0.0;
+                        for (int k = grp; k < len; k += 3) {
+                            if (k == diagOff) continue;
+                            const double v = src[(size_t)k * 9 + comp];
+                            s += v;
+                            out[(size_t)k * 9 + comp] = v;
+                        }
+                        a[grp][comp] = s;
+                    }
+                }
+                for (int comp = 0; comp < 9; comp++) {
+                    const double total = (a[0][comp] + a[1][comp]) + a[2][comp];
+                    const double diag = 0.0 - total;
+                    if (diagOff != 0xFFFF) out[(size_t)diagOff * 9 + comp] = diag;
+                    sDiag[(size_t)r * 9 + comp] = diag;
+                }
+            }
+        }
+        // ---- fused preconditioner: prec_init + prec_inversion of the owned rows -------------------
+        if (!fusePrec) continue;
+        for (int r = 0; r < h.nbRows; r++) {
+            const RingRow rr = rows[r];
+            const int node = rr.node & 0x7fffffff;
+            const bool isInterface = rr.node < 0, hasDiag = rr.diagOff != 0xFFFF;
+            if (OPDIM == 1) {
+                const double dgl = sDiag[r];
+                prec[node] = isInterface ? dgl : 1.0 / dgl;
+            }
+            else {
+                double b[9];
+                for (int q = 0; q < 9; q++) b[q] = sDiag[(size_t)r * 9 + q];
+                if (!isInterface) {
+                    int mx = 0, my = 0, mz = 0;
+                    if (checkBounds) { mx = checkBounds[node]; my = checkBounds[(size_t)nbNodes + node]; mz = checkBounds[2 * (size_t)nbNodes + node]; }
+                    mask_block (b, mx, my, mz);
+                    if (hasDiag) invert3_lu (b);
+                }
+                for (int q = 0; q < 9; q++) prec[(size_t)node * 9 + q] = b[q];
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" const char *mfb_ring_replay_error (void) { return g_error.c_str (); }
+
+// Builds the RING plan, verifies its structure, replays it.  values[nbEdges * dim] and
+// prec[nbNodes * dim] may be NULL (plan + statistics only).  stats: [0] tiles [1] jobs
+// [2] jobs that also write the transposed block [3] ring steps (element visits) [4] padded
+// lane-steps [5] chain breaks [6] modelled gather wavefronts [7] their conflict-free count
+// [8] modelled slab-store wavefronts per block component [9] their conflict-free count
+// [10] plan bytes [11] max rows [12] max nodes [13] max entries [14] max head bytes
+// [15] max tail bytes.
+extern "C" int mfb_ring_replay (int operatorID, int nbNodes, int nbElem, const int *elemToNode, const int *row,
+                                const int *col, const double *coord, const int *checkBounds, const uint8_t *isInterface,
+                                int maxRows, int maxEntries, int bankAware, double *values, double *prec, int64_t stats[16])
+{
+    RingPlanLimits lim;
+    if (maxRows > 0) lim.maxRows = maxRows;
+    if (maxEntries > 0) lim.maxEntries = maxEntries;
+    lim.bankAware = bankAware != 0;
+    RingPlan plan;
+    if (build_ring_plan (nbNodes, nbElem, elemToNode, row, col, coord, isInterface, lim, plan, g_error) != 0) return -1;
+    if (verify_ring_plan (plan, nbNodes, nbElem, elemToNode, row, col, g_error) != 0) { g_error = "verify_ring_plan: " + g_error; return -2; }
+    if (stats) {
+        const int64_t s[16] = {plan.nbTiles, plan.nbJobs, plan.nbSymmetricJobs, plan.nbRingSteps, plan.nbPaddedSteps, plan.nbBreaks,
+                               plan.gatherWavefronts, plan.gatherIdeal, plan.slabWriteWavefronts, plan.slabWriteIdeal,
+                               (int64_t)plan.blob.size (), plan.maxRows, plan.maxNodes, plan.maxEntries, plan.maxHeadBytes, plan.maxTailBytes};
+        memcpy (stats, s, sizeof s);
+    }
+    if (!values || !prec) return 0;
+    return operatorID == 0 ? replay<1> (plan, coord, checkBounds, nbNodes, 1, values, prec)
+                           : replay<9> (plan, coord, checkBounds, nbNodes, 1, values, prec);
+}
