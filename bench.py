@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, nargs=3, default=[100, 100, 100], help="cubes per GPU block")
     ap.add_argument("--op", default="ela", choices=["ela", "lap"])
-    ap.add_argument("--path", default="tiled", choices=["tiled", "atomic", "color"])
+    ap.add_argument("--path", default="tiled", choices=["tiled", "atomic", "color", "ring"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--tile-elems", type=int, default=0)
@@ -295,7 +295,7 @@ def main():
         sampler.stop_flag = True
         sampler.join()
 
-    stats = ctx.plan_stats() if args.path == "tiled" else None
+    stats = ctx.plan_stats() if args.path in ("tiled", "ring") else None
     mesh_bytes, plan_bytes = ctx.device_bytes()
     ctx.close()
 

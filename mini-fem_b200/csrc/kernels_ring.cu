@@ -16,8 +16,10 @@
 //      coordinates (cp.async) of tile t+1 while tile t is in its write-out;
 //   1. job phase: one lane per edge, 32 jobs per warp batch, ring codes 8 to a 64-bit word;
 //      finished 3x3 blocks go to the tile-wide slab at the slots of their CSR entries;
-//   2. write-out: one warp per row, 27 lanes = 3 entries x 9 components copy the row's slab run to
-//      global memory as contiguous 216-byte pieces and sum it; lanes 0..8 store the diagonal entry;
+//      (entry stride 80 bytes, so a block leaves as four 128-bit stores and one 64-bit store);
+//   2. write-out: one warp per row, 3 groups of 10 lanes (9 components + one idle lane, which keeps the
+//      slab reads conflict-free) copy the row's slab run to global memory as contiguous 216-byte
+//      pieces and sum it; lanes 0..8 store the diagonal entry;
 //   3. fused mode: one lane per row of the warp masks / inverts the diagonal block into prec
 //      (prec_init + prec_inversion, src/preconditioner.cc:25-87, src/Fortran/elasclpr.f:19-53).
 // Every CSR entry is written exactly once by a plain store; the summation order is fixed by the plan.
@@ -91,6 +93,9 @@ __device__ __forceinline__ void ring_cp_async_wait_all () { asm volatile ("cp.as
 
 __host__ __device__ __forceinline__ unsigned ring_align128 (unsigned x) { return (x + 127u) & ~127u; }
 
+// doubles per slab entry: an elasticity block is padded to 80 bytes so that it is 16-byte aligned
+__host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim == 9 ? 10 : 1; }
+
 template <int OPDIM>
 __global__ void __launch_bounds__(256, 3)
 ring_assembly_kernel (const RingArgs args)
@@ -106,7 +111,8 @@ ring_assembly_kernel (const RingArgs args)
     unsigned char *sHead0 = smemRaw, *sTail = smemRaw + 2 * headBytes;
     double *sX = reinterpret_cast<double*> (sTail + tailBytes), *sY = sX + planeStride, *sZ = sY + planeStride;
     double *slab = sZ + planeStride;
-    double *sDiag = slab + (((size_t)P.maxEntries * OPDIM + 15) & ~(size_t)15);
+    constexpr int SLAB = ring_slab_stride (OPDIM);
+    double *sDiag = slab + (((size_t)P.maxEntries * SLAB + 15) & ~(size_t)15);
     uint64_t *bars = reinterpret_cast<uint64_t*> (sDiag + (((size_t)P.maxRows * OPDIM + 1) & ~(size_t)1));
     uint64_t *headFull = bars, *tailFull = bars + 2;                  // headFull[2], tailFull
 
@@ -206,13 +212,15 @@ ring_assembly_kernel (const RingArgs args)
                 else {
                     double blk[9];
                     ring_block (acc, blk);
-                    double *dst = slab + sIJ * 9;
-                    #pragma unroll
-                    for (int q = 0; q < 9; q++) dst[q] = blk[q];
-                    if (sJI != 0xFFFF) {
-                        double *dstT = slab + sJI * 9;
-                        #pragma unroll
-                        for (int q = 0; q < 9; q++) dstT[3 * (q % 3) + q / 3] = blk[q];
+                    double2 *dst = reinterpret_cast<double2*> (slab + sIJ * SLAB);
+                    dst[0] = make_double2 (blk[0], blk[1]); dst[1] = make_double2 (blk[2], blk[3]);
+                    dst[2] = make_double2 (blk[4], blk[5]); dst[3] = make_double2 (blk[6], blk[7]);
+                    slab[sIJ * SLAB + 8] = blk[8];
+                    if (sJI != 0xFFFF) {                    // K_ji = K_ij^T
+                        double2 *dstT = reinterpret_cast<double2*> (slab + sJI * SLAB);
+                        dstT[0] = make_double2 (blk[0], blk[3]); dstT[1] = make_double2 (blk[6], blk[1]);
+                        dstT[2] = make_double2 (blk[4], blk[7]); dstT[3] = make_double2 (blk[2], blk[5]);
+                        slab[sJI * SLAB + 8] = blk[8];
                     }
                 }
             }
@@ -232,7 +240,7 @@ ring_assembly_kernel (const RingArgs args)
             const RingRow rr = sRows[r];
             const int len = rr.len, diagOff = rr.diagOff;             // 0xFFFF never equals a position
             double *out = args.values + (size_t)rr.valueStart * OPDIM;
-            const double *src = slab + (size_t)rr.localStart * OPDIM;
+            const double *src = slab + (size_t)rr.localStart * SLAB;
             if (OPDIM == 1) {
                 double a = 0.0;
                 for (int q = lane; q < len; q += 32) {
@@ -247,14 +255,14 @@ ring_assembly_kernel (const RingArgs args)
                 }
             }
             else {
-                const int grp = lane / 9, comp = lane - 9 * grp;      // lanes 27..31 idle
+                const int grp = lane / 10, comp = lane - 10 * grp;    // lanes 9, 19, 29, 30, 31 idle
                 double a = 0.0;
-                if (grp < 3) {
+                if (grp < 3 && comp < 9) {
                     for (int q = grp; q < len; q += 3) {
-                        if (q != diagOff) { const double v = src[q * 9 + comp]; a += v; out[q * 9 + comp] = v; }
+                        if (q != diagOff) { const double v = src[q * SLAB + comp]; a += v; out[q * 9 + comp] = v; }
                     }
                 }
-                const double a1 = __shfl_down_sync (0xffffffffu, a, 9), a2 = __shfl_down_sync (0xffffffffu, a, 18);
+                const double a1 = __shfl_down_sync (0xffffffffu, a, 10), a2 = __shfl_down_sync (0xffffffffu, a, 20);
                 const double diag = 0.0 - ((a + a1) + a2);
                 if (lane < 9) {
                     if (diagOff != 0xFFFF) out[diagOff * 9 + lane] = diag;
@@ -314,7 +322,7 @@ size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
 {
     const int opDim = operatorID == 0 ? 1 : 9;
     const size_t planeStride = ((size_t)plan.maxNodes + 15) & ~(size_t)15;
-    const size_t doubles = 3 * planeStride + (((size_t)plan.maxEntries * opDim + 15) & ~(size_t)15) +
+    const size_t doubles = 3 * planeStride + (((size_t)plan.maxEntries * ring_slab_stride (opDim) + 15) & ~(size_t)15) +
                            (((size_t)plan.maxRows * opDim + 1) & ~(size_t)1);
     return 2 * (size_t)ring_align128 (plan.maxHeadBytes) + ring_align128 (plan.maxTailBytes) + doubles * sizeof (double) +
            3 * sizeof (uint64_t);

@@ -236,49 +236,40 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
     const int nbJobs = (int)w.jobs.size ();
     w.order.resize ((size_t)nbJobs);
     for (int k = 0; k < nbJobs; k++) w.order[k] = k;
-    // longest rings first; inside a length class the jobs that also write the transposed block first,
-    // so that those stores come from full half-warps
-    std::stable_sort (w.order.begin (), w.order.end (), [&] (int a, int b) {
-        if (w.jobs[a].codeLen != w.jobs[b].codeLen) return w.jobs[a].codeLen > w.jobs[b].codeLen;
-        return (w.jobs[a].slotJI != 0xFFFF) > (w.jobs[b].slotJI != 0xFFFF);
-    });
-    if (lim.bankAware) {
-        // half-warp after half-warp: avoid two jobs whose slab slots share a bank (slot mod 16);
-        // a clashing job waits for the next half-warp, and is placed anyway when nothing else fits
-        std::vector<int> result, pending, keep;
-        result.reserve ((size_t)nbJobs);
-        size_t at = 0;
-        while (at < w.order.size () || !pending.empty ()) {
-            unsigned usedIJ = 0, usedJI = 0;
-            int taken = 0;
-            keep.clear ();
-            auto try_take = [&] (int k) {
-                const RingJob &jb = w.jobs[k];
-                const unsigned bIJ = 1u << (jb.slotIJ & 15), bJI = jb.slotJI != 0xFFFF ? 1u << (jb.slotJI & 15) : 0u;
-                if ((usedIJ & bIJ) || (usedJI & bJI)) return false;
-                usedIJ |= bIJ; usedJI |= bJI;
-                result.push_back (k);
-                taken++;
-                return true;
-            };
-            for (int k : pending) { if (taken == 16 || !try_take (k)) keep.push_back (k); }
-            const int paceLen = at < w.order.size () ? w.jobs[w.order[at]].codeLen : 0;
-            const bool paceSym = at < w.order.size () && w.jobs[w.order[at]].slotJI != 0xFFFF;
-            int lookahead = 0;
-            while (taken < 16 && at < w.order.size () && lookahead < 32 && w.jobs[w.order[at]].codeLen == paceLen &&
-                   (w.jobs[w.order[at]].slotJI != 0xFFFF) == paceSym) {
-                if (!try_take (w.order[at])) { keep.push_back (w.order[at]); lookahead++; }
-                at++;
-            }
-            size_t used = 0;
-            while (taken < 16 && used < keep.size ()) { result.push_back (keep[used++]); taken++; }
-            keep.erase (keep.begin (), keep.begin () + (long)used);
-            while (taken < 16 && at < w.order.size ()) { result.push_back (w.order[at++]); taken++; }   // class boundary
-            pending.swap (keep);
-        }
-        w.order.swap (result);
-    }
+    // longest rings first (a warp runs as many steps as its longest job); inside a length class the
+    // jobs keep their row order: the rings of one row share their nodes, which the bank-aware
+    // numbering below exploits, and consecutive lanes then write consecutive slab slots.
+    // (Tried on the model: jobs with a transposed block first, and half-warps picked for distinct
+    // slab banks — fewer slab conflicts, but more gather conflicts than they save.)
+    std::stable_sort (w.order.begin (), w.order.end (), [&] (int a, int b) { return w.jobs[a].codeLen > w.jobs[b].codeLen; });
     while (w.order.size () % 32) w.order.push_back (-1);
+    if (lim.bankAware) {
+        // Lane order inside a half-warp is free as far as the gather goes (its conflicts depend on which
+        // jobs share the half-warp, not on their lanes), so use it for the slab: split the 16 jobs into
+        // the two quarter-warps so that the slots a quarter stores to differ mod 8 as far as possible.
+        for (size_t h0 = 0; h0 < w.order.size (); h0 += 16) {
+            int group[2][8], count[2] = {0, 0};
+            unsigned loadIJ[2][8] = {{0}}, loadJI[2][8] = {{0}};
+            for (int l = 0; l < 16; l++) {
+                const int k = w.order[h0 + l];
+                int best = count[0] <= count[1] ? 0 : 1;
+                if (k >= 0) {
+                    const RingJob &jb = w.jobs[k];
+                    long bestCost = 1l << 60;
+                    for (int q = 0; q < 2; q++) {
+                        if (count[q] >= 8) continue;
+                        long cost = 16l * loadIJ[q][jb.slotIJ & 7] + (jb.slotJI != 0xFFFF ? 16l * loadJI[q][jb.slotJI & 7] : 0) + count[q];
+                        if (cost < bestCost) { bestCost = cost; best = q; }
+                    }
+                    loadIJ[best][jb.slotIJ & 7]++;
+                    if (jb.slotJI != 0xFFFF) loadJI[best][jb.slotJI & 7]++;
+                }
+                else if (count[best] >= 8) best ^= 1;
+                group[best][count[best]++] = k;
+            }
+            for (int q = 0; q < 2; q++) for (int l = 0; l < 8; l++) w.order[h0 + (size_t)q * 8 + l] = group[q][l];
+        }
+    }
     const int nbBatches = (int)w.order.size () / 32;
     out.nbBatches = nbBatches;
 
@@ -345,8 +336,9 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
         for (int h = 0; h < nbHalf; h++) {
             const int nbSteps = w.batches[h / 2].nbSteps;
             banks.reset (nbSteps + 2);
-            unsigned loadIJ[16] = {0}, loadJI[16] = {0};
-            bool anyIJ = false, anyJI = false;
+            // slab stores are 128-bit (entry stride 80 bytes): a quarter-warp of 8 lanes per wavefront,
+            // conflict-free when its slots differ mod 8
+            unsigned loadIJ[2][8] = {{0}}, loadJI[2][8] = {{0}};
             for (int l = 0; l < 16; l++) {
                 const int k = w.order[(size_t)h * 16 + l];
                 if (k < 0) continue;
@@ -378,18 +370,20 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
                 banks.add (0, w.newId[jb.i]);
                 banks.add (1, w.newId[jb.j]);
                 for (int q = 0; q < len; q++) if (codes[q] != kRingBreak) banks.add (2 + q, w.newId[codes[q]]);
-                loadIJ[jb.slotIJ & 15]++; anyIJ = true;
-                if (jb.slotJI != 0xFFFF) { loadJI[jb.slotJI & 15]++; anyJI = true; }
+                loadIJ[l >> 3][jb.slotIJ & 7]++;
+                if (jb.slotJI != 0xFFFF) loadJI[l >> 3][jb.slotJI & 7]++;
             }
             for (int s = 0; s < banks.steps; s++) {
                 const int wf = banks.wavefronts (s);
                 out.gatherWf += 3 * wf;
                 out.gatherIdeal += 3 * (wf > 0);
             }
-            unsigned mIJ = 0, mJI = 0;
-            for (int c = 0; c < 16; c++) { mIJ = std::max (mIJ, loadIJ[c]); mJI = std::max (mJI, loadJI[c]); }
-            out.slabWf += mIJ + mJI;
-            out.slabIdeal += (anyIJ ? 1 : 0) + (anyJI ? 1 : 0);
+            for (int quarter = 0; quarter < 2; quarter++) {
+                unsigned mIJ = 0, mJI = 0;
+                for (int c = 0; c < 8; c++) { mIJ = std::max (mIJ, loadIJ[quarter][c]); mJI = std::max (mJI, loadJI[quarter][c]); }
+                out.slabWf += mIJ + mJI;
+                out.slabIdeal += (mIJ ? 1 : 0) + (mJI ? 1 : 0);
+            }
         }
     };
     // With the rotations fixed, the loads that really meet in one half-warp step are known: move

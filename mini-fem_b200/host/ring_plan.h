@@ -76,7 +76,8 @@ struct RingPlanLimits {
     int maxEntries = 576;          // CSR entries per tile: the slab holds maxEntries * operatorDim doubles
     int maxNodes = kRingMaxNodes;  // tile-local nodes (<= 254: one code byte per node)
     bool bankAware = true;         // node numbering + ring rotation chosen against bank conflicts
-    int refinePasses = 2;          // renumber-and-rotate rounds after the first numbering
+    int refinePasses = 0;          // renumber-and-rotate rounds after the first numbering: one round takes 4 %
+                                   // off the modelled gather conflicts and adds 70 % to the plan build time
 };
 
 struct RingPlan {
@@ -84,7 +85,9 @@ struct RingPlan {
     int maxRows = 0, maxNodes = 0, maxEntries = 0, maxBatches = 0;
     uint32_t maxBlobBytes = 0, maxHeadBytes = 0, maxTailBytes = 0;
     int64_t nbJobs = 0, nbSymmetricJobs = 0, nbRingSteps = 0, nbPaddedSteps = 0, nbBreaks = 0;
-    // shared-memory model (wavefronts of 128 bytes, one per half-warp LDS.64 / STS.64 without conflicts)
+    // shared-memory model, in wavefronts of 128 bytes.  gather: the LDS.64 of the coordinate planes, one
+    // wavefront per half-warp and plane without conflicts.  slab: per quarter-warp (8 lanes) and per 128-bit
+    // store of a finished block (an elasticity block = 4 such stores + one 64-bit one)
     int64_t gatherWavefronts = 0, gatherIdeal = 0, slabWriteWavefronts = 0, slabWriteIdeal = 0;
     std::vector<uint64_t> tileOffset;   // nbTiles + 1 byte offsets into `blob`
     std::vector<uint8_t> blob;

@@ -15,6 +15,12 @@ from helpers import RTOL, ArrayMesh, block_scaled_error, random_tet_mesh, row_sc
 from oracle_lib import Oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The RING path evaluates the same gradients as elem_coef_seq with an algebraically identical
+# formula based at another node of the element (ring_math.h).  On FEM-quality meshes (Kuhn,
+# Delaunay) the two agree to ~1e-15; on RANDOM 4-subsets of points the elements can be arbitrarily
+# flat, both formulas lose eps * (h^3 / volume) digits, and they lose different ones — those
+# layout-stress meshes are compared at 1e-10.
+SLIVER_RTOL = 1e-10
 
 
 @pytest.fixture(scope="module")
@@ -50,12 +56,12 @@ def replay(lib, setup, rows=0, entries=0, bank_aware=1, interface=None):
     return values, prec, stats
 
 
-def check_against_oracle(oracle, setup, values, prec, interface=None):
+def check_against_oracle(oracle, setup, values, prec, interface=None, rtol=RTOL):
     want_v, want_p0, want_p = oracle.fem_iteration(setup)
     dim = setup.operatorDim
-    assert row_scaled_error(values, want_v, setup.row, dim) <= RTOL
+    assert row_scaled_error(values, want_v, setup.row, dim) <= rtol
     if interface is None:
-        assert block_scaled_error(prec, want_p, dim) <= RTOL
+        assert block_scaled_error(prec, want_p, dim) <= rtol
     else:          # interface rows keep the raw diagonal block for the halo sum, the others are inverted
         intf = interface.astype(bool)
         got, raw, inv = prec.reshape(-1, dim), want_p0.reshape(-1, dim), want_p.reshape(-1, dim)
@@ -104,12 +110,12 @@ def test_ring_replay_random_tets(ringlib, oracle, op):
     codes = rng.choice([0, 0, 0, 52, 53, 54, 10], size=60).astype(np.int32)
     setup = mfb.Setup(ArrayMesh(coord, e2n, 60, codes), op)
     values, prec, stats = replay(ringlib, setup, rows=8, entries=400)
-    check_against_oracle(oracle, setup, values, prec)
+    check_against_oracle(oracle, setup, values, prec, rtol=SLIVER_RTOL)
     assert 6 * 150 <= stats[3] <= 12 * 150                 # an (element, edge) pair is visited once, or once per tile when the edge crosses tiles
     coord, e2n = random_tet_mesh(rng, 25, 400)             # dense: many elements around every edge, chains with breaks
     setup = mfb.Setup(ArrayMesh(coord, e2n, 25), op)
     values, prec, stats = replay(ringlib, setup, rows=25, entries=640)
-    check_against_oracle(oracle, setup, values, prec)
+    check_against_oracle(oracle, setup, values, prec, rtol=SLIVER_RTOL)
     assert stats[0] == 1 and stats[3] == 6 * 400 and stats[5] > 0
 
 

@@ -24,6 +24,7 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
                    double *values, double *prec)
 {
     const double kNaN = std::numeric_limits<double>::quiet_NaN ();
+    constexpr int SLAB = OPDIM == 9 ? 10 : 1;          // doubles per slab entry, as in the kernel (ring_slab_stride)
     std::vector<double> X, Y, Z, slab, sDiag;
     for (int t = 0; t < plan.nbTiles; t++) {
         const uint8_t *base = plan.blob.data () + plan.tileOffset[t];
@@ -37,7 +38,7 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
         for (int n = 0; n < h.nbNodes; n++) {
             X[n] = coord[(size_t)tileNodes[n] * 3]; Y[n] = coord[(size_t)tileNodes[n] * 3 + 1]; Z[n] = coord[(size_t)tileNodes[n] * 3 + 2];
         }
-        slab.assign ((size_t)h.nbEntries * OPDIM, kNaN);       // a slot nobody writes must show up
+        slab.assign ((size_t)h.nbEntries * SLAB, kNaN);       // a slot nobody writes must show up
         sDiag.assign ((size_t)h.nbRows * OPDIM, kNaN);
         // ---- job phase: one lane per job ---------------------------------------------------
         for (int b = 0; b < h.nbBatches; b++) {
@@ -73,8 +74,8 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
                     double k9[9];
                     ring_block (acc, k9);
                     for (int k = 0; k < 9; k++) {
-                        slab[(size_t)sIJ * 9 + k] = k9[k];
-                        if (sJI != 0xFFFF) slab[(size_t)sJI * 9 + ring_transposed (k)] = k9[k];
+                        slab[(size_t)sIJ * SLAB + k] = k9[k];
+                        if (sJI != 0xFFFF) slab[(size_t)sJI * SLAB + ring_transposed (k)] = k9[k];
                     }
                 }
             }
@@ -84,7 +85,7 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
             const RingRow rr = rows[r];
             const int len = rr.len, diagOff = rr.diagOff;
             double *out = values + (size_t)rr.valueStart * OPDIM;
-            const double *src = slab.data () + (size_t)rr.localStart * OPDIM;
+            const double *src = slab.data () + (size_t)rr.localStart * SLAB;
             if (OPDIM == 1) {
                 double lanes[32];
                 for (int lane = 0; lane < 32; lane++) {
@@ -108,7 +109,7 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
                         double s = 0.0;
                         for (int k = grp; k < len; k += 3) {
                             if (k == diagOff) continue;
-                            const double v = src[(size_t)k * 9 + comp];
+                            const double v = src[(size_t)k * SLAB + comp];
                             s += v;
                             out[(size_t)k * 9 + comp] = v;
                         }
