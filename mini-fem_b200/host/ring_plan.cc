@@ -505,6 +505,95 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
 
 }  // namespace
 
+namespace {
+
+// Recursive coordinate bisection: the nodes of [lo, hi) are split across the longest axis of their
+// bounding box into two parts that hold a whole number of leaves of (nearly) equal size <= leafSize.
+// Leaves come out box-shaped, which is what keeps mesh edges inside one tile (an interior edge is
+// one job that writes both of its blocks); a run of the Morton curve of the same length is ragged.
+void rcb_split (std::vector<int> &idx, int lo, int hi, int leafSize, const double *coord, std::vector<int> &leafStart)
+{
+    const int count = hi - lo;
+    if (count <= leafSize && leafSize > 0) { leafStart.push_back (lo); leafSize = 0; }   // below a leaf: keep bisecting, for the order only
+    if (count <= 2) return;
+    double bmin[3], bmax[3];
+    for (int a = 0; a < 3; a++) bmin[a] = bmax[a] = coord[(size_t)idx[lo] * 3 + a];
+    for (int q = lo + 1; q < hi; q++) {
+        for (int a = 0; a < 3; a++) {
+            const double v = coord[(size_t)idx[q] * 3 + a];
+            bmin[a] = std::min (bmin[a], v); bmax[a] = std::max (bmax[a], v);
+        }
+    }
+    int axis = 0;
+    for (int a = 1; a < 3; a++) if (bmax[a] - bmin[a] > bmax[axis] - bmin[axis]) axis = a;
+    int mid = lo + count / 2;
+    if (leafSize > 0) {
+        const int leaves = (count + leafSize - 1) / leafSize, leavesLeft = leaves / 2;
+        mid = lo + (int)((int64_t)count * leavesLeft / leaves);
+    }
+    std::nth_element (idx.begin () + lo, idx.begin () + mid, idx.begin () + hi, [&] (int x, int y) {
+        const double cx = coord[(size_t)x * 3 + axis], cy = coord[(size_t)y * 3 + axis];
+        return cx < cy || (cx == cy && x < y);
+    });
+    rcb_split (idx, lo, mid, leafSize, coord, leafStart);
+    rcb_split (idx, mid, hi, leafSize, coord, leafStart);
+}
+
+// Tiles = the leaves of the bisection, cut further (greedily, in leaf order) wherever a leaf exceeds
+// the entry / node caps.  Same outputs as cut_node_tiles.
+int cut_node_tiles_rcb (int nbNodes, const int *elemToNode, const int *row, const double *coord, const int *n2eIndex,
+                        const int *n2eValue, const RingPlanLimits &lim, std::vector<int> &nodeOrder,
+                        std::vector<int> &tileStart, std::string &error)
+{
+    nodeOrder.resize ((size_t)nbNodes);
+    for (int n = 0; n < nbNodes; n++) nodeOrder[n] = n;
+    std::vector<int> leafStart;
+    if (nbNodes > 0) rcb_split (nodeOrder, 0, nbNodes, lim.maxRows, coord, leafStart);
+    leafStart.push_back (nbNodes);
+    tileStart.clear ();
+    std::vector<int> nodeStamp ((size_t)nbNodes, -1), fresh;
+    int tile = 0;
+    for (size_t leaf = 0; leaf + 1 < leafStart.size (); leaf++) {
+        int rows = 0, refs = 0, entries = 0;
+        tileStart.push_back (leafStart[leaf]);
+        for (int at = leafStart[leaf]; at < leafStart[leaf + 1]; at++) {
+            const int n = nodeOrder[at], rowLen = row[n + 1] - row[n];
+            for (int attempt = 0; attempt < 2; attempt++) {
+                int addRefs = (nodeStamp[n] != tile) ? 1 : 0;
+                fresh.clear ();
+                for (int p = n2eIndex[n]; p < n2eIndex[n + 1]; p++) {
+                    const int *en = elemToNode + (size_t)n2eValue[p] * kDimElem;
+                    for (int k = 0; k < kDimElem; k++) {
+                        const int m = en[k] - 1;
+                        if (m != n && nodeStamp[m] != tile && std::find (fresh.begin (), fresh.end (), m) == fresh.end ()) fresh.push_back (m);
+                    }
+                }
+                addRefs += (int)fresh.size ();
+                if (rows + 1 <= lim.maxRows && refs + addRefs <= lim.maxNodes && entries + rowLen <= lim.maxEntries) {
+                    nodeStamp[n] = tile;
+                    for (int m : fresh) nodeStamp[m] = tile;
+                    rows++; refs += addRefs; entries += rowLen;
+                    break;
+                }
+                if (rows == 0 || attempt == 1) {
+                    error = "node " + std::to_string (n + 1) + " alone exceeds the tile caps (" + std::to_string (addRefs) +
+                            " nodes, " + std::to_string (rowLen) + " entries)";
+                    return -1;
+                }
+                tile++;                       // close the tile inside the leaf, retry the node in a fresh one
+                tileStart.push_back (at);
+                rows = refs = entries = 0;
+            }
+        }
+        tile++;
+    }
+    tileStart.push_back (nbNodes);
+    if (nbNodes == 0) tileStart.assign (1, 0);
+    return 0;
+}
+
+}  // namespace
+
 int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *row, const int *col,
                      const double *coord, const uint8_t *isInterface, const RingPlanLimits &lim,
                      RingPlan &plan, std::string &error)
@@ -518,7 +607,11 @@ int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
     std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
     node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
     std::vector<int> nodeOrder, tileStart;
-    {
+    if (lim.bisection) {
+        if (cut_node_tiles_rcb (nbNodes, elemToNode, row, coord, n2eIndex.data (), n2eValue.data (), lim,
+                                nodeOrder, tileStart, error) != 0) return -1;
+    }
+    else {
         TileCutLimits cut = { lim.maxRows, 1 << 30, lim.maxNodes, lim.maxEntries };
         if (cut_node_tiles (nbNodes, nbElem, elemToNode, row, coord, n2eIndex.data (), n2eValue.data (), cut,
                             nodeOrder, tileStart, error) != 0) return -1;

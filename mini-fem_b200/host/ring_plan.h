@@ -76,6 +76,7 @@ struct RingPlanLimits {
     int maxEntries = 576;          // CSR entries per tile: the slab holds maxEntries * operatorDim doubles
     int maxNodes = kRingMaxNodes;  // tile-local nodes (<= 254: one code byte per node)
     bool bankAware = true;         // node numbering + ring rotation chosen against bank conflicts
+    bool bisection = true;         // tiles = leaves of a recursive coordinate bisection (false: runs of the Morton curve, as TILED)
     int refinePasses = 0;          // renumber-and-rotate rounds after the first numbering: one round takes 4 %
                                    // off the modelled gather conflicts and adds 70 % to the plan build time
 };
