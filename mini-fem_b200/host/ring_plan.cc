@@ -515,7 +515,7 @@ void rcb_split (std::vector<int> &idx, int lo, int hi, int leafSize, const doubl
 {
     const int count = hi - lo;
     if (count <= leafSize && leafSize > 0) { leafStart.push_back (lo); leafSize = 0; }   // below a leaf: keep bisecting, for the order only
-    if (count <= 2) return;
+    if (leafSize == 0 && count <= 2) return;
     double bmin[3], bmax[3];
     for (int a = 0; a < 3; a++) bmin[a] = bmax[a] = coord[(size_t)idx[lo] * 3 + a];
     for (int q = lo + 1; q < hi; q++) {
