@@ -49,6 +49,16 @@ struct RingArgs {
 __device__ __forceinline__ uint64_t ring_record_offset (uint64_t packed) { return packed & 0xFFFFFFFFFFFFull; }
 __device__ __forceinline__ unsigned ring_record_head_bytes (uint64_t packed) { return (unsigned)(packed >> 48) << 4; }
 
+#ifdef MFB_RING_HOST_EMULATION
+// tools/ring_kernel_host.cc compiles this file with g++ and runs the kernel below on host threads
+// (tools/cuda_cta_emulation.h): the PTX helpers become their emulated counterparts.
+inline void ring_mbar_init (uint64_t *bar, unsigned) { cta_emu::mbar_init (bar); }
+inline void ring_mbar_expect_tx (uint64_t *bar, unsigned bytes) { cta_emu::mbar_expect_tx (bar, bytes); }
+inline void ring_mbar_wait (uint64_t *bar, unsigned parity) { cta_emu::mbar_wait (bar, parity); }
+inline void ring_bulk_load (void *dst, const void *src, unsigned bytes, uint64_t *bar) { cta_emu::bulk_load (dst, src, bytes, bar); }
+inline void ring_cp_async_f64 (double *dst, const double *src) { *dst = *src; }
+inline void ring_cp_async_wait_all () {}
+#else
 __device__ __forceinline__ unsigned ring_smem_u32 (const void *p) { return (unsigned)__cvta_generic_to_shared (p); }
 
 __device__ __forceinline__ void ring_mbar_init (uint64_t *bar, unsigned count)
@@ -91,6 +101,8 @@ __device__ __forceinline__ void ring_cp_async_f64 (double *dst, const double *sr
 }
 __device__ __forceinline__ void ring_cp_async_wait_all () { asm volatile ("cp.async.wait_all;" ::: "memory"); }
 
+#endif
+
 __host__ __device__ __forceinline__ unsigned ring_align128 (unsigned x) { return (x + 127u) & ~127u; }
 
 // doubles per slab entry: an elasticity block is padded to 80 bytes so that it is 16-byte aligned
@@ -100,7 +112,11 @@ template <int OPDIM>
 __global__ void __launch_bounds__(256, 3)
 ring_assembly_kernel (const RingArgs args)
 {
+#ifdef MFB_RING_HOST_EMULATION
+    unsigned char *smemRaw = cta_emu::dynamic_smem ();
+#else
     extern __shared__ __align__(128) unsigned char smemRaw[];
+#endif
     const DeviceRingPlan &P = args.plan;
     const int tid = threadIdx.x, nThreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nWarps = nThreads >> 5;
@@ -309,12 +325,14 @@ ring_assembly_kernel (const RingArgs args)
     }
 }
 
+#ifndef MFB_RING_HOST_EMULATION
 template <class K>
 cudaError_t ring_opt_in (K kernel)
 {
     // The attribute belongs to the kernel, not to a context: always opt in to the device maximum.
     return cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
+#endif
 
 }  // namespace
 
@@ -328,6 +346,7 @@ size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
            3 * sizeof (uint64_t);
 }
 
+#ifndef MFB_RING_HOST_EMULATION
 cudaError_t ring_configure (int operatorID)
 {
     return operatorID == 0 ? ring_opt_in (ring_assembly_kernel<1>) : ring_opt_in (ring_assembly_kernel<9>);
@@ -347,5 +366,6 @@ cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTi
     else                 ring_assembly_kernel<9><<<grid, threads, smemBytes, stream>>> (args);
     return cudaGetLastError ();
 }
+#endif
 
 }  // namespace mfb

@@ -203,3 +203,79 @@ def test_ring_plan_property(ringlib, oracle):
         if np.all(np.isfinite(want_v)) and np.all(np.isfinite(want_p)) and np.abs(want_v).max() < 1e12:
             assert row_scaled_error(values, want_v, setup.row, setup.operatorDim) <= 1e-9
     check()
+
+
+# ------------------------------------------------------------------------------------------------
+# The kernel's SOURCE on host threads (tools/ring_kernel_host.cc + tools/cuda_cta_emulation.h): the
+# same csrc/kernels_ring.cu that nvcc compiles for sm_100a, built with g++, one std::thread per CUDA
+# thread, real barriers, emulated mbarriers / TMA / cp.async / shuffles.  Covers what the replay
+# cannot: the prefetch protocol across tiles, the mbarrier phase arithmetic, buffer offsets, the
+# persistent-grid stride, the lane mappings of the write-out.
+# ------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def kernel_host():
+    lib = C.CDLL(os.path.join(ROOT, "tools", "libmfb_ringkernel_host.so"))
+    lib.mfb_ring_kernel_host_error.restype = C.c_char_p
+    lib.mfb_ring_kernel_host.argtypes = [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p] * 2
+    return lib
+
+
+def run_kernel_on_host(lib, setup, rows=0, entries=0, ctas=3, fuse=1, interface=None):
+    m = setup.mesh
+    dim = setup.operatorDim
+    values = np.full(setup.nbEdges * dim, np.nan)
+    prec = np.full(m.nbNodes * dim, np.nan)
+    keep = [np.ascontiguousarray(setup.elemToNode, np.int32), np.ascontiguousarray(setup.row, np.int32),
+            np.ascontiguousarray(setup.col, np.int32), np.ascontiguousarray(m.coord, np.float64),
+            np.ascontiguousarray(setup.checkBounds, np.int32)]
+    rc = lib.mfb_ring_kernel_host(setup.operatorID, m.nbNodes, keep[0].size // 4, *[_p(k) for k in keep], _p(interface),
+                                  rows, entries, ctas, fuse, _p(values), _p(prec))
+    assert rc == 0, lib.mfb_ring_kernel_host_error().decode()
+    return values, prec
+
+
+@pytest.mark.parametrize("op", ["ela", "lap"])
+@pytest.mark.parametrize("grid,rows,entries,ctas", [((7, 6, 5), 0, 0, 3), ((7, 6, 5), 0, 0, 1), ((6, 5, 4), 5, 100, 2),
+                                                    ((8, 8, 6), 64, 960, 2), ((2, 2, 1), 0, 0, 4)])
+def test_ring_kernel_source_on_host_threads(kernel_host, oracle, op, grid, rows, entries, ctas):
+    mesh = mfb.Mesh.generate(*grid, seed=6)
+    setup = mfb.Setup(mesh, op)
+    values, prec = run_kernel_on_host(kernel_host, setup, rows, entries, ctas)
+    check_against_oracle(oracle, setup, values, prec)
+
+
+def test_ring_kernel_source_unfused_interface_and_random_tets(kernel_host, oracle):
+    mesh = mfb.Mesh.generate(6, 6, 6, blocks=(2, 1, 1), rank=1, seed=2)
+    setup = mfb.Setup(mesh, "ela")
+    interface = np.zeros(mesh.nbNodes, np.uint8)
+    interface[mesh.intfNodes - 1] = 1
+    values, prec = run_kernel_on_host(kernel_host, setup, interface=interface)
+    check_against_oracle(oracle, setup, values, prec, interface)
+    values, prec = run_kernel_on_host(kernel_host, setup, fuse=0)          # values only: prec stays untouched
+    want_v, _, _ = oracle.fem_iteration(setup)
+    assert row_scaled_error(values, want_v, setup.row, 9) <= RTOL and np.all(np.isnan(prec))
+    rng = np.random.default_rng(3)
+    coord, e2n = random_tet_mesh(rng, 40, 200)                             # chains with breaks, long rows
+    setup = mfb.Setup(ArrayMesh(coord, e2n, 40), "ela")
+    values, prec = run_kernel_on_host(kernel_host, setup, rows=10, entries=400, ctas=2)
+    check_against_oracle(oracle, setup, values, prec, rtol=SLIVER_RTOL)
+
+
+def test_ring_kernel_protocol_under_thread_sanitizer():
+    """The same host-thread run inside a ThreadSanitizer build: the asynchronous copies are performed
+    at issue (the earliest the hardware could touch their destination), so a missing barrier or a
+    wrong mbarrier phase between the tiles of a CTA is reported as a data race.  (Removing the block
+    barrier after the job phase makes this test report 11 races.)"""
+    import subprocess
+    pkg = os.path.join(ROOT, "mini-fem_b200")
+    build = subprocess.run(["make", "-C", pkg, "ringkernel-tsan"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if build.returncode != 0:
+        pytest.skip("no ThreadSanitizer build here: " + build.stdout[-300:])
+    env = dict(os.environ, OMP_NUM_THREADS="1", TSAN_OPTIONS="halt_on_error=0")
+    for cfg in (["6", "8", "140", "2"], ["7", "0", "0", "1"]):
+        res = subprocess.run([os.path.join(ROOT, "tools", "ring_kernel_tsan")] + cfg, env=env, stdout=subprocess.PIPE,
+                             stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert "TSAN_RUN_DONE" in res.stdout, res.stdout[-2000:]
+        assert "ThreadSanitizer" not in res.stdout, res.stdout[-4000:]
+        assert "NaNs left 0" in res.stdout

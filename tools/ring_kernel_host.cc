@@ -1,0 +1,51 @@
+// TEST AID, not product code: compiles the SOURCE of the RING kernel (csrc/kernels_ring.cu) with g++
+// and runs it on host threads — one std::thread per CUDA thread, CTAs one after the other — through
+// tools/cuda_cta_emulation.h.  tests/test_ring_plan.py compares the result with the oracle; built
+// with -fsanitize=thread (make -C mini-fem_b200 ringkernel-tsan) the same run checks the kernel's
+// synchronisation protocol (buffer reuse across tiles, mbarrier phases, block barriers) for data
+// races.  Built into tools/libmfb_ringkernel_host.so; nothing in libminifem_b200.so links it.
+#define MFB_RING_HOST_EMULATION 1
+#include "cuda_cta_emulation.h"
+
+#include "../mini-fem_b200/csrc/kernels_ring.cu"
+
+#include <string>
+
+using namespace mfb;
+
+static std::string g_error;
+
+extern "C" const char *mfb_ring_kernel_host_error (void) { return g_error.c_str (); }
+
+// One launch of ring_assembly_kernel over all tiles with `ctas` CTAs of 256 threads (the
+// persistent-grid stride is `ctas`).  fusePrec as on the device.  values / prec are host arrays.
+extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, const int *elemToNode, const int *row,
+                                     const int *col, const double *coord, const int *checkBounds, const uint8_t *isInterface,
+                                     int maxRows, int maxEntries, int ctas, int fusePrec, double *values, double *prec)
+{
+    RingPlanLimits lim;
+    if (maxRows > 0) lim.maxRows = maxRows;
+    if (maxEntries > 0) lim.maxEntries = maxEntries;
+    RingPlan hp;
+    if (build_ring_plan (nbNodes, nbElem, elemToNode, row, col, coord, isInterface, lim, hp, g_error) != 0) return -1;
+    std::vector<uint64_t> packed (hp.tileOffset);
+    for (int t = 0; t < hp.nbTiles; t++) packed[t] |= (uint64_t)(hp.header (t)->headBytes >> 4) << 48;
+    // 16-byte aligned copy of the records, as cudaMalloc would give
+    std::vector<uint8_t> blobStore (hp.blob.size () + 32);
+    uint8_t *blob = reinterpret_cast<uint8_t*> (((uintptr_t)blobStore.data () + 15) & ~(uintptr_t)15);
+    memcpy (blob, hp.blob.data (), hp.blob.size ());
+    RingArgs args;
+    args.plan.blob = blob; args.plan.tileOffset = packed.data ();
+    args.plan.nbTiles = hp.nbTiles; args.plan.nbInterfaceTiles = hp.nbInterfaceTiles;
+    args.plan.maxRows = std::max (hp.maxRows, 1); args.plan.maxNodes = std::max (hp.maxNodes, 4);
+    args.plan.maxEntries = std::max (hp.maxEntries, 1);
+    args.plan.maxHeadBytes = std::max (hp.maxHeadBytes, 16u); args.plan.maxTailBytes = std::max (hp.maxTailBytes, 16u);
+    args.coord = coord; args.values = values; args.prec = prec; args.checkBounds = checkBounds;
+    args.nbNodes = nbNodes; args.fusePrec = fusePrec; args.firstTile = 0; args.lastTile = hp.nbTiles;
+    if (hp.nbTiles == 0) return 0;
+    const int grid = std::max (1, std::min (ctas > 0 ? ctas : 3, hp.nbTiles));
+    const size_t smem = ring_smem_bytes (operatorID, args.plan);
+    if (operatorID == 0) cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<1> (args); });
+    else                 cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<9> (args); });
+    return 0;
+}
