@@ -8,7 +8,7 @@
 //
 // Compile-time switches of the reference become environment variables:
 //   MINIFEM_DATA_PATH   DATA_PATH of build/iMake:20            (default ./data)
-//   MINIFEM_PATH        tiled | atomic | color                 (default tiled; color = the
+//   MINIFEM_PATH        tiled | atomic | color | ring          (default tiled; color = the
 //                       COLORING build: colour + permute before the CSR, main.cc:209-236)
 //   MINIFEM_FUSED       1 = one fused launch per iteration, reported like the
 //                       multithreaded-comm build reports (FEM.cc:179-180: everything under
@@ -268,7 +268,8 @@ int main (int argCount, char **argValue)
     int path = MFB_PATH_TILED;
     if (pathName == "atomic") path = MFB_PATH_ATOMIC;
     else if (pathName == "color") path = MFB_PATH_COLOR;
-    else if (pathName != "tiled") die ("Incorrect MINIFEM_PATH \"" + pathName + "\" (tiled, atomic or color).");
+    else if (pathName == "ring") path = MFB_PATH_RING;
+    else if (pathName != "tiled") die ("Incorrect MINIFEM_PATH \"" + pathName + "\" (tiled, atomic, color or ring).");
 
     Timer timer;
     int nbIter;
