@@ -354,6 +354,7 @@ class Context:
         o = Options(PATH_NAMES[path] if isinstance(path, str) else path, device, tile_rows, tile_elems,
                     threads, int(use_graph), ctas, 1 if bank_aware else -1)
         self.handle = C.c_void_p()
+        self.path = o.path
         _check(lib.mfb_ctx_create(C.byref(p), C.byref(o), C.byref(self.handle)), "mfb_ctx_create")
         self.nbValues = setup.nbEdges * setup.operatorDim
         self.nbPrec = m.nbNodes * setup.operatorDim
@@ -443,6 +444,9 @@ class Context:
     def plan_stats(self):
         s = (C.c_int64 * 8)()
         _check(lib.mfb_ctx_plan_stats(self.handle, s), "mfb_ctx_plan_stats")
+        if self.path == PATH_RING:
+            return dict(tiles=s[0], jobs=s[1], ring_steps=s[2], max_rows=s[3], max_nodes=s[4], smem_bytes=s[5],
+                        padded_lane_steps=s[6], max_blob_bytes=s[7])
         return dict(tiles=s[0], tile_elems=s[1], contributions=s[2], max_rows=s[3], max_elems=s[4], smem_bytes=s[5],
                     padded_lane_steps=s[6], max_blob_bytes=s[7])
 
