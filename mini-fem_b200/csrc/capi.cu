@@ -365,9 +365,10 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     if (o && o->tileElems > 0) lim.maxEntries = o->tileElems;          // RING: tileElems caps the CSR entries of a tile
     lim.bankAware = !(o && o->bankAware < 0);
     // experiment knobs: MFB_RING_CUT=morton (tiles = runs of the Morton curve, like TILED),
-    // MFB_RING_REFINE=n (renumber-and-rotate rounds of the bank-aware numbering)
+    // MFB_RING_REFINE=n (renumber-and-rotate rounds of the bank-aware numbering), MFB_RING_SWEEPS=n
     if (const char *v = getenv ("MFB_RING_CUT")) lim.bisection = std::string (v) != "morton";
     if (const char *v = getenv ("MFB_RING_REFINE")) lim.refinePasses = std::max (atoi (v), 0);
+    if (const char *v = getenv ("MFB_RING_SWEEPS")) lim.rotationSweeps = std::max (atoi (v), 0);
     RingPlan hp;
     std::string err;
     if (build_ring_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, p->coord,

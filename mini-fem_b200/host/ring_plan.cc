@@ -108,6 +108,7 @@ void append_chains (TileWork &w, RingJob &job, int &breaks)
 struct HalfWarpBanks {
     static constexpr int kMaxSteps = 64;
     uint8_t node[kMaxSteps][16][16];
+    uint8_t refs[kMaxSteps][16][16];          // lanes of the half-warp loading that word
     uint8_t count[kMaxSteps][16];
     int steps = 0;
     void reset (int nbSteps) { steps = std::min (nbSteps, (int)kMaxSteps); memset (count, 0, sizeof (count[0]) * (size_t)steps); }
@@ -116,14 +117,28 @@ struct HalfWarpBanks {
         if (s >= steps) return 0;
         const int b = id & 15, n = count[s][b];
         for (int k = 0; k < n; k++) if (node[s][b][k] == id) return 0;   // same word: broadcast
-        return n;
+        // the step costs as many wavefronts as its busiest bank holds words: joining a bank that
+        // already is the busiest one adds a wavefront, joining a quieter one only makes that likelier
+        int busiest = 0;
+        for (int q = 0; q < 16; q++) busiest = std::max (busiest, (int)count[s][q]);
+        return n == 0 ? 0 : (n >= busiest ? 16 + n : n);
     }
     void add (int s, int id)
     {
         if (s >= steps) return;
         const int b = id & 15, n = count[s][b];
-        for (int k = 0; k < n; k++) if (node[s][b][k] == id) return;
-        if (n < 16) { node[s][b][n] = (uint8_t)id; count[s][b] = (uint8_t)(n + 1); }
+        for (int k = 0; k < n; k++) if (node[s][b][k] == id) { refs[s][b][k]++; return; }
+        if (n < 16) { node[s][b][n] = (uint8_t)id; refs[s][b][n] = 1; count[s][b] = (uint8_t)(n + 1); }
+    }
+    void remove (int s, int id)
+    {
+        if (s >= steps) return;
+        const int b = id & 15, n = count[s][b];
+        for (int k = 0; k < n; k++) {
+            if (node[s][b][k] != id) continue;
+            if (--refs[s][b][k] == 0) { node[s][b][k] = node[s][b][n - 1]; refs[s][b][k] = refs[s][b][n - 1]; count[s][b] = (uint8_t)(n - 1); }
+            return;
+        }
     }
     int wavefronts (int s) const { int m = 0; for (int b = 0; b < 16; b++) m = std::max (m, (int)count[s][b]); return m; }
 };
@@ -339,39 +354,60 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
             // slab stores are 128-bit (entry stride 80 bytes): a quarter-warp of 8 lanes per wavefront,
             // conflict-free when its slots differ mod 8
             unsigned loadIJ[2][8] = {{0}}, loadJI[2][8] = {{0}};
+            auto choose = [&] (RingJob &jb) {      // best start / direction of the job's ring against the banks taken so far
+                uint8_t *codes = w.codes.data () + jb.codeStart;
+                const int len = jb.codeLen;
+                if (!(lim.bankAware && jb.single && len >= 2)) return;
+                // candidates: the chain reversed; a closed ring of v elements (v + 1 bytes, first = last)
+                // may also start at any of its v nodes
+                const int v = len - 1, nbRot = jb.closedSingle ? v : 1;
+                long bestCost = 1l << 60;
+                best.assign (codes, codes + len);
+                cand.resize ((size_t)len);
+                for (int rot = 0; rot < nbRot; rot++) {
+                    for (int dir = 0; dir < 2; dir++) {
+                        for (int q = 0; q < len; q++) {
+                            int src;
+                            if (jb.closedSingle) src = dir ? ((rot - q) % v + v) % v : (rot + q) % v;
+                            else src = dir ? len - 1 - q : q;
+                            cand[q] = codes[src];
+                        }
+                        long cost = 0;
+                        for (int q = 0; q < len; q++) cost += banks.cost (2 + q, w.newId[cand[q]]);
+                        if (cost < bestCost) { bestCost = cost; best = cand; }
+                    }
+                }
+                memcpy (codes, best.data (), (size_t)len);
+            };
+            auto place = [&] (const RingJob &jb, bool add) {
+                const uint8_t *codes = w.codes.data () + jb.codeStart;
+                for (int q = 0; q < jb.codeLen; q++) {
+                    if (codes[q] == kRingBreak) continue;
+                    if (add) banks.add (2 + q, w.newId[codes[q]]); else banks.remove (2 + q, w.newId[codes[q]]);
+                }
+            };
             for (int l = 0; l < 16; l++) {
                 const int k = w.order[(size_t)h * 16 + l];
                 if (k < 0) continue;
                 RingJob &jb = w.jobs[k];
-                uint8_t *codes = w.codes.data () + jb.codeStart;
-                const int len = jb.codeLen;
-                if (lim.bankAware && jb.single && len >= 2) {
-                    // candidates: the chain reversed; a closed ring of v elements (v + 1 bytes, first = last)
-                    // may also start at any of its v nodes
-                    const int v = len - 1, nbRot = jb.closedSingle ? v : 1;
-                    long bestCost = 1l << 60;
-                    best.assign (codes, codes + len);
-                    cand.resize ((size_t)len);
-                    for (int rot = 0; rot < nbRot; rot++) {
-                        for (int dir = 0; dir < 2; dir++) {
-                            for (int q = 0; q < len; q++) {
-                                int src;
-                                if (jb.closedSingle) src = dir ? ((rot - q) % v + v) % v : (rot + q) % v;
-                                else src = dir ? len - 1 - q : q;
-                                cand[q] = codes[src];
-                            }
-                            long cost = 0;
-                            for (int q = 0; q < len; q++) cost += banks.cost (2 + q, w.newId[cand[q]]);
-                            if (cost < bestCost) { bestCost = cost; best = cand; }
-                        }
-                    }
-                    memcpy (codes, best.data (), (size_t)len);
-                }
+                choose (jb);
                 banks.add (0, w.newId[jb.i]);
                 banks.add (1, w.newId[jb.j]);
-                for (int q = 0; q < len; q++) if (codes[q] != kRingBreak) banks.add (2 + q, w.newId[codes[q]]);
+                place (jb, true);
                 loadIJ[l >> 3][jb.slotIJ & 7]++;
                 if (jb.slotJI != 0xFFFF) loadJI[l >> 3][jb.slotJI & 7]++;
+            }
+            // coordinate descent: every lane in turn is taken out and re-placed against all the others
+            for (int sweep = 0; sweep < (lim.bankAware ? lim.rotationSweeps : 0); sweep++) {
+                for (int l = 0; l < 16; l++) {
+                    const int k = w.order[(size_t)h * 16 + l];
+                    if (k < 0) continue;
+                    RingJob &jb = w.jobs[k];
+                    if (!(jb.single && jb.codeLen >= 2)) continue;
+                    place (jb, false);
+                    choose (jb);
+                    place (jb, true);
+                }
             }
             for (int s = 0; s < banks.steps; s++) {
                 const int wf = banks.wavefronts (s);

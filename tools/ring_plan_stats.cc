@@ -29,6 +29,7 @@ int main (int argc, char **argv)
     if (getenv ("RING_MORTON")) lim.bisection = false;
     if (getenv ("RING_NOBANK")) lim.bankAware = false;
     if (getenv ("RING_PASSES")) lim.refinePasses = atoi (getenv ("RING_PASSES"));
+    if (getenv ("RING_SWEEPS")) lim.rotationSweeps = atoi (getenv ("RING_SWEEPS"));
     RingPlan plan;
     std::string err;
     auto t0 = std::chrono::steady_clock::now ();
