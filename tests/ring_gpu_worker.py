@@ -62,6 +62,34 @@ def main():
         check(oracle, f"{op} random tets", mfb.Setup(ArrayMesh(coord, e2n, 60, codes), op), rtol=SLIVER_RTOL, tile_rows=8, tile_elems=400)
         coord, e2n = random_tet_mesh(rng, 25, 400)
         check(oracle, f"{op} dense random tets (chains with breaks)", mfb.Setup(ArrayMesh(coord, e2n, 25), op), rtol=SLIVER_RTOL, tile_rows=25, tile_elems=640)
+    # four subdomains on one GPU, interface values through the host halves of the exchange: interface rows
+    # leave the fused kernel raw, everything else inverted (as test_gpu_multirank.py does for TILED)
+    grid, blocks = (9, 8, 7), (2, 2, 1)
+    meshes = [mfb.Mesh.generate(*grid, blocks=blocks, rank=r, seed=5) for r in range(4)]
+    setups = [mfb.Setup(m, "ela") for m in meshes]
+    precs = [np.ascontiguousarray(oracle.fem_iteration(s)[1]) for s in setups]
+    oracle.halo_exchange(precs, [m.intfIndex for m in meshes], [m.intfNodes for m in meshes], [m.neighborsList for m in meshes], 9)
+    want = [oracle.prec_inversion(precs[r], s.row, s.col, s.checkBounds, s.mesh.nbNodes, 1) for r, s in enumerate(setups)]
+    ctxs = [mfb.Context(s, path="ring", nbBlocks=4, rank=r, tile_rows=16, tile_elems=260) for r, s in enumerate(setups)]
+    for c in ctxs:
+        c.assembly_fused()
+    send = [c.halo_pack_host() for c in ctxs]
+    for r, (c, m) in enumerate(zip(ctxs, meshes)):
+        recv = np.zeros_like(send[r])
+        for i in range(m.nbIntf):
+            src = int(m.neighborsList[i]) - 1
+            o = meshes[src]
+            q = [k for k in range(o.nbIntf) if o.neighborsList[k] - 1 == r][0]
+            recv[m.intfIndex[i] * 9:m.intfIndex[i + 1] * 9] = send[src][o.intfIndex[q] * 9:o.intfIndex[q + 1] * 9]
+        c.halo_add_host(recv)
+    for r, c in enumerate(ctxs):
+        c.prec_inversion_interface()
+        v, p = c.download()
+        ev = row_scaled_error(v, oracle.fem_iteration(setups[r])[0], setups[r].row, 9)
+        ep = block_scaled_error(p, want[r], 9)
+        print(f"ring 4 subdomains, rank {r}: values {ev:.2e} prec {ep:.2e}", flush=True)
+        assert ev <= RTOL and ep <= RTOL
+        c.close()
     # EIB size through a property: the element matrices have zero row sums, so every block row of the
     # assembled matrix sums to zero, and RING and TILED agree entry by entry
     mesh = mfb.Mesh.generate(100, 100, 100, seed=1)
