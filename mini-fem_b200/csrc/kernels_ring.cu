@@ -54,6 +54,7 @@ __device__ __forceinline__ unsigned ring_record_head_bytes (uint64_t packed) { r
 // (tools/cuda_cta_emulation.h): the PTX helpers become their emulated counterparts.
 inline void ring_mbar_init (uint64_t *bar, unsigned) { cta_emu::mbar_init (bar); }
 inline void ring_mbar_expect_tx (uint64_t *bar, unsigned bytes) { cta_emu::mbar_expect_tx (bar, bytes); }
+inline void ring_mbar_arrive (uint64_t *bar) { cta_emu::mbar_expect_tx (bar, 0); }
 inline void ring_mbar_wait (uint64_t *bar, unsigned parity) { cta_emu::mbar_wait (bar, parity); }
 inline void ring_bulk_load (void *dst, const void *src, unsigned bytes, uint64_t *bar) { cta_emu::bulk_load (dst, src, bytes, bar); }
 inline void ring_cp_async_f64 (double *dst, const double *src) { *dst = *src; }
@@ -70,6 +71,11 @@ __device__ __forceinline__ void ring_mbar_init (uint64_t *bar, unsigned count)
 __device__ __forceinline__ void ring_mbar_expect_tx (uint64_t *bar, unsigned bytes)
 {
     asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ring_smem_u32 (bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void ring_mbar_arrive (uint64_t *bar)
+{
+    asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ring_smem_u32 (bar)) : "memory");
 }
 
 // Bounded wait: a protocol bug must trap instead of hanging the device.
@@ -144,8 +150,11 @@ ring_assembly_kernel (const RingArgs args)
     auto fetch_tail = [&] (uint64_t packed, const unsigned char *head) {   // thread 0 only, `head` has landed
         const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
         const unsigned bytes = h.blobBytes - h.headBytes;
-        ring_mbar_expect_tx (tailFull, bytes);                           // zero bytes: the phase completes at once
-        if (bytes) ring_bulk_load (sTail, P.blob + ring_record_offset (packed) + h.headBytes, bytes, tailFull);
+        if (bytes) {
+            ring_mbar_expect_tx (tailFull, bytes);
+            ring_bulk_load (sTail, P.blob + ring_record_offset (packed) + h.headBytes, bytes, tailFull);
+        }
+        else ring_mbar_arrive (tailFull);                               // a tile without jobs: the phase completes at once
     };
     auto gather_coords = [&] (const unsigned char *head) {            // all threads, asynchronous
         const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);

@@ -279,3 +279,17 @@ def test_ring_kernel_protocol_under_thread_sanitizer():
         assert "TSAN_RUN_DONE" in res.stdout, res.stdout[-2000:]
         assert "ThreadSanitizer" not in res.stdout, res.stdout[-4000:]
         assert "NaNs left 0" in res.stdout
+
+
+@pytest.mark.parametrize("op", ["ela", "lap"])
+def test_ring_mesh_without_elements(ringlib, kernel_host, oracle, op):
+    """Nodes but no element: empty rows, tiles without jobs (a zero-byte tail), prec from an all-zero
+    diagonal — what the reference computes from its zero-filled arrays."""
+    codes = np.array([0, 52, 10, 0, 54], np.int32)
+    mesh = ArrayMesh(np.arange(15, dtype=np.float64), np.zeros(0, np.int32), 5, codes)
+    setup = mfb.Setup(mesh, op)
+    assert setup.nbEdges == 0
+    _, want_p0, want_p = oracle.fem_iteration(setup)
+    for values, prec in (replay(ringlib, setup)[:2], run_kernel_on_host(kernel_host, setup, ctas=2)):
+        assert values.size == 0
+        assert np.array_equal(prec, want_p, equal_nan=True)
