@@ -110,8 +110,14 @@ struct HalfWarpBanks {
     uint8_t node[kMaxSteps][16][16];
     uint8_t refs[kMaxSteps][16][16];          // lanes of the half-warp loading that word
     uint8_t count[kMaxSteps][16];
+    uint8_t busiest[kMaxSteps];               // max over the banks of count[s][.]
     int steps = 0;
-    void reset (int nbSteps) { steps = std::min (nbSteps, (int)kMaxSteps); memset (count, 0, sizeof (count[0]) * (size_t)steps); }
+    void reset (int nbSteps)
+    {
+        steps = std::min (nbSteps, (int)kMaxSteps);
+        memset (count, 0, sizeof (count[0]) * (size_t)steps);
+        memset (busiest, 0, (size_t)steps);
+    }
     int cost (int s, int id) const
     {
         if (s >= steps) return 0;
@@ -119,16 +125,17 @@ struct HalfWarpBanks {
         for (int k = 0; k < n; k++) if (node[s][b][k] == id) return 0;   // same word: broadcast
         // the step costs as many wavefronts as its busiest bank holds words: joining a bank that
         // already is the busiest one adds a wavefront, joining a quieter one only makes that likelier
-        int busiest = 0;
-        for (int q = 0; q < 16; q++) busiest = std::max (busiest, (int)count[s][q]);
-        return n == 0 ? 0 : (n >= busiest ? 16 + n : n);
+        return n == 0 ? 0 : (n >= busiest[s] ? 16 + n : n);
     }
     void add (int s, int id)
     {
         if (s >= steps) return;
         const int b = id & 15, n = count[s][b];
         for (int k = 0; k < n; k++) if (node[s][b][k] == id) { refs[s][b][k]++; return; }
-        if (n < 16) { node[s][b][n] = (uint8_t)id; refs[s][b][n] = 1; count[s][b] = (uint8_t)(n + 1); }
+        if (n < 16) {
+            node[s][b][n] = (uint8_t)id; refs[s][b][n] = 1; count[s][b] = (uint8_t)(n + 1);
+            busiest[s] = std::max (busiest[s], count[s][b]);
+        }
     }
     void remove (int s, int id)
     {
@@ -136,11 +143,14 @@ struct HalfWarpBanks {
         const int b = id & 15, n = count[s][b];
         for (int k = 0; k < n; k++) {
             if (node[s][b][k] != id) continue;
-            if (--refs[s][b][k] == 0) { node[s][b][k] = node[s][b][n - 1]; refs[s][b][k] = refs[s][b][n - 1]; count[s][b] = (uint8_t)(n - 1); }
+            if (--refs[s][b][k] == 0) {
+                node[s][b][k] = node[s][b][n - 1]; refs[s][b][k] = refs[s][b][n - 1]; count[s][b] = (uint8_t)(n - 1);
+                if (n == busiest[s]) { uint8_t m = 0; for (int q = 0; q < 16; q++) m = std::max (m, count[s][q]); busiest[s] = m; }
+            }
             return;
         }
     }
-    int wavefronts (int s) const { int m = 0; for (int b = 0; b < 16; b++) m = std::max (m, (int)count[s][b]); return m; }
+    int wavefronts (int s) const { return busiest[s]; }
 };
 
 // Plans one tile.  Global -> tile maps are thread-private dense arrays, reset on exit.
@@ -186,6 +196,7 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
     }
     out.nbRows = nbRows;
     out.nbEntries = localStart;
+    w.jobs.reserve ((size_t)localStart);
 
     // ---- jobs: one per mesh edge {i, j}, i owned; both blocks when j is owned too -------------
     auto first_position = [&] (int n, int target) {           // first l in row n with col[l] == target + 1, or -1
@@ -335,7 +346,8 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
     // ---- ring rotation / direction per job, lane after lane of a half-warp ---------------------
     // step 0 loads node i, step 1 node j, step 2 + q the q-th code byte
     static thread_local HalfWarpBanks banks;
-    std::vector<uint8_t> best, cand;
+    std::vector<uint8_t> best;
+    std::vector<int> costOf;
     int maxSteps = 0;
     for (int b = 0; b < nbBatches; b++) {
         int nbSteps = 0;
@@ -361,21 +373,30 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
                 // candidates: the chain reversed; a closed ring of v elements (v + 1 bytes, first = last)
                 // may also start at any of its v nodes
                 const int v = len - 1, nbRot = jb.closedSingle ? v : 1;
+                // cost of having ring node m in step q, once for all candidates
+                const int nbPos = jb.closedSingle ? v : len;
+                costOf.resize ((size_t)len * nbPos);
+                for (int q = 0; q < len; q++) for (int m = 0; m < nbPos; m++) costOf[(size_t)q * nbPos + m] = banks.cost (2 + q, w.newId[codes[m]]);
                 long bestCost = 1l << 60;
-                best.assign (codes, codes + len);
-                cand.resize ((size_t)len);
-                for (int rot = 0; rot < nbRot; rot++) {
-                    for (int dir = 0; dir < 2; dir++) {
+                int bestRot = 0, bestDir = 0;
+                for (int rot = 0; rot < nbRot && bestCost > 0; rot++) {
+                    for (int dir = 0; dir < 2 && bestCost > 0; dir++) {
+                        long cost = 0;
                         for (int q = 0; q < len; q++) {
                             int src;
                             if (jb.closedSingle) src = dir ? ((rot - q) % v + v) % v : (rot + q) % v;
                             else src = dir ? len - 1 - q : q;
-                            cand[q] = codes[src];
+                            cost += costOf[(size_t)q * nbPos + src];
                         }
-                        long cost = 0;
-                        for (int q = 0; q < len; q++) cost += banks.cost (2 + q, w.newId[cand[q]]);
-                        if (cost < bestCost) { bestCost = cost; best = cand; }
+                        if (cost < bestCost) { bestCost = cost; bestRot = rot; bestDir = dir; }
                     }
+                }
+                best.resize ((size_t)len);
+                for (int q = 0; q < len; q++) {
+                    int src;
+                    if (jb.closedSingle) src = bestDir ? ((bestRot - q) % v + v) % v : (bestRot + q) % v;
+                    else src = bestDir ? len - 1 - q : q;
+                    best[q] = codes[src];
                 }
                 memcpy (codes, best.data (), (size_t)len);
             };
@@ -426,7 +447,9 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
     // every node to the bank where it meets the fewest others, then rotate again.
     auto renumber_pass = [&] () {
         const int S = std::min (maxSteps + 2, (int)HalfWarpBanks::kMaxSteps);
-        std::vector<std::vector<int>> app ((size_t)nbRef);
+        static thread_local std::vector<std::vector<int>> app;          // inner vectors keep their capacity from tile to tile
+        if ((int)app.size () < nbRef) app.resize ((size_t)nbRef);
+        for (int n = 0; n < nbRef; n++) app[n].clear ();
         for (int h = 0; h < nbHalf; h++) {
             for (int l = 0; l < 16; l++) {
                 const int k = w.order[(size_t)h * 16 + l];
