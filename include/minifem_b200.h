@@ -202,7 +202,9 @@ int64_t mfb_ctx_launch_count (mfb_ctx *ctx);
 int mfb_ctx_device_bytes (mfb_ctx *ctx, int64_t *meshBytes, int64_t *planBytes);
 /* Tile statistics of the TILED plan: [0] tiles [1] tile elements (with duplicates)
  * [2] contributions [3] max rows [4] max elems [5] shared memory bytes per CTA
- * [6] padded lane-steps of the off-diagonal pass [7] largest tile record in bytes. */
+ * [6] padded lane-steps of the off-diagonal pass [7] largest tile record in bytes.
+ * RING plan: [1] jobs (mesh edges) [2] ring steps (element visits) [4] max tile-local nodes
+ * [6] padded lane-steps of the job phase; the others as above. */
 int mfb_ctx_plan_stats (mfb_ctx *ctx, int64_t stats[8]);
 
 /* Multi-GPU: one context per process / GPU, NCCL over NVLink for the interface sum. */

@@ -43,9 +43,22 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
     args.coord = coord; args.values = values; args.prec = prec; args.checkBounds = checkBounds;
     args.nbNodes = nbNodes; args.fusePrec = fusePrec; args.firstTile = 0; args.lastTile = hp.nbTiles;
     if (hp.nbTiles == 0) return 0;
-    const int grid = std::max (1, std::min (ctas > 0 ? ctas : 3, hp.nbTiles));
     const size_t smem = ring_smem_bytes (operatorID, args.plan);
-    if (operatorID == 0) cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<1> (args); });
-    else                 cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<9> (args); });
+    auto launch = [&] (int firstTile, int nbTiles, int grid) {
+        if (nbTiles <= 0) return;
+        args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
+        grid = std::max (1, std::min (grid, nbTiles));
+        if (operatorID == 0) cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<1> (args); });
+        else                 cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<9> (args); });
+    };
+    const int grid = ctas > 0 ? ctas : 3;
+    if (isInterface) {
+        // as the fused multi-GPU iteration launches it (capi.cu do_iteration): the tiles that own interface
+        // nodes first, then the interior tiles on a grid whose CTAs take four tiles each
+        const int nIntf = hp.nbInterfaceTiles, nInterior = hp.nbTiles - nIntf;
+        launch (0, nIntf, grid);
+        launch (nIntf, nInterior, (nInterior + 3) / 4);
+    }
+    else launch (0, hp.nbTiles, grid);
     return 0;
 }
