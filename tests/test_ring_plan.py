@@ -245,6 +245,17 @@ def test_ring_kernel_source_on_host_threads(kernel_host, oracle, op, grid, rows,
     check_against_oracle(oracle, setup, values, prec)
 
 
+@pytest.mark.parametrize("op", ["ela", "lap"])
+def test_ring_kernel_source_equals_replay_bit_for_bit(ringlib, kernel_host, op):
+    """Two independent readings of the plan — the sequential replay and the kernel's own source on 256
+    host threads per CTA — give identical bits (both test aids are built without FMA contraction)."""
+    mesh = mfb.Mesh.generate(9, 8, 7, seed=8)
+    setup = mfb.Setup(mesh, op)
+    v_replay, p_replay, _ = replay(ringlib, setup)
+    v_kernel, p_kernel = run_kernel_on_host(kernel_host, setup, ctas=2)
+    assert np.array_equal(v_replay, v_kernel) and np.array_equal(p_replay, p_kernel, equal_nan=True)
+
+
 def test_ring_kernel_source_unfused_interface_and_random_tets(kernel_host, oracle):
     mesh = mfb.Mesh.generate(6, 6, 6, blocks=(2, 1, 1), rank=1, seed=2)
     setup = mfb.Setup(mesh, "ela")
