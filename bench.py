@@ -334,6 +334,7 @@ def main():
     if args.path == "auto":
         selection = choose_path(args, rank, local)
         args.path = selection["chosen"]
+        os.environ["MFB_BENCH_AUTO_CHOSE"] = args.path
     grid, blocks = global_layout(args, world)
     t0 = time.perf_counter()
     mesh = mfb.Mesh.generate(*grid, blocks=blocks, rank=rank, seed=1)
@@ -449,6 +450,8 @@ def main():
             "other_paths": other}
     if selection:
         line["path_selection"] = selection
+    elif os.environ.get("MFB_BENCH_AUTO_CHOSE") == "tiled-after-ring-failure":
+        line["path_selection"] = {"chosen": "tiled", "note": "RING passed its probe but its measurement run failed; see stderr"}
     if world == 1 and not args.no_cpu_baseline:
         cores = args.cpu_ranks or (os.cpu_count() or 1)
         try:
@@ -475,4 +478,15 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception as exc:                                     # noqa: BLE001
+        # --path auto picked RING after its probe and the measurement still failed: the line must not be
+        # lost to a path that has one round of hardware history less than TILED — start over on TILED in a
+        # fresh process (a CUDA fault leaves this one without a usable context).  Single process only: under
+        # torchrun the other ranks are still inside their collectives.
+        if os.environ.get("MFB_BENCH_AUTO_CHOSE") == "ring" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            print(f"bench.py: the RING run failed ({exc!r}); measuring TILED instead", file=sys.stderr, flush=True)
+            os.environ["MFB_BENCH_AUTO_CHOSE"] = "tiled-after-ring-failure"
+            os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--path", "tiled"])
+        raise
