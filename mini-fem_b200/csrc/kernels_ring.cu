@@ -15,8 +15,8 @@
 //      list) is fetched at the start of tile t, the TAIL (batches, jobs, ring codes) and the
 //      coordinates (cp.async) of tile t+1 while tile t is in its write-out;
 //   1. job phase: one lane per edge, 32 jobs per warp batch, ring codes 8 to a 64-bit word;
-//      finished 3x3 blocks go to the tile-wide slab at the slots of their CSR entries;
-//      (entry stride 80 bytes, so a block leaves as four 128-bit stores and one 64-bit store);
+//      finished 3x3 blocks go to the tile-wide slab at the slots of their CSR entries (entry stride
+//      80 bytes, so a block leaves as four 128-bit stores and one 64-bit store);
 //   2. write-out: one warp per row, 3 groups of 10 lanes (9 components + one idle lane, which keeps the
 //      slab reads conflict-free) copy the row's slab run to global memory as contiguous 216-byte
 //      pieces and sum it; lanes 0..8 store the diagonal entry;
