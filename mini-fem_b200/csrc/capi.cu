@@ -586,7 +586,7 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     if (c->path == MFB_PATH_RING) {          // a write-once path like TILED: same stages, same fused iteration
         c->ring = true;
         c->path = MFB_PATH_TILED;
-        if (c->threads != 256) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 256 threads per CTA");
+        if (c->threads != 256 && c->threads != 384) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 256 or 384 threads per CTA");
     }
     if (c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {
         return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256], or the pipelined kernel's CTA size");

@@ -114,8 +114,10 @@ __host__ __device__ __forceinline__ unsigned ring_align128 (unsigned x) { return
 // doubles per slab entry: an elasticity block is padded to 80 bytes so that it is 16-byte aligned
 __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim == 9 ? 10 : 1; }
 
-template <int OPDIM>
-__global__ void __launch_bounds__(256, 3)
+// THREADS / MINB: 256 threads, three CTAs per SM (default) or 384 threads, two CTAs per SM (larger tiles:
+// mfb_options.threads = 384 with tileRows / tileElems raised, e.g. 54 / 810) — 24 warps per SM either way.
+template <int OPDIM, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 ring_assembly_kernel (const RingArgs args)
 {
 #ifdef MFB_RING_HOST_EMULATION
@@ -358,7 +360,13 @@ size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
 #ifndef MFB_RING_HOST_EMULATION
 cudaError_t ring_configure (int operatorID)
 {
-    return operatorID == 0 ? ring_opt_in (ring_assembly_kernel<1>) : ring_opt_in (ring_assembly_kernel<9>);
+    cudaError_t e;
+    if (operatorID == 0) {
+        if ((e = ring_opt_in (ring_assembly_kernel<1, 256, 3>)) != cudaSuccess) return e;
+        return ring_opt_in (ring_assembly_kernel<1, 384, 2>);
+    }
+    if ((e = ring_opt_in (ring_assembly_kernel<9, 256, 3>)) != cudaSuccess) return e;
+    return ring_opt_in (ring_assembly_kernel<9, 384, 2>);
 }
 
 cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,
@@ -371,8 +379,14 @@ cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTi
     args.checkBounds = checkBounds; args.nbNodes = nbNodes; args.fusePrec = fusePrec;
     args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
     const int grid = std::max (1, std::min (ctas, nbTiles));
-    if (operatorID == 0) ring_assembly_kernel<1><<<grid, threads, smemBytes, stream>>> (args);
-    else                 ring_assembly_kernel<9><<<grid, threads, smemBytes, stream>>> (args);
+    if (threads == 384) {
+        if (operatorID == 0) ring_assembly_kernel<1, 384, 2><<<grid, 384, smemBytes, stream>>> (args);
+        else                 ring_assembly_kernel<9, 384, 2><<<grid, 384, smemBytes, stream>>> (args);
+    }
+    else {
+        if (operatorID == 0) ring_assembly_kernel<1, 256, 3><<<grid, 256, smemBytes, stream>>> (args);
+        else                 ring_assembly_kernel<9, 256, 3><<<grid, 256, smemBytes, stream>>> (args);
+    }
     return cudaGetLastError ();
 }
 #endif

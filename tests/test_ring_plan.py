@@ -217,11 +217,11 @@ def test_ring_plan_property(ringlib, oracle):
 def kernel_host():
     lib = C.CDLL(os.path.join(ROOT, "tools", "libmfb_ringkernel_host.so"))
     lib.mfb_ring_kernel_host_error.restype = C.c_char_p
-    lib.mfb_ring_kernel_host.argtypes = [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p] * 2
+    lib.mfb_ring_kernel_host.argtypes = [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_int]
     return lib
 
 
-def run_kernel_on_host(lib, setup, rows=0, entries=0, ctas=3, fuse=1, interface=None):
+def run_kernel_on_host(lib, setup, rows=0, entries=0, ctas=3, fuse=1, interface=None, threads=256):
     m = setup.mesh
     dim = setup.operatorDim
     values = np.full(setup.nbEdges * dim, np.nan)
@@ -230,7 +230,7 @@ def run_kernel_on_host(lib, setup, rows=0, entries=0, ctas=3, fuse=1, interface=
             np.ascontiguousarray(setup.col, np.int32), np.ascontiguousarray(m.coord, np.float64),
             np.ascontiguousarray(setup.checkBounds, np.int32)]
     rc = lib.mfb_ring_kernel_host(setup.operatorID, m.nbNodes, keep[0].size // 4, *[_p(k) for k in keep], _p(interface),
-                                  rows, entries, ctas, fuse, _p(values), _p(prec))
+                                  rows, entries, ctas, fuse, _p(values), _p(prec), threads)
     assert rc == 0, lib.mfb_ring_kernel_host_error().decode()
     return values, prec
 
@@ -254,6 +254,15 @@ def test_ring_kernel_source_equals_replay_bit_for_bit(ringlib, kernel_host, op):
     v_replay, p_replay, _ = replay(ringlib, setup)
     v_kernel, p_kernel = run_kernel_on_host(kernel_host, setup, ctas=2)
     assert np.array_equal(v_replay, v_kernel) and np.array_equal(p_replay, p_kernel, equal_nan=True)
+
+
+@pytest.mark.parametrize("op", ["ela", "lap"])
+def test_ring_kernel_source_384_threads(kernel_host, oracle, op):
+    """The two-CTAs-per-SM instantiation (12 warps, larger tiles)."""
+    mesh = mfb.Mesh.generate(9, 8, 8, seed=9)
+    setup = mfb.Setup(mesh, op)
+    values, prec = run_kernel_on_host(kernel_host, setup, rows=54, entries=810, ctas=2, threads=384)
+    check_against_oracle(oracle, setup, values, prec)
 
 
 def test_ring_kernel_source_unfused_interface_and_random_tets(kernel_host, oracle):

@@ -32,6 +32,9 @@ for caps in "48 720" "64 960" "24 360"; do
     timeout 300 python tools/quick_bench.py --paths ring --steps 20 --tile-rows $1 --tile-elems $2 > gpurun_out/ring_quick_bench_$1.log 2>&1
     tail -1 gpurun_out/ring_quick_bench_$1.log
 done
+# two CTAs of 384 threads per SM with larger tiles (fewer edges cut by tile borders)
+timeout 300 python tools/quick_bench.py --paths ring --steps 20 --threads 384 --tile-rows 54 --tile-elems 810 > gpurun_out/ring_quick_bench_384.log 2>&1
+tail -1 gpurun_out/ring_quick_bench_384.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/ring_launches.csv \
     python bench.py --path ring --steps 3 --warmup 3 --no-cpu-baseline --no-other-paths > gpurun_out/ring_bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:ring_assembly -s 4 -c 1 -o gpurun_out/ring_ela_full \

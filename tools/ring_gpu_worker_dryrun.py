@@ -6,7 +6,7 @@ sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__im
 import ring_gpu_worker as w
 mfb = w.mfb
 klib = C.CDLL(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "libmfb_ringkernel_host.so"))
-klib.mfb_ring_kernel_host.argtypes = [C.c_int]*3 + [C.c_void_p]*6 + [C.c_int]*4 + [C.c_void_p]*2
+klib.mfb_ring_kernel_host.argtypes = [C.c_int]*3 + [C.c_void_p]*6 + [C.c_int]*4 + [C.c_void_p]*2 + [C.c_int]
 def p(a): return None if a is None else a.ctypes.data_as(C.c_void_p)
 class FakeCtx:
     def __init__(self, setup, path="tiled", nbBlocks=1, rank=0, tile_rows=0, tile_elems=0, ctas=0, bank_aware=True, **kw):
@@ -22,7 +22,7 @@ class FakeCtx:
         keep = [np.ascontiguousarray(s.elemToNode, np.int32), np.ascontiguousarray(s.row, np.int32), np.ascontiguousarray(s.col, np.int32),
                 np.ascontiguousarray(m.coord, np.float64), np.ascontiguousarray(s.checkBounds, np.int32)]
         rc = klib.mfb_ring_kernel_host(s.operatorID, m.nbNodes, keep[0].size//4, *[p(k) for k in keep], p(self.intf), self.rows, self.entries,
-                                       3 if self.ctas <= 0 else min(self.ctas, 4), fuse, p(v), p(pr))
+                                       3 if self.ctas <= 0 else min(self.ctas, 4), fuse, p(v), p(pr), 256)
         assert rc == 0
         self.v, self.n = v, self.n + 1
         if fuse: self.p = pr

@@ -18,10 +18,11 @@ static std::string g_error;
 extern "C" const char *mfb_ring_kernel_host_error (void) { return g_error.c_str (); }
 
 // One launch of ring_assembly_kernel over all tiles with `ctas` CTAs of 256 threads (the
-// persistent-grid stride is `ctas`).  fusePrec as on the device.  values / prec are host arrays.
+// persistent-grid stride is `ctas`; threads = 384 selects the two-CTAs-per-SM instantiation).  fusePrec as
+// on the device.  values / prec are host arrays.
 extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, const int *elemToNode, const int *row,
                                      const int *col, const double *coord, const int *checkBounds, const uint8_t *isInterface,
-                                     int maxRows, int maxEntries, int ctas, int fusePrec, double *values, double *prec)
+                                     int maxRows, int maxEntries, int ctas, int fusePrec, double *values, double *prec, int threads)
 {
     RingPlanLimits lim;
     if (maxRows > 0) lim.maxRows = maxRows;
@@ -48,8 +49,14 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
         if (nbTiles <= 0) return;
         args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
         grid = std::max (1, std::min (grid, nbTiles));
-        if (operatorID == 0) cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<1> (args); });
-        else                 cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<9> (args); });
+        if (threads == 384) {
+            if (operatorID == 0) cta_emu::launch (grid, 384, smem, [&] () { ring_assembly_kernel<1, 384, 2> (args); });
+            else                 cta_emu::launch (grid, 384, smem, [&] () { ring_assembly_kernel<9, 384, 2> (args); });
+        }
+        else {
+            if (operatorID == 0) cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<1, 256, 3> (args); });
+            else                 cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<9, 256, 3> (args); });
+        }
     };
     const int grid = ctas > 0 ? ctas : 3;
     if (isInterface) {

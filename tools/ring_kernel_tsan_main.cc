@@ -8,7 +8,7 @@
 #include <vector>
 #include "../mini-fem_b200/host/mesh_data.h"
 #include "../mini-fem_b200/host/mesh_topology.h"
-extern "C" int mfb_ring_kernel_host (int, int, int, const int*, const int*, const int*, const double*, const int*, const uint8_t*, int, int, int, int, double*, double*);
+extern "C" int mfb_ring_kernel_host (int, int, int, const int*, const int*, const int*, const double*, const int*, const uint8_t*, int, int, int, int, double*, double*, int);
 extern "C" const char *mfb_ring_kernel_host_error (void);
 using namespace mfb;
 int main (int argc, char **argv)
@@ -23,7 +23,7 @@ int main (int argc, char **argv)
         const int dim = op ? 9 : 1;
         std::vector<double> values ((size_t)row[m.nbNodes] * dim, NAN), prec ((size_t)m.nbNodes * dim, NAN);
         int rc = mfb_ring_kernel_host (op, m.nbNodes, m.nbElem, m.elemToNode.data (), row.data (), col.data (), m.coord.data (), cb.data (), nullptr,
-                                       rows, entries, ctas, 1, values.data (), prec.data ());
+                                       rows, entries, ctas, 1, values.data (), prec.data (), argc > 5 ? atoi (argv[5]) : 256);
         if (rc) { printf ("error: %s\n", mfb_ring_kernel_host_error ()); return 1; }
         size_t nans = 0; for (double v : values) nans += std::isnan (v); for (double v : prec) nans += std::isnan (v);
         printf ("op %d: %d nodes %d elems, NaNs left %zu\n", op, m.nbNodes, m.nbElem, nans);
