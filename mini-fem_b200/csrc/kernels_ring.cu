@@ -111,6 +111,9 @@ __device__ __forceinline__ void ring_cp_async_wait_all () { asm volatile ("cp.as
 
 __host__ __device__ __forceinline__ unsigned ring_align128 (unsigned x) { return (x + 127u) & ~127u; }
 
+// doubles per coordinate plane: tile-local node ids are one byte (kRingMaxNodes = 254)
+constexpr int kRingPlane = 256;
+
 // doubles per slab entry: an elasticity block is padded to 80 bytes so that it is 16-byte aligned
 __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim == 9 ? 10 : 1; }
 
@@ -131,7 +134,8 @@ ring_assembly_kernel (const RingArgs args)
 
     // shared memory: [head 0][head 1][tail][X Y Z][slab][diagonal blocks][3 mbarriers]
     const unsigned headBytes = ring_align128 (P.maxHeadBytes), tailBytes = ring_align128 (P.maxTailBytes);
-    const int planeStride = (P.maxNodes + 15) & ~15;                  // planes start on a 128-byte line: bank = id mod 16
+    constexpr int planeStride = kRingPlane;                           // planes start on a 128-byte line: bank = id mod 16;
+                                                                      // a constant, so that Y and Z are immediate offsets from X
     unsigned char *sHead0 = smemRaw, *sTail = smemRaw + 2 * headBytes;
     double *sX = reinterpret_cast<double*> (sTail + tailBytes), *sY = sX + planeStride, *sZ = sY + planeStride;
     double *slab = sZ + planeStride;
@@ -210,21 +214,37 @@ ring_assembly_kernel (const RingArgs args)
             const int sIJ = (int)((job >> 16) & 0xFFFF), sJI = (int)((job >> 32) & 0xFFFF);
             const double xi[3] = {sX[i], sY[i], sZ[i]};
             const double d[3] = {sX[j] - xi[0], sY[j] - xi[1], sZ[j] - xi[2]};
+            const int len = (int)(job >> 48), nbSteps = rb.nbSteps;
             double acc[OPDIM], u[3] = {0.0, 0.0, 0.0};
             #pragma unroll
             for (int q = 0; q < OPDIM; q++) acc[q] = 0.0;
-            bool have = false;
             const uint64_t *cw = codes + rb.codeBase + lane;
-            int remaining = rb.nbSteps;
-            for (int wd = 0; wd < rb.nbWords; wd++, remaining -= 8) {
-                uint64_t word = cw[wd * 32];
-                const int n = min (remaining, 8);
-                for (int q = 0; q < n; q++, word >>= 8) {
+            uint64_t word = 0;
+            if (rb.flags == 0) {
+                // regular batch (every mesh without non-manifold edges): one chain per job.  Byte 0 names its
+                // first node, every further byte adds one element; bytes beyond the job's length name a valid
+                // node and their contribution is masked — no branch inside the step.
+                if (nbSteps > 0) {
+                    word = cw[0];
                     const int id = (int)(word & 0xFF);
-                    if (id >= kRingBreak) {                 // idle step, or the chain of elements is interrupted
-                        if (id == kRingBreak) have = false;
-                        continue;
-                    }
+                    u[0] = sX[id] - xi[0]; u[1] = sY[id] - xi[1]; u[2] = sZ[id] - xi[2];
+                }
+                for (int k = 1; k < nbSteps; k++) {
+                    if ((k & 7) == 0) word = cw[(k >> 3) * 32]; else word >>= 8;
+                    const int id = (int)(word & 0xFF);
+                    const double w[3] = {sX[id] - xi[0], sY[id] - xi[1], sZ[id] - xi[2]};
+                    ring_accumulate<OPDIM> (d, u, w, acc, k < len);
+                    u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
+                }
+            }
+            else {
+                // general batch: chains separated by breaks
+                bool have = false;
+                for (int k = 0; k < nbSteps; k++) {
+                    if ((k & 7) == 0) word = cw[(k >> 3) * 32]; else word >>= 8;
+                    const int id = (int)(word & 0xFF);
+                    if (k >= len) continue;
+                    if (id == kRingBreak) { have = false; continue; }
                     const double w[3] = {sX[id] - xi[0], sY[id] - xi[1], sZ[id] - xi[2]};
                     if (have) ring_accumulate<OPDIM> (d, u, w, acc);
                     u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
@@ -350,7 +370,7 @@ cudaError_t ring_opt_in (K kernel)
 size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
 {
     const int opDim = operatorID == 0 ? 1 : 9;
-    const size_t planeStride = ((size_t)plan.maxNodes + 15) & ~(size_t)15;
+    const size_t planeStride = kRingPlane;
     const size_t doubles = 3 * planeStride + (((size_t)plan.maxEntries * ring_slab_stride (opDim) + 15) & ~(size_t)15) +
                            (((size_t)plan.maxRows * opDim + 1) & ~(size_t)1);
     return 2 * (size_t)ring_align128 (plan.maxHeadBytes) + ring_align128 (plan.maxTailBytes) + doubles * sizeof (double) +

@@ -55,8 +55,10 @@ MFB_RM double ring_rcp (double x)
 // the order of p and q does not matter (both normals and det change sign).
 // OPDIM 9: acc = the 3x3 sum A_ij (row component from node i); OPDIM 1: acc[0] = sum of
 // grad_i . grad_j, the Laplacian entry (src/assembly.cc:539-541).
+// live = false: a padding step of the regular loop; the contribution is discarded by selecting a zero
+// weight (the operands are finite coordinates differences; a degenerate u, w only poisons r, which is dropped).
 template <int OPDIM>
-MFB_RM void ring_accumulate (const double d[3], const double u[3], const double w[3], double acc[OPDIM])
+MFB_RM void ring_accumulate (const double d[3], const double u[3], const double w[3], double acc[OPDIM], bool live = true)
 {
     const double njx = u[1] * w[2] - u[2] * w[1];
     const double njy = u[2] * w[0] - u[0] * w[2];
@@ -66,7 +68,8 @@ MFB_RM void ring_accumulate (const double d[3], const double u[3], const double 
     const double niy = njy + (ez * d[0] - ex * d[2]);
     const double niz = njz + (ex * d[1] - ey * d[0]);
     const double det = njx * d[0] + njy * d[1] + njz * d[2];
-    const double r = -ring_rcp (det * det);
+    const double rr = -ring_rcp (det * det);
+    const double r = live ? rr : 0.0;
     if (OPDIM == 1) {
         acc[0] += r * (nix * njx + niy * njy + niz * njz);
     }

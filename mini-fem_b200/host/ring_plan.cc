@@ -353,7 +353,12 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
         int nbSteps = 0;
         for (int l = 0; l < 32; l++) if (w.order[(size_t)b * 32 + l] >= 0) nbSteps = std::max (nbSteps, w.jobs[w.order[(size_t)b * 32 + l]].codeLen);
         RingBatch rb;
-        rb.codeBase = 0; rb.nbSteps = (uint16_t)nbSteps; rb.nbWords = (uint16_t)((nbSteps + 7) / 8);
+        rb.codeBase = 0; rb.nbSteps = (uint16_t)nbSteps; rb.flags = 0;
+        for (int l = 0; l < 32; l++) {
+            const int k = w.order[(size_t)b * 32 + l];
+            if (k < 0) continue;
+            for (int q = 0; q < w.jobs[k].codeLen; q++) if (w.codes[(size_t)w.jobs[k].codeStart + q] == kRingBreak) rb.flags |= kRingBatchGeneral;
+        }
         w.batches.push_back (rb);
         out.paddedSteps += (int64_t)32 * nbSteps;
         maxSteps = std::max (maxSteps, nbSteps);
@@ -515,7 +520,7 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
     at += 256u * (uint32_t)nbBatches;
     const uint32_t offCodes = at;
     uint32_t words = 0;
-    for (RingBatch &rb : w.batches) { rb.codeBase = words * 32; words += rb.nbWords; }
+    for (RingBatch &rb : w.batches) { rb.codeBase = words * 32; words += (rb.nbSteps + 7u) / 8u; }
     at += 256u * words;
     out.headBytes = headBytes;
     out.blob.assign ((size_t)at, 0);
@@ -535,20 +540,21 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
     uint64_t *codesOut = reinterpret_cast<uint64_t*> (base + offCodes);
     for (int b = 0; b < nbBatches; b++) {
         const RingBatch &rb = w.batches[b];
+        const int nbWords = (rb.nbSteps + 7) / 8;
         for (int l = 0; l < 32; l++) {
             const int k = w.order[(size_t)b * 32 + l];
             if (k < 0) {
-                jobsOut[(size_t)b * 32 + l] = ring_job (0, 0, 0xFFFF, 0xFFFF);
-                for (int wd = 0; wd < rb.nbWords; wd++) codesOut[(size_t)rb.codeBase + (size_t)wd * 32 + l] = ~0ull;
+                jobsOut[(size_t)b * 32 + l] = ring_job (0, 0, 0xFFFF, 0xFFFF, 0);          // node 0 exists in every tile
+                for (int wd = 0; wd < nbWords; wd++) codesOut[(size_t)rb.codeBase + (size_t)wd * 32 + l] = 0;
                 continue;
             }
             const RingJob &jb = w.jobs[k];
-            jobsOut[(size_t)b * 32 + l] = ring_job (w.newId[jb.i], w.newId[jb.j], jb.slotIJ, jb.slotJI);
-            for (int wd = 0; wd < rb.nbWords; wd++) {
+            jobsOut[(size_t)b * 32 + l] = ring_job (w.newId[jb.i], w.newId[jb.j], jb.slotIJ, jb.slotJI, jb.codeLen);
+            for (int wd = 0; wd < nbWords; wd++) {
                 uint64_t word = 0;
                 for (int q = 0; q < 8; q++) {
                     const int pos = wd * 8 + q;
-                    int byte = kRingIdle;
+                    int byte = w.newId[jb.i];                  // padding: any valid node, the step is masked
                     if (pos < jb.codeLen) {
                         const int c = w.codes[(size_t)jb.codeStart + pos];
                         byte = c == kRingBreak ? kRingBreak : w.newId[c];
@@ -773,28 +779,31 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
         if (expectStart != h.nbEntries) { error = "entry count mismatch"; return -1; }
         for (int b = 0; b < h.nbBatches; b++) {
             const RingBatch &rb = batches[b];
-            if (rb.nbWords != (rb.nbSteps + 7) / 8) { error = "batch word count"; return -1; }
+            const int nbWords = (rb.nbSteps + 7) / 8;
+            bool batchHasBreak = false;
             for (int lane = 0; lane < 32; lane++) {
                 const uint64_t job = jobs[(size_t)b * 32 + lane];
                 const int li = (int)(job & 0xFF), lj = (int)((job >> 8) & 0xFF);
-                const int sIJ = (int)((job >> 16) & 0xFFFF), sJI = (int)((job >> 32) & 0xFFFF);
+                const int sIJ = (int)((job >> 16) & 0xFFFF), sJI = (int)((job >> 32) & 0xFFFF), len = (int)(job >> 48);
                 std::vector<int> bytes;
-                for (int wd = 0; wd < rb.nbWords; wd++) {
+                for (int wd = 0; wd < nbWords; wd++) {
                     const uint64_t word = codes[(size_t)rb.codeBase + (size_t)wd * 32 + lane];
                     for (int q = 0; q < 8 && wd * 8 + q < rb.nbSteps; q++) bytes.push_back ((int)((word >> (8 * q)) & 0xFF));
                 }
+                if (len > rb.nbSteps) { error = "job longer than its batch"; return -1; }
+                // bytes beyond the job's length are loaded and masked: they must name a node of the tile
+                for (int q = len; q < rb.nbSteps; q++) if (bytes[q] >= h.nbNodes) { error = "padding byte is not a node of the tile"; return -1; }
                 if (sIJ == 0xFFFF) {                                   // idle lane
-                    if (sJI != 0xFFFF) { error = "idle lane with a transposed slot"; return -1; }
-                    for (int c : bytes) if (c != kRingIdle) { error = "idle lane with codes"; return -1; }
+                    if (sJI != 0xFFFF || len != 0) { error = "idle lane with a transposed slot or codes"; return -1; }
                     continue;
                 }
+                bytes.resize ((size_t)len);
                 if (li >= h.nbNodes || lj >= h.nbNodes || sIJ >= h.nbEntries || (sJI != 0xFFFF && sJI >= h.nbEntries)) { error = "job out of range"; return -1; }
                 const int gi = tileNodes[li], gj = tileNodes[lj];
                 const int eIJ = slotEntry[sIJ];
                 if (entrySeen[eIJ]) { error = "CSR entry written twice"; return -1; }
                 entrySeen[eIJ] = 1;
-                bool empty = true;
-                for (int c : bytes) empty &= c == kRingIdle;
+                const bool empty = len == 0;
                 // the entry must sit in row i; with elements to add, its column must be j
                 {
                     int r = 0;
@@ -813,11 +822,8 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
                 // walk the chains: consecutive nodes p, q name the element {i, j, p, q}
                 elemsOfEdge.clear ();
                 int prev = -1;
-                bool ended = false;
                 for (int c : bytes) {
-                    if (c == kRingIdle) { ended = true; continue; }
-                    if (ended) { error = "code after the end of a job"; return -1; }
-                    if (c == kRingBreak) { prev = -1; continue; }
+                    if (c == kRingBreak) { prev = -1; batchHasBreak = true; continue; }
                     if (c >= h.nbNodes) { error = "ring node out of range"; return -1; }
                     const int g = tileNodes[c];
                     if (prev >= 0) {
@@ -847,6 +853,8 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
                     prev = g;
                 }
             }
+            // the kernel's regular loop takes every byte for a node: a break needs the general loop
+            if (batchHasBreak != ((rb.flags & kRingBatchGeneral) != 0)) { error = "batch flag does not match its codes"; return -1; }
         }
     }
     if (rowsTotal != nbNodes) { error = "not every node is owned by a tile"; return -1; }

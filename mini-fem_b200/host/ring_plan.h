@@ -36,8 +36,8 @@
 
 namespace mfb {
 
-constexpr int kRingIdle  = 0xFF;   // code byte: nothing to do in this step
 constexpr int kRingBreak = 0xFE;   // code byte: the chain of elements is interrupted, the next node starts a new one
+constexpr int kRingBatchGeneral = 1; // RingBatch::flags: some job of the batch holds a break (the kernel's general loop)
 constexpr int kRingMaxNodes = 254; // tile-local node ids 0 .. 253
 
 struct RingTileHeader {            // 32 bytes
@@ -45,7 +45,8 @@ struct RingTileHeader {            // 32 bytes
     uint32_t offNodes;             // int[nbNodes]: 0-based global ids by tile-local id (holes name a valid node)
     uint32_t headBytes;            // bytes [0, headBytes) = header + rows + nodes; the tail starts here with RingBatch[nbBatches]
     uint32_t offJobs;              // uint64[32 * nbBatches]
-    uint32_t offCodes;             // uint64[]: per batch [word][32 lanes], 8 code bytes per word, low byte first
+    uint32_t offCodes;             // uint64[]: per batch [word][32 lanes], 8 code bytes per word, low byte first;
+                                   // a job's bytes beyond its length name a valid node (they are loaded and masked)
     uint32_t blobBytes;
 };
 
@@ -60,15 +61,17 @@ struct RingRow {                   // 16 bytes per owned row, right after the he
 
 struct RingBatch {                 // 8 bytes per warp batch of 32 jobs
     uint32_t codeBase;             // first code word of the batch (index into the codes section)
-    uint16_t nbSteps;              // code bytes to walk (longest job of the batch)
-    uint16_t nbWords;              // ceil (nbSteps / 8)
+    uint16_t nbSteps;              // code bytes to walk (longest job of the batch); ceil (nbSteps / 8) code words per lane
+    uint16_t flags;                // kRingBatchGeneral
 };
 
-// job word: i | j << 8 | slotIJ << 16 | slotJI << 32; slots are tile-local entry indices
-// (slab position = slot * operatorDim), 0xFFFF = no such block; an idle lane has both 0xFFFF.
-inline uint64_t ring_job (int i, int j, int slotIJ, int slotJI)
+// job word: i | j << 8 | slotIJ << 16 | slotJI << 32 | len << 48; slots are tile-local entry indices
+// (slab position = slot * slab stride), 0xFFFF = no such block; len = code bytes of the job (byte 0 names the
+// first node of a chain, every further node byte adds one element); an idle lane has both slots 0xFFFF and len 0.
+inline uint64_t ring_job (int i, int j, int slotIJ, int slotJI, int len)
 {
-    return (uint64_t)(i & 0xFF) | ((uint64_t)(j & 0xFF) << 8) | ((uint64_t)(slotIJ & 0xFFFF) << 16) | ((uint64_t)(slotJI & 0xFFFF) << 32);
+    return (uint64_t)(i & 0xFF) | ((uint64_t)(j & 0xFF) << 8) | ((uint64_t)(slotIJ & 0xFFFF) << 16) |
+           ((uint64_t)(slotJI & 0xFFFF) << 32) | ((uint64_t)(len & 0xFFFF) << 48);
 }
 
 struct RingPlanLimits {

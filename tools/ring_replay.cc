@@ -49,16 +49,32 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
                 const int sIJ = (int)((job >> 16) & 0xFFFF), sJI = (int)((job >> 32) & 0xFFFF);
                 const double xi[3] = {X[i], Y[i], Z[i]};
                 const double d[3] = {X[j] - xi[0], Y[j] - xi[1], Z[j] - xi[2]};
+                const int len = (int)(job >> 48), nbSteps = rb.nbSteps;
                 double acc[OPDIM], u[3] = {0, 0, 0};
                 for (int k = 0; k < OPDIM; k++) acc[k] = 0.0;
-                bool have = false;
-                int remaining = rb.nbSteps;
-                for (int wd = 0; wd < rb.nbWords; wd++, remaining -= 8) {
-                    uint64_t word = codes[(size_t)rb.codeBase + (size_t)wd * 32 + lane];
-                    const int n = remaining < 8 ? remaining : 8;
-                    for (int q = 0; q < n; q++, word >>= 8) {
+                const uint64_t *cw = codes + rb.codeBase + lane;
+                uint64_t word = 0;
+                if (rb.flags == 0) {                                 // regular batch: no branch inside the step, padding masked
+                    if (nbSteps > 0) {
+                        word = cw[0];
                         const int id = (int)(word & 0xFF);
-                        if (id >= kRingBreak) { if (id == kRingBreak) have = false; continue; }
+                        u[0] = X[id] - xi[0]; u[1] = Y[id] - xi[1]; u[2] = Z[id] - xi[2];
+                    }
+                    for (int k = 1; k < nbSteps; k++) {
+                        if ((k & 7) == 0) word = cw[(size_t)(k >> 3) * 32]; else word >>= 8;
+                        const int id = (int)(word & 0xFF);
+                        const double w[3] = {X[id] - xi[0], Y[id] - xi[1], Z[id] - xi[2]};
+                        ring_accumulate<OPDIM> (d, u, w, acc, k < len);
+                        u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
+                    }
+                }
+                else {                                               // general batch: chains separated by breaks
+                    bool have = false;
+                    for (int k = 0; k < nbSteps; k++) {
+                        if ((k & 7) == 0) word = cw[(size_t)(k >> 3) * 32]; else word >>= 8;
+                        const int id = (int)(word & 0xFF);
+                        if (k >= len) continue;
+                        if (id == kRingBreak) { have = false; continue; }
                         const double w[3] = {X[id] - xi[0], Y[id] - xi[1], Z[id] - xi[2]};
                         if (have) ring_accumulate<OPDIM> (d, u, w, acc);
                         u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
