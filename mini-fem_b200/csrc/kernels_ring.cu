@@ -305,8 +305,10 @@ ring_assembly_kernel (const RingArgs args)
                 const int grp = lane / 10, comp = lane - 10 * grp;    // lanes 9, 19, 29, 30, 31 idle
                 double a = 0.0;
                 if (grp < 3 && comp < 9) {
-                    for (int q = grp; q < len; q += 3) {
-                        if (q != diagOff) { const double v = src[q * SLAB + comp]; a += v; out[q * 9 + comp] = v; }
+                    const double *sp = src + grp * SLAB + comp;
+                    double *op = out + grp * 9 + comp;
+                    for (int q = grp; q < len; q += 3, sp += 3 * SLAB, op += 27) {
+                        if (q != diagOff) { const double v = *sp; a += v; *op = v; }
                     }
                 }
                 const double a1 = __shfl_down_sync (0xffffffffu, a, 10), a2 = __shfl_down_sync (0xffffffffu, a, 20);
