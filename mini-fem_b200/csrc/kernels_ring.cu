@@ -20,8 +20,10 @@
 //   2. write-out: one warp per row, 3 groups of 10 lanes (9 components + one idle lane, which keeps the
 //      slab reads conflict-free) copy the row's slab run to global memory as contiguous 216-byte
 //      pieces and sum it; lanes 0..8 store the diagonal entry;
-//   3. fused mode: one lane per row of the warp masks / inverts the diagonal block into prec
-//      (prec_init + prec_inversion, src/preconditioner.cc:25-87, src/Fortran/elasclpr.f:19-53).
+//   3. fused mode: the diagonal blocks wait in shared memory until the tile is done; the last two warps
+//      of the CTA (they get the fewest job batches) then mask / invert them into prec, one lane per
+//      row, at the head of the next tile (prec_init + prec_inversion, src/preconditioner.cc:25-87,
+//      src/Fortran/elasclpr.f:19-53) — two warps with full lanes instead of every warp with four.
 // Every CSR entry is written exactly once by a plain store; the summation order is fixed by the plan.
 #include "kernels.cuh"
 #include "device_math.cuh"
@@ -141,7 +143,8 @@ ring_assembly_kernel (const RingArgs args)
     double *slab = sZ + planeStride;
     constexpr int SLAB = ring_slab_stride (OPDIM);
     double *sDiag = slab + (((size_t)P.maxEntries * SLAB + 15) & ~(size_t)15);
-    uint64_t *bars = reinterpret_cast<uint64_t*> (sDiag + (((size_t)P.maxRows * OPDIM + 1) & ~(size_t)1));
+    int *sMeta = reinterpret_cast<int*> (sDiag + (((size_t)P.maxRows * OPDIM + 1) & ~(size_t)1));   // node | interface << 31 | hasDiag << 30
+    uint64_t *bars = reinterpret_cast<uint64_t*> (sMeta + (((size_t)P.maxRows + 1) & ~(size_t)1));
     uint64_t *headFull = bars, *tailFull = bars + 2;                  // headFull[2], tailFull
 
     if (tid == 0) { ring_mbar_init (headFull, 1); ring_mbar_init (headFull + 1, 1); ring_mbar_init (tailFull, 1); }
@@ -188,6 +191,40 @@ ring_assembly_kernel (const RingArgs args)
     }
     __syncthreads ();
 
+    // Fused preconditioner of one finished tile: its diagonal blocks and row tags are in sDiag / sMeta.
+    // Run by the last two warps, one lane per row.
+    auto prec_pass = [&] (int nbRowsDone) {
+        for (int r = (warp - (nWarps - 2)) * 32 + lane; r < nbRowsDone; r += 64) {
+            const int meta = sMeta[r];
+            const int node = meta & 0x3fffffff;
+            const bool isInterface = meta < 0, hasDiag = (meta & 0x40000000) != 0;
+            if (OPDIM == 1) {
+                const double dgl = sDiag[r];
+                args.prec[node] = isInterface ? dgl : 1.0 / dgl;
+            }
+            else {
+                double b[9];
+                #pragma unroll
+                for (int q = 0; q < 9; q++) b[q] = sDiag[r * 9 + q];
+                if (!isInterface) {
+                    int mx = 0, my = 0, mz = 0;
+                    if (args.checkBounds) {
+                        mx = __ldg (args.checkBounds + node);
+                        my = __ldg (args.checkBounds + (size_t)args.nbNodes + node);
+                        mz = __ldg (args.checkBounds + 2 * (size_t)args.nbNodes + node);
+                    }
+                    mask_block (b, mx, my, mz);
+                    if (hasDiag) invert3_lu (b);
+                }
+                double *dst = args.prec + (size_t)node * 9;
+                #pragma unroll
+                for (int q = 0; q < 9; q++) dst[q] = b[q];
+            }
+        }
+    };
+    const bool precWarp = args.fusePrec && warp >= nWarps - 2;
+    int rowsDone = 0;             // rows of the previous tile whose preconditioner blocks are still to be written
+
     int k = 0;
     for (int tile = firstTile; tile < args.lastTile; tile += tileStep, k++) {
         const unsigned char *sHead = sHead0 + (k & 1) * headBytes;
@@ -204,6 +241,10 @@ ring_assembly_kernel (const RingArgs args)
         const RingBatch *batches = reinterpret_cast<const RingBatch*> (sTail);
         const uint64_t *jobs = reinterpret_cast<const uint64_t*> (sTail + (hdr.offJobs - hdr.headBytes));
         const uint64_t *codes = reinterpret_cast<const uint64_t*> (sTail + (hdr.offCodes - hdr.headBytes));
+
+        // ---- 0b. preconditioner blocks of the previous tile (its write-out ended at the block barrier) ----
+        if (precWarp) prec_pass (rowsDone);
+        rowsDone = nbRows;
 
         // ---- 1. job phase: one lane per mesh edge ----------------------------------------------
         ring_mbar_wait (tailFull, k & 1);
@@ -299,6 +340,7 @@ ring_assembly_kernel (const RingArgs args)
                 if (lane == 0) {
                     if (diagOff != 0xFFFF) out[diagOff] = diag;
                     sDiag[r] = diag;
+                    sMeta[r] = rr.node | (diagOff != 0xFFFF ? 0x40000000 : 0);
                 }
             }
             else {
@@ -316,46 +358,15 @@ ring_assembly_kernel (const RingArgs args)
                 if (lane < 9) {
                     if (diagOff != 0xFFFF) out[diagOff * 9 + lane] = diag;
                     sDiag[r * 9 + lane] = diag;
+                    if (lane == 0) sMeta[r] = rr.node | (diagOff != 0xFFFF ? 0x40000000 : 0);
                 }
             }
         }
-        // ---- 4. fused preconditioner: lane t of a warp takes the t-th row the warp wrote out ------
-        if (args.fusePrec) {
-            __syncwarp ();
-            const int r = warp + lane * nWarps;
-            if (r < nbRows) {
-                const RingRow rr = sRows[r];
-                const int node = rr.node & 0x7fffffff;
-                const bool isInterface = rr.node < 0, hasDiag = rr.diagOff != 0xFFFF;
-                if (OPDIM == 1) {
-                    const double dgl = sDiag[r];
-                    args.prec[node] = isInterface ? dgl : 1.0 / dgl;
-                }
-                else {
-                    double b[9];
-                    #pragma unroll
-                    for (int q = 0; q < 9; q++) b[q] = sDiag[r * 9 + q];
-                    if (!isInterface) {
-                        int mx = 0, my = 0, mz = 0;
-                        if (args.checkBounds) {
-                            mx = __ldg (args.checkBounds + node);
-                            my = __ldg (args.checkBounds + (size_t)args.nbNodes + node);
-                            mz = __ldg (args.checkBounds + 2 * (size_t)args.nbNodes + node);
-                        }
-                        mask_block (b, mx, my, mz);
-                        if (hasDiag) invert3_lu (b);
-                    }
-                    double *dst = args.prec + (size_t)node * 9;
-                    #pragma unroll
-                    for (int q = 0; q < 9; q++) dst[q] = b[q];
-                }
-            }
-        }
-
         offCur = offNext; offNext = offAfter;
         ring_cp_async_wait_all ();  // next tile's coordinates are in
-        __syncthreads ();           // every reader of this tile's slab / head is done
+        __syncthreads ();           // every reader of this tile's slab / head is done; sDiag / sMeta are complete
     }
+    if (precWarp) prec_pass (rowsDone);     // the CTA's last tile
 }
 
 #ifndef MFB_RING_HOST_EMULATION
@@ -376,7 +387,7 @@ size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
     const size_t doubles = 3 * planeStride + (((size_t)plan.maxEntries * ring_slab_stride (opDim) + 15) & ~(size_t)15) +
                            (((size_t)plan.maxRows * opDim + 1) & ~(size_t)1);
     return 2 * (size_t)ring_align128 (plan.maxHeadBytes) + ring_align128 (plan.maxTailBytes) + doubles * sizeof (double) +
-           3 * sizeof (uint64_t);
+           (((size_t)plan.maxRows + 1) & ~(size_t)1) * sizeof (int) + 3 * sizeof (uint64_t);
 }
 
 #ifndef MFB_RING_HOST_EMULATION

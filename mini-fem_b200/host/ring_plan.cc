@@ -669,6 +669,7 @@ int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         error = "ring plan limits out of range";
         return -1;
     }
+    if (nbNodes >= (1 << 30)) { error = "more than 2^30 nodes in one subdomain (the row tags keep two flag bits)"; return -1; }
     std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
     node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
     std::vector<int> nodeOrder, tileStart;
