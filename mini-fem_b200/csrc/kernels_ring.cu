@@ -36,8 +36,16 @@ namespace {
 static_assert (sizeof (RingTileHeader) == 32 && sizeof (RingRow) == 16 && sizeof (RingBatch) == 8,
                "plan records are copied to the device verbatim");
 
+// Byte offsets of the kernel's shared-memory sections, computed once on the host and passed as kernel
+// arguments (constant bank): the compiler otherwise rebuilds them from the plan maxima inside the loops.
+struct RingSmemLayout {
+    unsigned headBytes;          // size of one head buffer; head 0 at 0, head 1 at headBytes
+    unsigned tail, planes, slab, diag, meta, bars, total;
+};
+
 struct RingArgs {
     DeviceRingPlan plan;
+    RingSmemLayout smem;
     const double *coord;
     double *values;
     double *prec;
@@ -121,6 +129,21 @@ __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim ==
 
 // THREADS / MINB: 256 threads, three CTAs per SM (default) or 384 threads, two CTAs per SM (larger tiles:
 // mfb_options.threads = 384 with tileRows / tileElems raised, e.g. 54 / 810) — 24 warps per SM either way.
+inline RingSmemLayout ring_smem_layout (int operatorID, const DeviceRingPlan &plan)
+{
+    const int opDim = operatorID == 0 ? 1 : 9;
+    RingSmemLayout L;
+    L.headBytes = ring_align128 (plan.maxHeadBytes);
+    L.tail = 2 * L.headBytes;
+    L.planes = L.tail + ring_align128 (plan.maxTailBytes);
+    L.slab = L.planes + 3 * kRingPlane * (unsigned)sizeof (double);
+    L.diag = L.slab + ring_align128 ((unsigned)plan.maxEntries * ring_slab_stride (opDim) * (unsigned)sizeof (double));
+    L.meta = L.diag + (((unsigned)plan.maxRows * opDim * (unsigned)sizeof (double) + 15u) & ~15u);
+    L.bars = L.meta + (((unsigned)plan.maxRows * (unsigned)sizeof (int) + 15u) & ~15u);
+    L.total = L.bars + 3 * (unsigned)sizeof (uint64_t);
+    return L;
+}
+
 template <int OPDIM, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 ring_assembly_kernel (const RingArgs args)
@@ -134,17 +157,18 @@ ring_assembly_kernel (const RingArgs args)
     const int tid = threadIdx.x, nThreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nWarps = nThreads >> 5;
 
-    // shared memory: [head 0][head 1][tail][X Y Z][slab][diagonal blocks][3 mbarriers]
-    const unsigned headBytes = ring_align128 (P.maxHeadBytes), tailBytes = ring_align128 (P.maxTailBytes);
+    // shared memory: [head 0][head 1][tail][X Y Z][slab][diagonal blocks][row tags][3 mbarriers]
+    const RingSmemLayout &L = args.smem;
+    const unsigned headBytes = L.headBytes;
     constexpr int planeStride = kRingPlane;                           // planes start on a 128-byte line: bank = id mod 16;
                                                                       // a constant, so that Y and Z are immediate offsets from X
-    unsigned char *sHead0 = smemRaw, *sTail = smemRaw + 2 * headBytes;
-    double *sX = reinterpret_cast<double*> (sTail + tailBytes), *sY = sX + planeStride, *sZ = sY + planeStride;
-    double *slab = sZ + planeStride;
     constexpr int SLAB = ring_slab_stride (OPDIM);
-    double *sDiag = slab + (((size_t)P.maxEntries * SLAB + 15) & ~(size_t)15);
-    int *sMeta = reinterpret_cast<int*> (sDiag + (((size_t)P.maxRows * OPDIM + 1) & ~(size_t)1));   // node | interface << 31 | hasDiag << 30
-    uint64_t *bars = reinterpret_cast<uint64_t*> (sMeta + (((size_t)P.maxRows + 1) & ~(size_t)1));
+    unsigned char *sHead0 = smemRaw, *sTail = smemRaw + L.tail;
+    double *sX = reinterpret_cast<double*> (smemRaw + L.planes), *sY = sX + planeStride, *sZ = sY + planeStride;
+    double *slab = reinterpret_cast<double*> (smemRaw + L.slab);
+    double *sDiag = reinterpret_cast<double*> (smemRaw + L.diag);
+    int *sMeta = reinterpret_cast<int*> (smemRaw + L.meta);           // node | interface << 31 | hasDiag << 30
+    uint64_t *bars = reinterpret_cast<uint64_t*> (smemRaw + L.bars);
     uint64_t *headFull = bars, *tailFull = bars + 2;                  // headFull[2], tailFull
 
     if (tid == 0) { ring_mbar_init (headFull, 1); ring_mbar_init (headFull + 1, 1); ring_mbar_init (tailFull, 1); }
@@ -382,12 +406,7 @@ cudaError_t ring_opt_in (K kernel)
 
 size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
 {
-    const int opDim = operatorID == 0 ? 1 : 9;
-    const size_t planeStride = kRingPlane;
-    const size_t doubles = 3 * planeStride + (((size_t)plan.maxEntries * ring_slab_stride (opDim) + 15) & ~(size_t)15) +
-                           (((size_t)plan.maxRows * opDim + 1) & ~(size_t)1);
-    return 2 * (size_t)ring_align128 (plan.maxHeadBytes) + ring_align128 (plan.maxTailBytes) + doubles * sizeof (double) +
-           (((size_t)plan.maxRows + 1) & ~(size_t)1) * sizeof (int) + 3 * sizeof (uint64_t);
+    return ring_smem_layout (operatorID, plan).total;
 }
 
 #ifndef MFB_RING_HOST_EMULATION
@@ -408,7 +427,8 @@ cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTi
 {
     if (nbTiles <= 0) return cudaSuccess;
     RingArgs args;
-    args.plan = plan; args.coord = coord; args.values = values; args.prec = prec;
+    args.plan = plan; args.smem = ring_smem_layout (operatorID, plan);
+    args.coord = coord; args.values = values; args.prec = prec;
     args.checkBounds = checkBounds; args.nbNodes = nbNodes; args.fusePrec = fusePrec;
     args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
     const int grid = std::max (1, std::min (ctas, nbTiles));

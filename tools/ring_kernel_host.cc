@@ -41,6 +41,7 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
     args.plan.maxRows = std::max (hp.maxRows, 1); args.plan.maxNodes = std::max (hp.maxNodes, 4);
     args.plan.maxEntries = std::max (hp.maxEntries, 1);
     args.plan.maxHeadBytes = std::max (hp.maxHeadBytes, 16u); args.plan.maxTailBytes = std::max (hp.maxTailBytes, 16u);
+    args.smem = ring_smem_layout (operatorID, args.plan);
     args.coord = coord; args.values = values; args.prec = prec; args.checkBounds = checkBounds;
     args.nbNodes = nbNodes; args.fusePrec = fusePrec; args.firstTile = 0; args.lastTile = hp.nbTiles;
     if (hp.nbTiles == 0) return 0;
