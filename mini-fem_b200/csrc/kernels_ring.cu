@@ -17,9 +17,10 @@
 //   1. job phase: one lane per edge, 32 jobs per warp batch, ring codes 8 to a 64-bit word;
 //      finished 3x3 blocks go to the tile-wide slab at the slots of their CSR entries (entry stride
 //      80 bytes, so a block leaves as four 128-bit stores and one 64-bit store);
-//   2. write-out: one warp per row, 3 groups of 10 lanes (9 components + one idle lane, which keeps the
-//      slab reads conflict-free) copy the row's slab run to global memory as contiguous 216-byte
-//      pieces and sum it; lanes 0..8 store the diagonal entry;
+//   2. write-out: three consecutive rows per warp, ten lanes each (9 components + one idle lane): a lane
+//      walks its row entry by entry, copies its component to global memory (72 contiguous bytes per
+//      group and instruction) and sums it, then stores its component of the diagonal entry; row starts
+//      in the slab are padded so that the three pieces read together fall into disjoint banks;
 //   3. fused mode: the diagonal blocks wait in shared memory until the tile is done; the last two warps
 //      of the CTA (they get the fewest job batches) then mask / invert them into prec, one lane per
 //      row, at the head of the next tile (prec_init + prec_inversion, src/preconditioner.cc:25-87,
@@ -347,13 +348,14 @@ ring_assembly_kernel (const RingArgs args)
             gather_coords (nextHead);
         }
 
-        // ---- 3. write-out: one warp per row, the diagonal entry is minus the sum of the run -------
-        for (int r = warp; r < nbRows; r += nWarps) {
-            const RingRow rr = sRows[r];
-            const int len = rr.len, diagOff = rr.diagOff;             // 0xFFFF never equals a position
-            double *out = args.values + (size_t)rr.valueStart * OPDIM;
-            const double *src = slab + (size_t)rr.localStart * SLAB;
-            if (OPDIM == 1) {
+        // ---- 3. write-out: the diagonal entry of a row is minus the sum of the row's run ------------
+        if (OPDIM == 1) {
+            // Laplacian: one warp per row, entries side by side
+            for (int r = warp; r < nbRows; r += nWarps) {
+                const RingRow rr = sRows[r];
+                const int len = rr.len, diagOff = rr.diagOff;         // 0xFFFF never equals a position
+                double *out = args.values + (size_t)rr.valueStart;
+                const double *src = slab + (size_t)rr.localStart;
                 double a = 0.0;
                 for (int q = lane; q < len; q += 32) {
                     if (q != diagOff) { const double v = src[q]; a += v; out[q] = v; }
@@ -367,25 +369,32 @@ ring_assembly_kernel (const RingArgs args)
                     sMeta[r] = rr.node | (diagOff != 0xFFFF ? 0x40000000 : 0);
                 }
             }
-            else {
-                const int grp = lane / 10, comp = lane - 10 * grp;    // lanes 9, 19, 29, 30, 31 idle
-                double a = 0.0;
-                if (grp < 3 && comp < 9) {
-                    const double *sp = src + grp * SLAB + comp;
-                    double *op = out + grp * 9 + comp;
-                    for (int q = grp; q < len; q += 3, sp += 3 * SLAB, op += 27) {
+        }
+        else {
+            // Elasticity: three consecutive rows per warp side by side, ten lanes each (nine components and an
+            // idle lane); a lane walks the entries of its row, so the row sum needs no exchange between lanes.
+            // The slab starts of consecutive rows are 1 (mod 8) slots apart (ring_row_padding): the three
+            // 72-byte pieces read in one instruction fall into disjoint banks.
+            const int grp = lane / 10, comp = lane - 10 * grp;        // lanes 9, 19, 29, 30, 31 idle
+            for (int r0 = warp * 3; r0 < nbRows; r0 += nWarps * 3) {
+                const int r = r0 + grp;
+                if (grp < 3 && comp < 9 && r < nbRows) {
+                    const RingRow rr = sRows[r];
+                    const int len = rr.len, diagOff = rr.diagOff;     // 0xFFFF never equals a position
+                    const double *sp = slab + (size_t)rr.localStart * SLAB + comp;
+                    double *out = args.values + (size_t)rr.valueStart * 9 + comp, *op = out;
+                    double a = 0.0;
+                    for (int q = 0; q < len; q++, sp += SLAB, op += 9) {
                         if (q != diagOff) { const double v = *sp; a += v; *op = v; }
                     }
-                }
-                const double a1 = __shfl_down_sync (0xffffffffu, a, 10), a2 = __shfl_down_sync (0xffffffffu, a, 20);
-                const double diag = 0.0 - ((a + a1) + a2);
-                if (lane < 9) {
-                    if (diagOff != 0xFFFF) out[diagOff * 9 + lane] = diag;
-                    sDiag[r * 9 + lane] = diag;
-                    if (lane == 0) sMeta[r] = rr.node | (diagOff != 0xFFFF ? 0x40000000 : 0);
+                    const double diag = 0.0 - a;
+                    if (diagOff != 0xFFFF) out[diagOff * 9] = diag;
+                    sDiag[r * 9 + comp] = diag;
+                    if (comp == 0) sMeta[r] = rr.node | (diagOff != 0xFFFF ? 0x40000000 : 0);
                 }
             }
         }
+
         offCur = offNext; offNext = offAfter;
         ring_cp_async_wait_all ();  // next tile's coordinates are in
         __syncthreads ();           // every reader of this tile's slab / head is done; sDiag / sMeta are complete

@@ -192,7 +192,7 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
         rr.diagOff = 0xFFFF;
         for (int l = begin; l < end; l++) if (col[l] == n + 1) { rr.diagOff = (uint16_t)(l - begin); break; }
         w.rows.push_back (rr);
-        localStart += end - begin;
+        localStart += (end - begin) + ring_row_padding (end - begin);
     }
     out.nbRows = nbRows;
     out.nbEntries = localStart;
@@ -664,7 +664,7 @@ int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
                      RingPlan &plan, std::string &error)
 {
     plan = RingPlan ();
-    if (lim.maxRows < 1 || lim.maxRows > 255 || lim.maxEntries < 1 || lim.maxEntries > 65534 ||
+    if (lim.maxRows < 1 || lim.maxRows > 255 || lim.maxEntries < 1 || lim.maxEntries > 60000 ||
         lim.maxNodes < 4 || lim.maxNodes > kRingMaxNodes) {
         error = "ring plan limits out of range";
         return -1;
@@ -768,7 +768,8 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
             rowsTotal++;
             if (rr.valueStart != row[n] || rr.len != row[n + 1] - row[n] || rr.localStart != expectStart) { error = "row table differs from nodeToNodeRow"; return -1; }
             for (int l = 0; l < rr.len; l++) slotEntry[(size_t)expectStart + l] = rr.valueStart + l;
-            expectStart += rr.len;
+            expectStart += rr.len + ring_row_padding (rr.len);
+            if (expectStart > h.nbEntries) { error = "rows exceed the slab"; return -1; }
             int diag = 0xFFFF;
             for (int l = 0; l < rr.len; l++) if (col[rr.valueStart + l] == n + 1) { diag = l; break; }
             if (diag != rr.diagOff) { error = "diagOff is not the first diagonal entry"; return -1; }
@@ -802,6 +803,7 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
                 if (li >= h.nbNodes || lj >= h.nbNodes || sIJ >= h.nbEntries || (sJI != 0xFFFF && sJI >= h.nbEntries)) { error = "job out of range"; return -1; }
                 const int gi = tileNodes[li], gj = tileNodes[lj];
                 const int eIJ = slotEntry[sIJ];
+                if (eIJ < 0) { error = "job writes a padding slot"; return -1; }
                 if (entrySeen[eIJ]) { error = "CSR entry written twice"; return -1; }
                 entrySeen[eIJ] = 1;
                 const bool empty = len == 0;
@@ -814,6 +816,7 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
                 }
                 if (sJI != 0xFFFF) {
                     const int eJI = slotEntry[sJI];
+                    if (eJI < 0) { error = "job writes a padding slot (transposed block)"; return -1; }
                     if (entrySeen[eJI]) { error = "CSR entry written twice (transposed block)"; return -1; }
                     entrySeen[eJI] = 1;
                     int r = 0;

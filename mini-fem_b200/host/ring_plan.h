@@ -41,7 +41,7 @@ constexpr int kRingBatchGeneral = 1; // RingBatch::flags: some job of the batch 
 constexpr int kRingMaxNodes = 254; // tile-local node ids 0 .. 253
 
 struct RingTileHeader {            // 32 bytes
-    uint16_t nbRows, nbNodes, nbBatches, nbEntries, hasInterface, pad0;
+    uint16_t nbRows, nbNodes, nbBatches, nbEntries, hasInterface, pad0;   // nbEntries = slab slots, padding included
     uint32_t offNodes;             // int[nbNodes]: 0-based global ids by tile-local id (holes name a valid node)
     uint32_t headBytes;            // bytes [0, headBytes) = header + rows + nodes; the tail starts here with RingBatch[nbBatches]
     uint32_t offJobs;              // uint64[32 * nbBatches]
@@ -53,11 +53,17 @@ struct RingTileHeader {            // 32 bytes
 struct RingRow {                   // 16 bytes per owned row, right after the header
     int node;                      // 0-based global node id; bit 31 set = interface node
     int valueStart;                // nodeToNodeRow[node]
-    uint16_t localStart;           // slab slot of the row's first entry
+    uint16_t localStart;           // slab slot of the row's first entry; consecutive rows start 1 (mod 8) slots apart
+                                   // (ring_row_padding), so that three rows can stream out side by side
     uint16_t len;                  // entries of the row
     uint16_t diagOff;              // position of the diagonal entry inside the row, 0xFFFF = none
     uint16_t pad0;
 };
+
+// Idle slab slots after a row of `len` entries: the next row starts at a slot = 1 (mod 8) past this row's
+// start.  The write-out lets three groups of ten lanes copy three consecutive rows at once, entry q of each
+// in the same instruction; with 80-byte slab entries the three 72-byte pieces then fall into disjoint banks.
+inline int ring_row_padding (int len) { return ((1 - len) % 8 + 8) % 8; }
 
 struct RingBatch {                 // 8 bytes per warp batch of 32 jobs
     uint32_t codeBase;             // first code word of the batch (index into the codes section)
@@ -76,7 +82,7 @@ inline uint64_t ring_job (int i, int j, int slotIJ, int slotJI, int len)
 
 struct RingPlanLimits {
     int maxRows = 36;              // rows per tile (<= 255)
-    int maxEntries = 576;          // CSR entries per tile: the slab holds maxEntries * operatorDim doubles
+    int maxEntries = 576;          // CSR entries per tile (the slab also holds up to 7 idle slots per row)
     int maxNodes = kRingMaxNodes;  // tile-local nodes (<= 254: one code byte per node)
     bool bankAware = true;         // node numbering + ring rotation chosen against bank conflicts
     int rotationSweeps = 1;        // coordinate-descent sweeps over the lanes of a half-warp after the greedy rotation choice

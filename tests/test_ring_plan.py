@@ -81,7 +81,7 @@ def test_ring_replay_matches_oracle(ringlib, oracle, op, grid, rows, entries):
     assert stats[1] + stats[2] == nb_offdiag
     assert stats[5] == 0                                   # a conforming mesh: one chain per edge
     if rows:
-        assert stats[11] <= rows and stats[13] <= entries
+        assert stats[11] <= rows and stats[13] <= entries + 7 * rows      # slab slots: up to 7 idle ones per row
 
 
 @pytest.mark.parametrize("op", ["ela", "lap"])
@@ -197,7 +197,7 @@ def test_ring_plan_property(ringlib, oracle):
             msg = ringlib.mfb_ring_replay_error()
             assert rc == -1 and (b"exceeds the tile caps" in msg or b"more than 254 nodes" in msg), msg
             return
-        assert stats[11] <= rows and stats[13] <= entries and stats[12] <= 254
+        assert stats[11] <= rows and stats[13] <= entries + 7 * rows and stats[12] <= 254
         want_v, _, want_p = oracle.fem_iteration(setup)
         # random tetrahedra can be arbitrarily flat: compare where the reference's own numbers are finite
         if np.all(np.isfinite(want_v)) and np.all(np.isfinite(want_p)) and np.abs(want_v).max() < 1e12:

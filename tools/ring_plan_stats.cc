@@ -44,9 +44,9 @@ int main (int argc, char **argv)
     const double misc = (plan.nbPaddedSteps / 32.0 / 7.0 * 4.0 + plan.nbTiles * 3.0 * plan.maxNodes * 8.0 / 128.0) / E;
     printf ("%s: E %d N %d Z %.0f | rows<=%d entries<=%d | build %.2f s | tiles %d | plan %.1f MB (%.1f B/elem)\n", what, m.nbElem, m.nbNodes, Z,
             lim.maxRows, lim.maxEntries, seconds, plan.nbTiles, plan.blob.size () / 1e6, plan.blob.size () / E);
-    printf ("  jobs/E %.3f (transposed too: %.3f)  ring steps/E %.3f  padded lane-steps/E %.3f  breaks %lld  maxNodes %d  head %u B tail %u B\n",
+    printf ("  jobs/E %.3f (transposed too: %.3f)  ring steps/E %.3f  padded lane-steps/E %.3f  breaks %lld  maxNodes %d  slab slots %d  head %u B tail %u B\n",
             plan.nbJobs / E, plan.nbSymmetricJobs / E, plan.nbRingSteps / E, plan.nbPaddedSteps / E, (long long)plan.nbBreaks,
-            plan.maxNodes, plan.maxHeadBytes, plan.maxTailBytes);
+            plan.maxNodes, plan.maxEntries, plan.maxHeadBytes, plan.maxTailBytes);
     printf ("  modelled shared-memory wavefronts per element: gather %.2f (x%.2f of conflict-free) + slab stores %.2f (x%.2f) + slab reads %.2f + codes/coords %.2f = %.2f  -> %.1f M per iteration\n",
             gather, (double)plan.gatherWavefronts / plan.gatherIdeal, slabW, (double)plan.slabWriteWavefronts / plan.slabWriteIdeal, slabR, misc,
             gather + slabW + slabR + misc, (gather + slabW + slabR + misc) * E / 1e6);

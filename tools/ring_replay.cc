@@ -119,22 +119,15 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
                 sDiag[r] = diag;
             }
             else {
-                double a[3][9];
-                for (int grp = 0; grp < 3; grp++) {
-                    for (int comp = 0; comp < 9; comp++) {
-                        double s = 0.0;
-                        for (int k = grp; k < len; k += 3) {
-                            if (k == diagOff) continue;
-                            const double v = src[(size_t)k * SLAB + comp];
-                            s += v;
-                            out[(size_t)k * 9 + comp] = v;
-                        }
-                        a[grp][comp] = s;
+                for (int comp = 0; comp < 9; comp++) {              // one lane per component walks the row
+                    double a = 0.0;
+                    for (int k = 0; k < len; k++) {
+                        if (k == diagOff) continue;
+                        const double v = src[(size_t)k * SLAB + comp];
+                        a += v;
+                        out[(size_t)k * 9 + comp] = v;
                     }
-                }
-                for (int comp = 0; comp < 9; comp++) {
-                    const double total = (a[0][comp] + a[1][comp]) + a[2][comp];
-                    const double diag = 0.0 - total;
+                    const double diag = 0.0 - a;
                     if (diagOff != 0xFFFF) out[(size_t)diagOff * 9 + comp] = diag;
                     sDiag[(size_t)r * 9 + comp] = diag;
                 }
