@@ -313,3 +313,37 @@ def test_ring_mesh_without_elements(ringlib, kernel_host, oracle, op):
     for values, prec in (replay(ringlib, setup)[:2], run_kernel_on_host(kernel_host, setup, ctas=2)):
         assert values.size == 0
         assert np.array_equal(prec, want_p, equal_nan=True)
+
+
+def test_ring_kernel_source_randomized_against_replay(ringlib, kernel_host):
+    """Random meshes (Kuhn, random tetrahedra with chain breaks, partitioned blocks with interface rows),
+    tile caps, grid sizes and both CTA shapes: the kernel's source on host threads equals the sequential
+    replay bit for bit (60 such trials were run once; the suite keeps 16)."""
+    rng = np.random.default_rng(2024)
+    for _ in range(16):
+        kind = int(rng.integers(0, 3))
+        op = "ela" if rng.integers(0, 2) else "lap"
+        if kind == 0:
+            mesh = mfb.Mesh.generate(*(int(x) for x in rng.integers(1, 8, size=3)), seed=int(rng.integers(1, 99)))
+        elif kind == 1:
+            n = int(rng.integers(5, 60))
+            coord, e2n = random_tet_mesh(rng, n, max(int(n * rng.uniform(0.5, 5)), 1))
+            mesh = ArrayMesh(coord, e2n, n)
+        else:
+            mesh = mfb.Mesh.generate(*(int(x) for x in rng.integers(2, 6, size=3)), blocks=(2, 1, 1),
+                                     rank=int(rng.integers(0, 2)), seed=3)
+        setup = mfb.Setup(mesh, op)
+        rows = int(rng.choice([0, 0, 3, 9, 20, 54]))
+        entries = 0 if rows == 0 else int(rows * rng.integers(20, 40))
+        interface = None
+        if kind == 2 and mesh.nbIntfNodes > 0:
+            interface = np.zeros(mesh.nbNodes, np.uint8)
+            interface[mesh.intfNodes - 1] = 1
+        try:
+            v_replay, p_replay, _ = replay(ringlib, setup, rows, entries, 1, interface)
+        except AssertionError as refused:                   # a row that cannot fit the caps: reported, not hidden
+            assert "exceeds the tile caps" in str(refused) or "254 nodes" in str(refused)
+            continue
+        v_kernel, p_kernel = run_kernel_on_host(kernel_host, setup, rows, entries, int(rng.integers(1, 5)), 1, interface,
+                                                int(rng.choice([256, 256, 384])))
+        assert np.array_equal(v_replay, v_kernel, equal_nan=True) and np.array_equal(p_replay, p_kernel, equal_nan=True)
