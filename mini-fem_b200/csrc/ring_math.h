@@ -19,11 +19,12 @@
 
 namespace mfb {
 
-// 1 / x for a normal, finite, non-zero x.  Device: MUFU.RCP64H seed (rcp.approx.ftz.f64, about
-// 20 good bits, low mantissa word zero) and two Newton steps, 4 DFMA instead of the ~10 FP64
-// instructions plus slow-path branch of an IEEE division; the result is within an ulp or two,
-// far inside the 1e-12 the values are held to.  The host replay starts from the same kind of
-// 20-bit seed so that the tests exercise the same iteration.
+// 1 / x for a normal, finite, non-zero x.  Device: MUFU.RCP64H seed (rcp.approx.ftz.f64: it looks at the high
+// word of x only, about 20 good bits) refined by one cubic step r (1 + e + e^2) and one Newton step — the
+// sequence nvcc itself emits for 1.0 / x, minus its range checks and slow path (5 DFMA instead of ~10 FP64
+// instructions and a branch).  The error is the sixth power of the seed's: below an ulp even for a 10-bit
+// seed, far inside the 1e-12 the values are held to.  The host replay starts from a seed cut to 20 bits so
+// that the tests exercise the same iteration.
 MFB_RM double ring_rcp (double x)
 {
 #if MFB_RING_FAST_RCP
@@ -38,6 +39,7 @@ MFB_RM double ring_rcp (double x)
     memcpy (&r, &bits, 8);
 #endif
     double e = fma (-x, r, 1.0);
+    e = fma (e, e, e);
     r = fma (r, e, r);
     e = fma (-x, r, 1.0);
     r = fma (r, e, r);
