@@ -21,12 +21,15 @@ for op in ("ela", "lap"):
     ctx.iteration(); ctx.iteration(); ctx.download(); ctx.close()
 print("RING_SANITIZE_DONE")
 PY
-for tool in memcheck racecheck synccheck; do
+for tool in memcheck racecheck synccheck initcheck; do
     timeout 600 compute-sanitizer --tool $tool python gpurun_out/ring_sanitize_case.py > gpurun_out/ring_sanitize_$tool.log 2>&1
     echo "$tool rc=$? $(grep -c 'ERROR SUMMARY\|RACECHECK SUMMARY' gpurun_out/ring_sanitize_$tool.log)"; tail -2 gpurun_out/ring_sanitize_$tool.log
 done
 timeout 600 python tools/quick_bench.py --paths tiled,ring --steps 20 > gpurun_out/ring_quick_bench.log 2>&1
 tail -4 gpurun_out/ring_quick_bench.log
+# the tile cut as TILED cuts it (runs of the Morton curve) instead of the bisection
+MFB_RING_CUT=morton timeout 300 python tools/quick_bench.py --paths ring --steps 20 > gpurun_out/ring_quick_bench_morton.log 2>&1
+tail -1 gpurun_out/ring_quick_bench_morton.log
 for caps in "48 720" "64 960" "24 360"; do
     set -- $caps
     timeout 300 python tools/quick_bench.py --paths ring --steps 20 --tile-rows $1 --tile-elems $2 > gpurun_out/ring_quick_bench_$1.log 2>&1
