@@ -8,7 +8,7 @@ import minifem_b200 as mfb
 ap = argparse.ArgumentParser()
 ap.add_argument("--grid", type=int, nargs=3, default=[100, 100, 100])
 ap.add_argument("--op", default="ela")
-ap.add_argument("--paths", default="tiled,atomic,color")
+ap.add_argument("--paths", default="tiled,atomic,color", help="comma-separated: tiled, ring, atomic, color")
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--tile-rows", type=int, default=0)
 ap.add_argument("--tile-elems", type=int, default=0)
@@ -49,7 +49,7 @@ for path in a.paths.split(","):
         ms.append(ctx.stage_ms()[4])
     ms = np.array(ms)
     line = f"{path:7s} setup {t1-t0:.1f}s ctx {t2-t1:.1f}s  iter ms: med {np.median(ms):.4f} min {ms.min():.4f}  -> {E/np.median(ms)/1e6:.2f} Gelem/s, alg {alg/np.median(ms)/1e6:.1f} GB/s"
-    if path == "tiled":
+    if path in ("tiled", "ring"):
         line += f"  plan {ctx.plan_stats()} bytes {ctx.device_bytes()}"
     print(line, flush=True)
     v, p = ctx.download()
