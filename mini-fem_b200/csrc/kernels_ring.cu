@@ -295,12 +295,23 @@ ring_assembly_kernel (const RingArgs args)
                     const int id = (int)(word & 0xFF);
                     u[0] = sX[id] - xi[0]; u[1] = sY[id] - xi[1]; u[2] = sZ[id] - xi[2];
                 }
-                for (int k = 1; k < nbSteps; k++) {
+                // two steps per trip, u and w changing roles: no register copies between steps
+                double w[3];
+                auto load_node = [&] (int k, double v[3]) {
                     if ((k & 7) == 0) word = cw[(k >> 3) * 32]; else word >>= 8;
                     const int id = (int)(word & 0xFF);
-                    const double w[3] = {sX[id] - xi[0], sY[id] - xi[1], sZ[id] - xi[2]};
+                    v[0] = sX[id] - xi[0]; v[1] = sY[id] - xi[1]; v[2] = sZ[id] - xi[2];
+                };
+                int k = 1;
+                for (; k + 1 < nbSteps; k += 2) {
+                    load_node (k, w);
                     ring_accumulate<OPDIM> (d, u, w, acc, k < len);
-                    u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
+                    load_node (k + 1, u);
+                    ring_accumulate<OPDIM> (d, w, u, acc, k + 1 < len);
+                }
+                if (k < nbSteps) {
+                    load_node (k, w);
+                    ring_accumulate<OPDIM> (d, u, w, acc, k < len);
                 }
             }
             else {
