@@ -137,7 +137,7 @@ typedef struct {
     int path;                       /* MFB_PATH_* */
     int device;                     /* CUDA device ordinal */
     int tileRows;                   /* TILED: max rows per tile (0 = default) */
-    int tileElems;                  /* TILED: max elements per tile; RING: max CSR entries per tile (0 = default) */
+    int tileElems;                  /* TILED: max elements per tile; RING: max slab slots per tile = CSR entries + row padding (0 = default) */
     int threads;                    /* TILED: threads per CTA (0 = default) */
     int useGraph;                   /* capture mfb_ctx_iteration in a CUDA graph */
     int ctas;                       /* TILED: CTAs walking the tiles (0 = default, -1 = one per tile) */

@@ -634,10 +634,11 @@ int cut_node_tiles_rcb (int nbNodes, const int *elemToNode, const int *row, cons
                     }
                 }
                 addRefs += (int)fresh.size ();
-                if (rows + 1 <= lim.maxRows && refs + addRefs <= lim.maxNodes && entries + rowLen <= lim.maxEntries) {
+                const int slots = rowLen + ring_row_padding (rowLen);      // the slab keeps the padding too
+                if (rows + 1 <= lim.maxRows && refs + addRefs <= lim.maxNodes && entries + slots <= lim.maxEntries) {
                     nodeStamp[n] = tile;
                     for (int m : fresh) nodeStamp[m] = tile;
-                    rows++; refs += addRefs; entries += rowLen;
+                    rows++; refs += addRefs; entries += slots;
                     break;
                 }
                 if (rows == 0 || attempt == 1) {

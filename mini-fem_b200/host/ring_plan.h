@@ -82,7 +82,8 @@ inline uint64_t ring_job (int i, int j, int slotIJ, int slotJI, int len)
 
 struct RingPlanLimits {
     int maxRows = 36;              // rows per tile (<= 255)
-    int maxEntries = 576;          // CSR entries per tile (the slab also holds up to 7 idle slots per row)
+    int maxEntries = 640;          // slab slots per tile: CSR entries plus the padding between rows (with the Morton
+                                   // cut the cap applies to the entries alone); 640 x 80 bytes keeps three CTAs per SM
     int maxNodes = kRingMaxNodes;  // tile-local nodes (<= 254: one code byte per node)
     bool bankAware = true;         // node numbering + ring rotation chosen against bank conflicts
     int rotationSweeps = 1;        // coordinate-descent sweeps over the lanes of a half-warp after the greedy rotation choice

@@ -30,13 +30,13 @@ tail -4 gpurun_out/ring_quick_bench.log
 # the tile cut as TILED cuts it (runs of the Morton curve) instead of the bisection
 MFB_RING_CUT=morton timeout 300 python tools/quick_bench.py --paths ring --steps 20 > gpurun_out/ring_quick_bench_morton.log 2>&1
 tail -1 gpurun_out/ring_quick_bench_morton.log
-for caps in "48 720" "64 960" "24 360"; do
+for caps in "48 820" "64 1100" "24 410"; do
     set -- $caps
     timeout 300 python tools/quick_bench.py --paths ring --steps 20 --tile-rows $1 --tile-elems $2 > gpurun_out/ring_quick_bench_$1.log 2>&1
     tail -1 gpurun_out/ring_quick_bench_$1.log
 done
 # two CTAs of 384 threads per SM with larger tiles (fewer edges cut by tile borders)
-timeout 300 python tools/quick_bench.py --paths ring --steps 20 --threads 384 --tile-rows 54 --tile-elems 810 > gpurun_out/ring_quick_bench_384.log 2>&1
+timeout 300 python tools/quick_bench.py --paths ring --steps 20 --threads 384 --tile-rows 54 --tile-elems 960 > gpurun_out/ring_quick_bench_384.log 2>&1
 tail -1 gpurun_out/ring_quick_bench_384.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/ring_launches.csv \
     python bench.py --path ring --steps 3 --warmup 3 --no-cpu-baseline --no-other-paths > gpurun_out/ring_bench_under_ncu.log 2>&1
