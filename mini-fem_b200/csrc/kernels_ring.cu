@@ -129,7 +129,7 @@ constexpr int kRingPlane = 256;
 __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim == 9 ? 10 : 1; }
 
 // THREADS / MINB: 256 threads, three CTAs per SM (default) or 384 threads, two CTAs per SM (larger tiles:
-// mfb_options.threads = 384 with tileRows / tileElems raised, e.g. 54 / 810) — 24 warps per SM either way.
+// mfb_options.threads = 384 with tileRows / tileElems raised, e.g. 54 / 960) — 24 warps per SM either way.
 inline RingSmemLayout ring_smem_layout (int operatorID, const DeviceRingPlan &plan)
 {
     const int opDim = operatorID == 0 ? 1 : 9;

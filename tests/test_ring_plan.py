@@ -261,7 +261,7 @@ def test_ring_kernel_source_384_threads(kernel_host, oracle, op):
     """The two-CTAs-per-SM instantiation (12 warps, larger tiles)."""
     mesh = mfb.Mesh.generate(9, 8, 8, seed=9)
     setup = mfb.Setup(mesh, op)
-    values, prec = run_kernel_on_host(kernel_host, setup, rows=54, entries=810, ctas=2, threads=384)
+    values, prec = run_kernel_on_host(kernel_host, setup, rows=54, entries=960, ctas=2, threads=384)
     check_against_oracle(oracle, setup, values, prec)
 
 
