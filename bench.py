@@ -288,7 +288,7 @@ def choose_path(args, rank, local):
         cmd = [sys.executable, os.path.abspath(__file__), "--probe-ring", "--device", str(local), "--op", args.op,
                "--grid"] + [str(g) for g in args.grid]
         try:
-            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=420)
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
             lines = [l for l in res.stdout.splitlines() if l.startswith("PROBE ")]
             verdict["probe"] = json.loads(lines[-1][6:]) if lines else {"ok": False, "error": "no verdict; rc=%d: %s" % (res.returncode, res.stdout[-300:])}
         except Exception as e:                               # noqa: BLE001

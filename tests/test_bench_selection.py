@@ -35,7 +35,7 @@ def test_choose_path(monkeypatch):
     monkeypatch.setattr(subprocess, "run", _fake_run("Segmentation fault", returncode=-11))
     verdict = bench.choose_path(_args(), 0, 0)
     assert verdict["chosen"] == "tiled" and "no verdict" in verdict["probe"]["error"]
-    monkeypatch.setattr(subprocess, "run", _fake_run("", raises=subprocess.TimeoutExpired("bench.py", 420)))
+    monkeypatch.setattr(subprocess, "run", _fake_run("", raises=subprocess.TimeoutExpired("bench.py", 300)))
     assert bench.choose_path(_args(), 0, 0)["chosen"] == "tiled"
     # ranks other than 0 do not probe; without a process group they keep TILED
     monkeypatch.setattr(subprocess, "run", _fake_run("", raises=AssertionError("rank 1 must not probe")))
