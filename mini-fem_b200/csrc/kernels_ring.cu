@@ -361,24 +361,23 @@ ring_assembly_kernel (const RingArgs args)
 
         // ---- 3. write-out: the diagonal entry of a row is minus the sum of the row's run ------------
         if (OPDIM == 1) {
-            // Laplacian: one warp per row, entries side by side
-            for (int r = warp; r < nbRows; r += nWarps) {
+            // Laplacian: one lane per row walks its entries (rows are short and the whole matrix is an eighth of
+            // the elasticity one: 8-byte stores to 32 different rows per instruction are affordable; the four
+            // entries of a sector come from the same lane in consecutive trips).  Row starts 1 (mod 8) slots
+            // apart keep the slab reads of a half-warp in different banks.
+            for (int r = warp * 32 + lane; r < nbRows; r += nWarps * 32) {
                 const RingRow rr = sRows[r];
                 const int len = rr.len, diagOff = rr.diagOff;         // 0xFFFF never equals a position
                 double *out = args.values + (size_t)rr.valueStart;
                 const double *src = slab + (size_t)rr.localStart;
                 double a = 0.0;
-                for (int q = lane; q < len; q += 32) {
+                for (int q = 0; q < len; q++) {
                     if (q != diagOff) { const double v = src[q]; a += v; out[q] = v; }
                 }
-                #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync (0xffffffffu, a, off);
                 const double diag = 0.0 - a;
-                if (lane == 0) {
-                    if (diagOff != 0xFFFF) out[diagOff] = diag;
-                    sDiag[r] = diag;
-                    sMeta[r] = rr.node | (diagOff != 0xFFFF ? 0x40000000 : 0);
-                }
+                if (diagOff != 0xFFFF) out[diagOff] = diag;
+                sDiag[r] = diag;
+                sMeta[r] = rr.node | (diagOff != 0xFFFF ? 0x40000000 : 0);
             }
         }
         else {

@@ -102,19 +102,10 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
             const int len = rr.len, diagOff = rr.diagOff;
             double *out = values + (size_t)rr.valueStart * OPDIM;
             const double *src = slab.data () + (size_t)rr.localStart * SLAB;
-            if (OPDIM == 1) {
-                double lanes[32];
-                for (int lane = 0; lane < 32; lane++) {
-                    double a = 0.0;
-                    for (int k = lane; k < len; k += 32) if (k != diagOff) { a += src[k]; out[k] = src[k]; }
-                    lanes[lane] = a;
-                }
-                for (int off = 16; off >= 1; off >>= 1) {         // shfl_xor butterfly
-                    double next[32];
-                    for (int lane = 0; lane < 32; lane++) next[lane] = lanes[lane] + lanes[lane ^ off];
-                    memcpy (lanes, next, sizeof lanes);
-                }
-                const double diag = 0.0 - lanes[0];
+            if (OPDIM == 1) {                                       // one lane walks the row
+                double a = 0.0;
+                for (int k = 0; k < len; k++) if (k != diagOff) { a += src[k]; out[k] = src[k]; }
+                const double diag = 0.0 - a;
                 if (diagOff != 0xFFFF) out[diagOff] = diag;
                 sDiag[r] = diag;
             }
