@@ -49,3 +49,37 @@ def test_probe_without_gpu_reports_instead_of_raising(capsys):
     import minifem_b200 as mfb
     if mfb.device_count() == 0:
         assert verdict["ok"] is False and "no CUDA device" in verdict["error"]
+
+
+SELECTION_WORKER = r'''
+import argparse, json, os, subprocess, sys, types
+ROOT = %r
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "mini-fem_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench
+from minifem_b200 import dist as mdist
+rank, world = mdist.init_from_env("gloo")
+def run(cmd, **kw):
+    assert rank == 0, "only rank 0 may probe"
+    verdict = {"ok": True, "ring_ms": 0.3, "tiled_ms": 0.6}
+    return types.SimpleNamespace(stdout="PROBE " + json.dumps(verdict), returncode=0)
+subprocess.run = run
+verdict = bench.choose_path(argparse.Namespace(op="ela", grid=[100, 100, 100]), rank, rank)
+assert verdict["chosen"] == "ring", verdict                      # every rank measures the path rank 0 chose
+assert (verdict["probe"] is not None) == (rank == 0)
+mdist.barrier()
+print("SELECTION_WORKER_OK", rank, flush=True)
+'''
+
+
+def test_choice_of_rank_0_reaches_every_rank(tmp_path):
+    """World size 2 over gloo: rank 0 probes, both ranks end up on the same path."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "selection_worker.py"
+    script.write_text(SELECTION_WORKER % root)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29549", str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
+    assert res.returncode == 0 and res.stdout.count("SELECTION_WORKER_OK") == 2, res.stdout[-3000:]
