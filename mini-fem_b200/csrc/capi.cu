@@ -360,19 +360,28 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
         isIntf.assign ((size_t)p->nbNodes, 0);
         for (int j = 0; j < p->nbIntfNodes; j++) isIntf[p->intfNodes[j] - 1] = 1;
     }
+    // Tiles sized for the CTA: one warp batch of 32 jobs and one group of three rows per warp and tile, so that
+    // neither phase leaves warps idle at the block barrier.  384 threads (12 warps, two CTAs per SM): 34 rows,
+    // <= 384 jobs; 256 threads (8 warps, three CTAs per SM): 22 rows, <= 256 jobs.
     RingPlanLimits lim;
+    const bool wide = c->threads == 384;
+    lim.maxRows = wide ? 34 : 22;
+    lim.maxEntries = wide ? 544 : 352;
+    lim.maxJobs = wide ? 384 : 256;
     if (o && o->tileRows > 0) lim.maxRows = o->tileRows;
-    if (o && o->tileElems > 0) lim.maxEntries = o->tileElems;          // RING: tileElems caps the CSR entries of a tile
+    if (o && o->tileElems > 0) lim.maxEntries = o->tileElems;          // RING: tileElems caps the slab slots of a tile
+    if (o && (o->tileRows > 0 || o->tileElems > 0)) lim.maxJobs = 1 << 30;
     lim.bankAware = !(o && o->bankAware < 0);
     // experiment knobs: MFB_RING_CUT=morton (tiles = runs of the Morton curve, like TILED),
     // MFB_RING_REFINE=n (renumber-and-rotate rounds of the bank-aware numbering), MFB_RING_SWEEPS=n
     if (const char *v = getenv ("MFB_RING_CUT")) lim.bisection = std::string (v) != "morton";
     if (const char *v = getenv ("MFB_RING_REFINE")) lim.refinePasses = std::max (atoi (v), 0);
     if (const char *v = getenv ("MFB_RING_SWEEPS")) lim.rotationSweeps = std::max (atoi (v), 0);
+    if (const char *v = getenv ("MFB_RING_MAXJOBS")) lim.maxJobs = std::max (atoi (v), 32);
     RingPlan hp;
     std::string err;
     if (build_ring_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, p->coord,
-                         isIntf.empty () ? nullptr : isIntf.data (), lim, hp, err) != 0) {
+                         isIntf.empty () ? nullptr : isIntf.data (), p->checkBounds, lim, hp, err) != 0) {
         return fail (MFB_ERR_ARG, "ring plan: " + err);
     }
     if (hp.blob.empty ()) hp.blob.resize (16);
@@ -397,7 +406,9 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     MFB_CUDA (ring_configure (c->operatorID));
     cudaDeviceProp prop;
     MFB_CUDA (cudaGetDeviceProperties (&prop, c->device));
-    const int perSM = std::max (1, std::min ((int)(prop.sharedMemPerMultiprocessor / (c->tiledSmem + 1024)), 2048 / c->threads));
+    int perSM = 1;         // registers limit the 384-thread kernel to two CTAs per SM whatever the shared memory allows
+    MFB_CUDA (ring_ctas_per_sm (c->operatorID, c->threads, c->tiledSmem, &perSM));
+    perSM = std::max (perSM, 1);
     c->tiledCtas = (o && o->ctas > 0) ? o->ctas : (o && o->ctas == -1) ? (1 << 30) : prop.multiProcessorCount * perSM;
     return MFB_OK;
 }
@@ -407,7 +418,7 @@ cudaError_t launch_write_once (mfb_ctx *c, int firstTile, int nbTiles, int ctas,
 {
     if (c->ring) {
         return launch_ring (c->operatorID, c->ringPlan, firstTile, nbTiles, ctas, c->threads, c->tiledSmem, c->dCoord,
-                            c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, stream);
+                            c->dValues, c->dPrec, fusePrec, stream);
     }
     return launch_tiled (c->operatorID, c->plan, firstTile, nbTiles, ctas, c->threads, c->tiledSmem, c->dCoord,
                          c->dValues, c->dPrec, c->dCheckBounds, c->nbNodes, fusePrec, stream, c->tiledPrefetch);
@@ -576,11 +587,28 @@ extern "C" void mfb_ctx_destroy (mfb_ctx *c)
     delete c;
 }
 
+// Node ids of the caller's arrays are used as indices by the plan builders: range-check them before.
+static const char *check_problem_ids (const mfb_problem *p)
+{
+    if (p->nbElem > 0 && !p->elemToNode) return "missing elemToNode";
+    for (size_t k = 0; k < (size_t)std::max (p->nbElem, 0) * 4; k++) {
+        if (p->elemToNode[k] < 1 || p->elemToNode[k] > p->nbNodes) return "elemToNode id out of range";
+    }
+    if (p->nbBlocks > 1 && p->nbIntf > 0 && p->nbIntfNodes > 0) {
+        if (!p->intfIndex || !p->intfNodes) return "missing interface arrays";
+        if (p->intfIndex[0] != 0 || p->intfIndex[p->nbIntf] != p->nbIntfNodes) return "intfIndex / nbIntfNodes mismatch";
+        for (int j = 0; j < p->nbIntfNodes; j++) {
+            if (p->intfNodes[j] < 1 || p->intfNodes[j] > p->nbNodes) return "interface node id out of range";
+        }
+    }
+    return nullptr;
+}
+
 static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx *c)
 {
     c->path = o ? o->path : MFB_PATH_TILED;
     c->device = o ? o->device : 0;
-    c->threads = (o && o->threads > 0) ? o->threads : 256;
+    c->threads = (o && o->threads > 0) ? o->threads : ((o ? o->path : MFB_PATH_TILED) == MFB_PATH_RING ? 384 : 256);
     c->useGraph = o ? o->useGraph : 0;
     if (c->path < MFB_PATH_TILED || c->path > MFB_PATH_RING) return fail (MFB_ERR_ARG, "mfb_ctx_create: unknown path");
     if (c->path == MFB_PATH_RING) {          // a write-once path like TILED: same stages, same fused iteration
@@ -588,7 +616,7 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
         c->path = MFB_PATH_TILED;
         if (c->threads != 256 && c->threads != 384) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 256 or 384 threads per CTA");
     }
-    if (c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {
+    if (!c->ring && c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {
         return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256], or the pipelined kernel's CTA size");
     }
     if (p->operatorID != 0 && p->operatorID != 1) return fail (MFB_ERR_ARG, "mfb_ctx_create: operatorID must be 0 (lap) or 1 (ela)");
@@ -604,6 +632,8 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     if (p->nbBlocks > 1 && p->nbIntf > 0 && (!p->intfIndex || !p->intfNodes || !p->neighborsList)) {
         return fail (MFB_ERR_ARG, "mfb_ctx_create: missing interface arrays");
     }
+    // ids are used as indices by the plan builders below: range-check them first
+    if (const char *bad = check_problem_ids (p)) return fail (MFB_ERR_ARG, std::string ("mfb_ctx_create: ") + bad);
     c->operatorID = p->operatorID;
     c->operatorDim = p->operatorID == 0 ? 1 : 9;
     c->nbElem = p->nbElem; c->nbNodes = p->nbNodes; c->nbEdges = p->nbEdges;
@@ -1011,6 +1041,7 @@ extern "C" int mfb_ctx_run_timed (mfb_ctx *c, int steps, float *ms)
 extern "C" int mfb_tile_plan_selfcheck (const mfb_problem *p, int tileRows, int tileElems, int64_t stats[6])
 {
     if (!p || !stats) return fail (MFB_ERR_ARG, "mfb_tile_plan_selfcheck: NULL argument");
+    if (const char *bad = check_problem_ids (p)) return fail (MFB_ERR_ARG, std::string ("mfb_tile_plan_selfcheck: ") + bad);
     TilePlanLimits lim;
     if (tileRows > 0) lim.maxRows = tileRows;
     if (tileElems > 0) lim.maxElems = tileElems;
@@ -1039,6 +1070,7 @@ extern "C" int mfb_tile_plan_selfcheck (const mfb_problem *p, int tileRows, int 
 extern "C" int mfb_ring_plan_selfcheck (const mfb_problem *p, int tileRows, int tileEntries, int64_t stats[12])
 {
     if (!p || !stats) return fail (MFB_ERR_ARG, "mfb_ring_plan_selfcheck: NULL argument");
+    if (const char *bad = check_problem_ids (p)) return fail (MFB_ERR_ARG, std::string ("mfb_ring_plan_selfcheck: ") + bad);
     RingPlanLimits lim;
     if (tileRows > 0) lim.maxRows = tileRows;
     if (tileEntries > 0) lim.maxEntries = tileEntries;
@@ -1050,10 +1082,10 @@ extern "C" int mfb_ring_plan_selfcheck (const mfb_problem *p, int tileRows, int 
     RingPlan plan;
     std::string err;
     if (build_ring_plan (p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, p->coord,
-                         isIntf.empty () ? nullptr : isIntf.data (), lim, plan, err) != 0) {
+                         isIntf.empty () ? nullptr : isIntf.data (), p->checkBounds, lim, plan, err) != 0) {
         return fail (MFB_ERR_ARG, "ring plan: " + err);
     }
-    if (verify_ring_plan (plan, p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, err) != 0) {
+    if (verify_ring_plan (plan, p->nbNodes, p->nbElem, p->elemToNode, p->nodeToNodeRow, p->nodeToNodeColumn, p->checkBounds, err) != 0) {
         return fail (MFB_ERR_STATE, "ring plan self-check: " + err);
     }
     stats[0] = plan.nbTiles; stats[1] = plan.nbJobs; stats[2] = plan.nbSymmetricJobs; stats[3] = plan.nbRingSteps;

@@ -113,6 +113,33 @@ MFB_DM void invert3_lu (double b[9])
     b[2] = x20; b[5] = x21; b[8] = x22;
 }
 
+// The same block — masked like mask_block, inverted like ela_invert_prec — the way the RING kernel's write-out
+// forms it: nine lanes hold one component each, so instead of an LU with row exchanges every lane builds the
+// cofactor it needs from four other components (fetched by shuffles) and divides by the determinant (expansion
+// along row 0; the reciprocal by `rcp`).  For the 3x3 diagonal blocks of the elasticity operator (symmetric
+// positive definite, condition number of a few units) this agrees with LAPACK's result to a few ulp of the
+// largest entry.  Returns false when the determinant is zero or not finite: the caller then runs invert3_lu,
+// whose infinities and NaNs are the ones DGETRF / DGETRI produce.
+// m = masked block, row-major; component c = 3a + b of the inverse is cofactor (b, a) / det.
+MFB_DM int adj_src (int r, int s) { return 3 * (r % 3) + s % 3; }
+
+template <class Rcp>
+MFB_DM bool invert3_adj (const double m[9], double inv[9], Rcp rcp)
+{
+    double cof[9];
+    for (int c = 0; c < 9; c++) {
+        const int a = c / 3, b = c % 3;            // cofactor of row b, column a
+        const double t = m[adj_src (b + 1, a + 2)] * m[adj_src (b + 2, a + 1)];
+        cof[c] = fma (m[adj_src (b + 1, a + 1)], m[adj_src (b + 2, a + 2)], -t);
+    }
+    // cofactors of row 0 sit at c = 0, 3, 6 (b = 0, a = 0..2)
+    const double det = (m[0] * cof[0] + m[1] * cof[3]) + m[2] * cof[6];
+    if (!(fabs (det) > 0.0) || !(fabs (det) < 1.0e300)) return false;
+    const double r = rcp (det);
+    for (int c = 0; c < 9; c++) inv[c] = cof[c] * r;
+    return true;
+}
+
 }  // namespace mfb
 
 #endif

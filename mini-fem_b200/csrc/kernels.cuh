@@ -86,9 +86,11 @@ struct DeviceRingPlan {
 };
 size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan);
 cudaError_t ring_configure (int operatorID);
+// resident CTAs per SM of the RING kernel for this CTA size and dynamic shared memory (occupancy API)
+cudaError_t ring_ctas_per_sm (int operatorID, int threads, size_t smemBytes, int *ctas);
 cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,
                          int threads, size_t smemBytes, const double *coord, double *values, double *prec,
-                         const int *checkBounds, int nbNodes, int fusePrec, cudaStream_t stream);
+                         int fusePrec, cudaStream_t stream);      // the Dirichlet mask travels in the plan (RingRow::node)
 
 }  // namespace mfb
 

@@ -28,7 +28,7 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
     if (maxRows > 0) lim.maxRows = maxRows;
     if (maxEntries > 0) lim.maxEntries = maxEntries;
     RingPlan hp;
-    if (build_ring_plan (nbNodes, nbElem, elemToNode, row, col, coord, isInterface, lim, hp, g_error) != 0) return -1;
+    if (build_ring_plan (nbNodes, nbElem, elemToNode, row, col, coord, isInterface, checkBounds, lim, hp, g_error) != 0) return -1;
     std::vector<uint64_t> packed (hp.tileOffset);
     for (int t = 0; t < hp.nbTiles; t++) packed[t] |= (uint64_t)(hp.header (t)->headBytes >> 4) << 48;
     // 16-byte aligned copy of the records, as cudaMalloc would give
@@ -42,8 +42,8 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
     args.plan.maxEntries = std::max (hp.maxEntries, 1);
     args.plan.maxHeadBytes = std::max (hp.maxHeadBytes, 16u); args.plan.maxTailBytes = std::max (hp.maxTailBytes, 16u);
     args.smem = ring_smem_layout (operatorID, args.plan);
-    args.coord = coord; args.values = values; args.prec = prec; args.checkBounds = checkBounds;
-    args.nbNodes = nbNodes; args.fusePrec = fusePrec; args.firstTile = 0; args.lastTile = hp.nbTiles;
+    args.coord = coord; args.values = values; args.prec = prec;
+    args.fusePrec = fusePrec; args.firstTile = 0; args.lastTile = hp.nbTiles;
     if (hp.nbTiles == 0) return 0;
     const size_t smem = ring_smem_bytes (operatorID, args.plan);
     auto launch = [&] (int firstTile, int nbTiles, int grid) {

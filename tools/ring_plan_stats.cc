@@ -30,16 +30,19 @@ int main (int argc, char **argv)
     if (getenv ("RING_NOBANK")) lim.bankAware = false;
     if (getenv ("RING_PASSES")) lim.refinePasses = atoi (getenv ("RING_PASSES"));
     if (getenv ("RING_SWEEPS")) lim.rotationSweeps = atoi (getenv ("RING_SWEEPS"));
+    if (getenv ("RING_NOSPLIT")) lim.slabSplit = false;
+    if (getenv ("RING_MAXJOBS")) lim.maxJobs = atoi (getenv ("RING_MAXJOBS"));
+    const int warps = getenv ("RING_WARPS") ? atoi (getenv ("RING_WARPS")) : 8;      // warps per CTA: rounds of the job phase / write-out
     RingPlan plan;
     std::string err;
     auto t0 = std::chrono::steady_clock::now ();
-    if (build_ring_plan (m.nbNodes, m.nbElem, m.elemToNode.data (), row.data (), col.data (), m.coord.data (), nullptr, lim, plan, err)) {
+    if (build_ring_plan (m.nbNodes, m.nbElem, m.elemToNode.data (), row.data (), col.data (), m.coord.data (), nullptr, nullptr, lim, plan, err)) {
         printf ("ring plan: %s\n", err.c_str ());
         return 1;
     }
     const double seconds = std::chrono::duration<double> (std::chrono::steady_clock::now () - t0).count ();
     const double E = m.nbElem, Z = row[m.nbNodes];
-    const double gather = plan.gatherWavefronts / E, slabW = 4.5 * plan.slabWriteWavefronts / E;
+    const double gather = plan.gatherWavefronts / E, slabW = 9.0 * plan.slabWriteWavefronts / E;
     const double slabR = 2.0 * (Z - m.nbNodes) / 3.0 / E;             // 3 entries per warp iteration, 2 wavefronts
     const double misc = (plan.nbPaddedSteps / 32.0 / 7.0 * 4.0 + plan.nbTiles * 3.0 * plan.maxNodes * 8.0 / 128.0) / E;
     printf ("%s: E %d N %d Z %.0f | rows<=%d entries<=%d | build %.2f s | tiles %d | plan %.1f MB (%.1f B/elem)\n", what, m.nbElem, m.nbNodes, Z,
@@ -50,7 +53,26 @@ int main (int argc, char **argv)
     printf ("  modelled shared-memory wavefronts per element: gather %.2f (x%.2f of conflict-free) + slab stores %.2f (x%.2f) + slab reads %.2f + codes/coords %.2f = %.2f  -> %.1f M per iteration\n",
             gather, (double)plan.gatherWavefronts / plan.gatherIdeal, slabW, (double)plan.slabWriteWavefronts / plan.slabWriteIdeal, slabR, misc,
             gather + slabW + slabR + misc, (gather + slabW + slabR + misc) * E / 1e6);
-    if (verify_ring_plan (plan, m.nbNodes, m.nbElem, m.elemToNode.data (), row.data (), col.data (), err)) { printf ("  VERIFY FAILED: %s\n", err.c_str ()); return 1; }
+    {   // per tile: warp batches of the job phase, row groups of the write-out -> rounds of a CTA of `warps` warps
+        std::vector<long long> histB (64, 0), histR (64, 0);
+        long long roundsJob = 0, roundsOut = 0, batches = 0, groups = 0;
+        for (int t = 0; t < plan.nbTiles; t++) {
+            const RingTileHeader &h = *plan.header (t);
+            const int g = (h.nbRows + 2) / 3;
+            histB[std::min<int> (h.nbBatches, 63)]++; histR[std::min<int> (h.nbRows, 63)]++;
+            batches += h.nbBatches; groups += g;
+            roundsJob += (h.nbBatches + warps - 1) / warps; roundsOut += (g + warps - 1) / warps;
+        }
+        printf ("  %d warps per CTA: job phase %.3f rounds per tile (batches / warps = %.3f: efficiency %.2f), write-out %.3f rounds (row groups / warps = %.3f: efficiency %.2f)\n",
+                warps, (double)roundsJob / plan.nbTiles, (double)batches / plan.nbTiles / warps, (double)batches / warps / roundsJob,
+                (double)roundsOut / plan.nbTiles, (double)groups / plan.nbTiles / warps, (double)groups / warps / roundsOut);
+        printf ("  batches per tile:");
+        for (int b = 0; b < 64; b++) if (histB[b]) printf (" %d:%lld", b, histB[b]);
+        printf ("\n  rows per tile:");
+        for (int b = 0; b < 64; b++) if (histR[b]) printf (" %d:%lld", b, histR[b]);
+        printf ("\n");
+    }
+    if (verify_ring_plan (plan, m.nbNodes, m.nbElem, m.elemToNode.data (), row.data (), col.data (), nullptr, err)) { printf ("  VERIFY FAILED: %s\n", err.c_str ()); return 1; }
     printf ("  verify ok\n");
     return 0;
 }

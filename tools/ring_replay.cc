@@ -24,7 +24,7 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
                    double *values, double *prec)
 {
     const double kNaN = std::numeric_limits<double>::quiet_NaN ();
-    constexpr int SLAB = OPDIM == 9 ? 10 : 1;          // doubles per slab entry, as in the kernel (ring_slab_stride)
+    constexpr int SLAB = OPDIM;                        // the slab is an image of the CSR rows: no padding inside an entry
     std::vector<double> X, Y, Z, slab, sDiag;
     for (int t = 0; t < plan.nbTiles; t++) {
         const uint8_t *base = plan.blob.data () + plan.tileOffset[t];
@@ -124,24 +124,28 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
                 }
             }
         }
-        // ---- fused preconditioner: prec_init + prec_inversion of the owned rows -------------------
+        // ---- fused preconditioner: prec_init + prec_inversion of the owned rows (the mask comes from the plan) ----
         if (!fusePrec) continue;
         for (int r = 0; r < h.nbRows; r++) {
             const RingRow rr = rows[r];
-            const int node = rr.node & 0x7fffffff;
+            const int node = rr.node & kRingNodeMask;
             const bool isInterface = rr.node < 0, hasDiag = rr.diagOff != 0xFFFF;
+            if (checkBounds) {
+                for (int c = 0; c < 3; c++) if (((rr.node >> (28 + c)) & 1) != (checkBounds[(size_t)c * nbNodes + node] != 0)) { g_error = "mask bits"; return -1; }
+            }
             if (OPDIM == 1) {
                 const double dgl = sDiag[r];
                 prec[node] = isInterface ? dgl : 1.0 / dgl;
             }
             else {
-                double b[9];
+                double b[9], inv[9];
                 for (int q = 0; q < 9; q++) b[q] = sDiag[(size_t)r * 9 + q];
                 if (!isInterface) {
-                    int mx = 0, my = 0, mz = 0;
-                    if (checkBounds) { mx = checkBounds[node]; my = checkBounds[(size_t)nbNodes + node]; mz = checkBounds[2 * (size_t)nbNodes + node]; }
-                    mask_block (b, mx, my, mz);
-                    if (hasDiag) invert3_lu (b);
+                    mask_block (b, (rr.node >> 28) & 1, (rr.node >> 29) & 1, (rr.node >> 30) & 1);
+                    if (hasDiag) {
+                        if (invert3_adj (b, inv, [] (double x) { return ring_rcp (x); })) { for (int q = 0; q < 9; q++) b[q] = inv[q]; }
+                        else invert3_lu (b);
+                    }
                 }
                 for (int q = 0; q < 9; q++) prec[(size_t)node * 9 + q] = b[q];
             }
@@ -168,8 +172,8 @@ extern "C" int mfb_ring_replay (int operatorID, int nbNodes, int nbElem, const i
     if (maxEntries > 0) lim.maxEntries = maxEntries;
     lim.bankAware = bankAware != 0;
     RingPlan plan;
-    if (build_ring_plan (nbNodes, nbElem, elemToNode, row, col, coord, isInterface, lim, plan, g_error) != 0) return -1;
-    if (verify_ring_plan (plan, nbNodes, nbElem, elemToNode, row, col, g_error) != 0) { g_error = "verify_ring_plan: " + g_error; return -2; }
+    if (build_ring_plan (nbNodes, nbElem, elemToNode, row, col, coord, isInterface, checkBounds, lim, plan, g_error) != 0) return -1;
+    if (verify_ring_plan (plan, nbNodes, nbElem, elemToNode, row, col, checkBounds, g_error) != 0) { g_error = "verify_ring_plan: " + g_error; return -2; }
     if (stats) {
         const int64_t s[16] = {plan.nbTiles, plan.nbJobs, plan.nbSymmetricJobs, plan.nbRingSteps, plan.nbPaddedSteps, plan.nbBreaks,
                                plan.gatherWavefronts, plan.gatherIdeal, plan.slabWriteWavefronts, plan.slabWriteIdeal,
