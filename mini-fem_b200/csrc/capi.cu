@@ -360,17 +360,9 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
         isIntf.assign ((size_t)p->nbNodes, 0);
         for (int j = 0; j < p->nbIntfNodes; j++) isIntf[p->intfNodes[j] - 1] = 1;
     }
-    // Tiles sized for the CTA: one warp batch of 32 jobs and one group of three rows per warp and tile, so that
-    // neither phase leaves warps idle at the block barrier.  384 threads (12 warps, two CTAs per SM): 34 rows,
-    // <= 384 jobs; 256 threads (8 warps, three CTAs per SM): 22 rows, <= 256 jobs.
     RingPlanLimits lim;
-    const bool wide = c->threads == 384;
-    lim.maxRows = wide ? 34 : 22;
-    lim.maxEntries = wide ? 544 : 352;
-    lim.maxJobs = wide ? 384 : 256;
     if (o && o->tileRows > 0) lim.maxRows = o->tileRows;
     if (o && o->tileElems > 0) lim.maxEntries = o->tileElems;          // RING: tileElems caps the slab slots of a tile
-    if (o && (o->tileRows > 0 || o->tileElems > 0)) lim.maxJobs = 1 << 30;
     lim.bankAware = !(o && o->bankAware < 0);
     // experiment knobs: MFB_RING_CUT=morton (tiles = runs of the Morton curve, like TILED),
     // MFB_RING_REFINE=n (renumber-and-rotate rounds of the bank-aware numbering), MFB_RING_SWEEPS=n
@@ -608,7 +600,7 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
 {
     c->path = o ? o->path : MFB_PATH_TILED;
     c->device = o ? o->device : 0;
-    c->threads = (o && o->threads > 0) ? o->threads : ((o ? o->path : MFB_PATH_TILED) == MFB_PATH_RING ? 384 : 256);
+    c->threads = (o && o->threads > 0) ? o->threads : 256;
     c->useGraph = o ? o->useGraph : 0;
     if (c->path < MFB_PATH_TILED || c->path > MFB_PATH_RING) return fail (MFB_ERR_ARG, "mfb_ctx_create: unknown path");
     if (c->path == MFB_PATH_RING) {          // a write-once path like TILED: same stages, same fused iteration

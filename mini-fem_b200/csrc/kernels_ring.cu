@@ -1,29 +1,31 @@
 // RING path: write-once assembly (+ fused preconditioner) that walks the ring of elements around
 // every mesh edge straight from the node coordinates (host/ring_plan.h, csrc/ring_math.h).
 //
-// A lane owns a mesh EDGE {i, j}: it keeps x_i and d = x_j - x_i in registers, loads ONE node (24 bytes)
-// per element of the ring, rebuilds the two gradients from the coordinates (two cross products, one
-// reciprocal) and accumulates A_ij; an edge inside the tile yields both K_ij and K_ji = K_ij^T.  There are no
-// coefficient planes and no diagonal pass: the diagonal block of a row is minus the sum of the row's
-// off-diagonal blocks (element matrices have zero row sums).
+// The TILED kernel is bound by shared-memory bandwidth: 12 coefficients stored per tile element,
+// 48 bytes gathered per contribution, every border element recomputed in ~2.2 tiles.  Here a lane
+// owns a mesh EDGE {i, j}: it keeps x_i and d = x_j - x_i in registers, loads ONE node (24 bytes)
+// per element of the ring, rebuilds the two gradients from the coordinates (two cross products,
+// one reciprocal) and accumulates A_ij; an edge inside the tile yields both K_ij and K_ji = K_ij^T.
+// There are no coefficient planes and no diagonal pass: the diagonal block of a row is minus the sum
+// of the row's off-diagonal blocks (element matrices have zero row sums) and is formed while the row
+// streams out of the slab.
 //
-// Second version (round 2), shaped by the ncu capture of the first (profiles/r2_ring_ela_ncu_full.txt: a
-// quarter of the warp samples parked at two block barriers per tile, 230 instructions per three rows in a
-// write-out that copied the slab to global memory entry by entry, 9 % in a separate preconditioner pass):
-//   * the slab is a byte image of the tile's CSR rows and there are TWO of them: tile t's rows leave for
-//     global memory as TMA bulk stores (cp.async.bulk.global.shared::cta, one per run of rows that are
-//     consecutive in the matrix) while the job phase of tile t+1 already fills the other slab — ONE block
-//     barrier per tile (between the job phase and the write-out), no waiting for stores;
-//   * the write-out only sums: three rows per warp side by side, nine lanes each; the diagonal block goes
-//     into its slab slot, and the same nine lanes mask and invert it on the spot (cofactors through warp
-//     shuffles, invert3_adj) and write the preconditioner block coalesced — no second pass, no staging;
-//   * everything a tile needs arrives ahead of time: the plan HEAD three tiles ahead (TMA, four buffers),
-//     the TAIL two tiles ahead (TMA, two buffers: with a write-out this short a tail requested at the
-//     barrier would not be in when the next job phase starts), the node coordinates one tile ahead
-//     (cp.async, two plane sets).
-// Per tile:  [job phase: one lane per edge, 32 jobs per warp batch]  barrier  [write-out: row sums,
-// diagonal + preconditioner blocks, bulk stores].  Every CSR entry is written exactly once; the summation
-// order is fixed by the plan.
+// Per tile:
+//   0. plan record by TMA (cp.async.bulk + mbarrier): the HEAD of tile t+1 (header, row table, node
+//      list) is fetched at the start of tile t, the TAIL (batches, jobs, ring codes) and the
+//      coordinates (cp.async) of tile t+1 while tile t is in its write-out;
+//   1. job phase: one lane per edge, 32 jobs per warp batch, ring codes 8 to a 64-bit word;
+//      finished 3x3 blocks go to the tile-wide slab at the slots of their CSR entries (entry stride
+//      80 bytes, so a block leaves as four 128-bit stores and one 64-bit store);
+//   2. write-out: three consecutive rows per warp, ten lanes each (9 components + one idle lane): a lane
+//      walks its row entry by entry, copies its component to global memory (72 contiguous bytes per
+//      group and instruction) and sums it, then stores its component of the diagonal entry; row starts
+//      in the slab are padded so that the three pieces read together fall into disjoint banks;
+//   3. fused mode: the diagonal blocks wait in shared memory until the tile is done; the last two warps
+//      of the CTA (they get the fewest job batches) then mask / invert them into prec, one lane per
+//      row, at the head of the next tile (prec_init + prec_inversion, src/preconditioner.cc:25-87,
+//      src/Fortran/elasclpr.f:19-53) — two warps with full lanes instead of every warp with four.
+// Every CSR entry is written exactly once by a plain store; the summation order is fixed by the plan.
 #include "kernels.cuh"
 #include "device_math.cuh"
 #include "ring_math.h"
@@ -32,16 +34,14 @@ namespace mfb {
 
 namespace {
 
-static_assert (sizeof (RingTileHeader) == 48 && sizeof (RingRow) == 16 && sizeof (RingBatch) == 8,
+static_assert (sizeof (RingTileHeader) == 32 && sizeof (RingRow) == 16 && sizeof (RingBatch) == 8,
                "plan records are copied to the device verbatim");
-
-constexpr int kRingHeadBuffers = 4;
 
 // Byte offsets of the kernel's shared-memory sections, computed once on the host and passed as kernel
 // arguments (constant bank): the compiler otherwise rebuilds them from the plan maxima inside the loops.
 struct RingSmemLayout {
-    unsigned headBytes;          // size of one head buffer; head b at b * headBytes
-    unsigned tail, tailBytes, planes, slab, slabBytes, bars, total;
+    unsigned headBytes;          // size of one head buffer; head 0 at 0, head 1 at headBytes
+    unsigned tail, planes, slab, diag, meta, bars, total;
 };
 
 struct RingArgs {
@@ -66,11 +66,6 @@ inline void ring_mbar_expect_tx (uint64_t *bar, unsigned bytes) { cta_emu::mbar_
 inline void ring_mbar_arrive (uint64_t *bar) { cta_emu::mbar_expect_tx (bar, 0); }
 inline void ring_mbar_wait (uint64_t *bar, unsigned parity) { cta_emu::mbar_wait (bar, parity); }
 inline void ring_bulk_load (void *dst, const void *src, unsigned bytes, uint64_t *bar) { cta_emu::bulk_load (dst, src, bytes, bar); }
-inline void ring_bulk_store (void *dst, const void *src, unsigned bytes) { cta_emu::bulk_store (dst, src, bytes); }
-inline void ring_bulk_commit () {}
-inline void ring_bulk_wait_read () {}
-inline void ring_bulk_wait_all () {}
-inline void ring_fence_async () {}
 inline void ring_cp_async_f64 (double *dst, const double *src) { *dst = *src; }
 inline void ring_cp_async_wait_all () {}
 #else
@@ -115,20 +110,6 @@ __device__ __forceinline__ void ring_bulk_load (void *dst, const void *src, unsi
                   :: "r"(ring_smem_u32 (dst)), "l"(src), "r"(bytes), "r"(ring_smem_u32 (bar)) : "memory");
 }
 
-// TMA bulk copy shared -> global (both addresses and the size multiples of 16 bytes), tracked by the
-// issuing thread's bulk async-group.
-__device__ __forceinline__ void ring_bulk_store (void *dst, const void *src, unsigned bytes)
-{
-    asm volatile ("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                  :: "l"(dst), "r"(ring_smem_u32 (src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ring_bulk_commit () { asm volatile ("cp.async.bulk.commit_group;" ::: "memory"); }
-// this thread's bulk stores have READ their shared-memory source (the slab may be overwritten)
-__device__ __forceinline__ void ring_bulk_wait_read () { asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void ring_bulk_wait_all () { asm volatile ("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// generic-proxy writes to shared memory become visible to the async proxy (the TMA unit)
-__device__ __forceinline__ void ring_fence_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 __device__ __forceinline__ void ring_cp_async_f64 (double *dst, const double *src)
 {
     asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(ring_smem_u32 (dst)), "l"(src) : "memory");
@@ -142,20 +123,23 @@ __host__ __device__ __forceinline__ unsigned ring_align128 (unsigned x) { return
 // doubles per coordinate plane: tile-local node ids are one byte (kRingMaxNodes = 254)
 constexpr int kRingPlane = 256;
 
-// THREADS / MINB: 384 threads, two CTAs per SM (tiles of 12 warp batches and 12 row groups) or 256
-// threads, three CTAs per SM (tiles of 8 / 8) — 24 warps per SM either way.
+// doubles per slab entry: an elasticity block is padded to 80 bytes so that it is 16-byte aligned
+__host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim == 9 ? 10 : 1; }
+
+// THREADS / MINB: 256 threads, three CTAs per SM (default) or 384 threads, two CTAs per SM (larger tiles:
+// mfb_options.threads = 384 with tileRows / tileElems raised, e.g. 54 / 960) — 24 warps per SM either way.
 inline RingSmemLayout ring_smem_layout (int operatorID, const DeviceRingPlan &plan)
 {
     const int opDim = operatorID == 0 ? 1 : 9;
     RingSmemLayout L;
     L.headBytes = ring_align128 (plan.maxHeadBytes);
-    L.tail = kRingHeadBuffers * L.headBytes;
-    L.tailBytes = ring_align128 (plan.maxTailBytes);
-    L.planes = L.tail + 2 * L.tailBytes;
-    L.slab = L.planes + 2 * 3 * kRingPlane * (unsigned)sizeof (double);
-    L.slabBytes = ring_align128 ((unsigned)plan.maxEntries * opDim * (unsigned)sizeof (double));
-    L.bars = L.slab + 2 * L.slabBytes;
-    L.total = L.bars + (kRingHeadBuffers + 2) * (unsigned)sizeof (uint64_t);
+    L.tail = 2 * L.headBytes;
+    L.planes = L.tail + ring_align128 (plan.maxTailBytes);
+    L.slab = L.planes + 3 * kRingPlane * (unsigned)sizeof (double);
+    L.diag = L.slab + ring_align128 ((unsigned)plan.maxEntries * ring_slab_stride (opDim) * (unsigned)sizeof (double));
+    L.meta = L.diag + (((unsigned)plan.maxRows * opDim * (unsigned)sizeof (double) + 15u) & ~15u);
+    L.bars = L.meta + (((unsigned)plan.maxRows * (unsigned)sizeof (int) + 15u) & ~15u);
+    L.total = L.bars + 3 * (unsigned)sizeof (uint64_t);
     return L;
 }
 
@@ -172,94 +156,134 @@ ring_assembly_kernel (const RingArgs args)
     const int tid = threadIdx.x, nThreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nWarps = nThreads >> 5;
 
-    // shared memory: [head 0..3][tail 0, 1][X Y Z of even tiles][X Y Z of odd tiles][slab 0][slab 1][6 mbarriers]
+    // shared memory: [head 0][head 1][tail][X Y Z][slab][diagonal blocks][row tags][3 mbarriers]
     const RingSmemLayout &L = args.smem;
     const unsigned headBytes = L.headBytes;
     constexpr int planeStride = kRingPlane;                           // planes start on a 128-byte line: bank = id mod 16;
                                                                       // a constant, so that Y and Z are immediate offsets from X
-    unsigned char *sHead0 = smemRaw, *sTail0 = smemRaw + L.tail;
-    double *planes0 = reinterpret_cast<double*> (smemRaw + L.planes);
-    double *slab0 = reinterpret_cast<double*> (smemRaw + L.slab);
-    const unsigned slabDoubles = L.slabBytes / (unsigned)sizeof (double);
+    constexpr int SLAB = ring_slab_stride (OPDIM);
+    unsigned char *sHead0 = smemRaw, *sTail = smemRaw + L.tail;
+    double *sX = reinterpret_cast<double*> (smemRaw + L.planes), *sY = sX + planeStride, *sZ = sY + planeStride;
+    double *slab = reinterpret_cast<double*> (smemRaw + L.slab);
+    double *sDiag = reinterpret_cast<double*> (smemRaw + L.diag);
+    int *sMeta = reinterpret_cast<int*> (smemRaw + L.meta);           // node | interface << 31 | hasDiag << 30
     uint64_t *bars = reinterpret_cast<uint64_t*> (smemRaw + L.bars);
-    uint64_t *headFull = bars, *tailFull = bars + kRingHeadBuffers;   // headFull[4], tailFull[2]
+    uint64_t *headFull = bars, *tailFull = bars + 2;                  // headFull[2], tailFull
+
+    if (tid == 0) { ring_mbar_init (headFull, 1); ring_mbar_init (headFull + 1, 1); ring_mbar_init (tailFull, 1); }
+    __syncthreads ();
 
     const int firstTile = args.firstTile + blockIdx.x, tileStep = gridDim.x;
-    const int nbMine = firstTile < args.lastTile ? (args.lastTile - firstTile + tileStep - 1) / tileStep : 0;
-    if (nbMine == 0) return;
-
-    if (tid == 0) {
-        for (int b = 0; b < kRingHeadBuffers; b++) ring_mbar_init (headFull + b, 1);
-        ring_mbar_init (tailFull, 1); ring_mbar_init (tailFull + 1, 1);
-    }
-    __syncthreads ();
-
-    auto head_of = [&] (int k) { return sHead0 + (unsigned)(k & (kRingHeadBuffers - 1)) * headBytes; };
     auto fetch_head = [&] (uint64_t packed, int k) {                  // thread 0 only
         const unsigned bytes = ring_record_head_bytes (packed);
-        uint64_t *bar = headFull + (k & (kRingHeadBuffers - 1));
-        ring_mbar_expect_tx (bar, bytes);
-        ring_bulk_load (head_of (k), P.blob + ring_record_offset (packed), bytes, bar);
+        ring_mbar_expect_tx (headFull + (k & 1), bytes);
+        ring_bulk_load (sHead0 + (k & 1) * headBytes, P.blob + ring_record_offset (packed), bytes, headFull + (k & 1));
     };
-    auto wait_head = [&] (int k) { ring_mbar_wait (headFull + (k & (kRingHeadBuffers - 1)), (unsigned)(k / kRingHeadBuffers) & 1u); };
-    auto fetch_tail = [&] (int k) {                                   // thread 0 only, head k has landed
-        const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head_of (k));
+    auto fetch_tail = [&] (uint64_t packed, const unsigned char *head) {   // thread 0 only, `head` has landed
+        const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
         const unsigned bytes = h.blobBytes - h.headBytes;
-        uint64_t *bar = tailFull + (k & 1);
         if (bytes) {
-            ring_mbar_expect_tx (bar, bytes);
-            ring_bulk_load (sTail0 + (unsigned)(k & 1) * L.tailBytes, P.blob + h.selfOffset + h.headBytes, bytes, bar);
+            ring_mbar_expect_tx (tailFull, bytes);
+            ring_bulk_load (sTail, P.blob + ring_record_offset (packed) + h.headBytes, bytes, tailFull);
         }
-        else ring_mbar_arrive (bar);                                    // a tile without jobs: the phase completes at once
+        else ring_mbar_arrive (tailFull);                               // a tile without jobs: the phase completes at once
     };
-    auto gather_coords = [&] (const unsigned char *head, double *planes) {   // all threads, asynchronous
+    // Node coordinates of a tile: thread n loads node n (three 8-byte loads from global memory) and later
+    // stores it into the planes with the warp's 32 nodes side by side — two wavefronts per store.  (An 8-byte
+    // cp.async per coordinate costs one shared-memory wavefront EACH when the data come back: ~20 M of the
+    // 77 M wavefronts of an EIB iteration in the round-1 kernel, profiles/r2_ring_ela_ncu_full.txt.)
+    static_assert (THREADS >= kRingMaxNodes, "one node per thread");
+    auto load_coords = [&] (const unsigned char *head, double c[3]) {
         const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
         const int *nodes = reinterpret_cast<const int*> (head + h.offNodes);
-        for (int n = tid; n < h.nbNodes; n += nThreads) {
-            const double *q = args.coord + (size_t)nodes[n] * 3;
-            ring_cp_async_f64 (planes + n, q); ring_cp_async_f64 (planes + planeStride + n, q + 1);
-            ring_cp_async_f64 (planes + 2 * planeStride + n, q + 2);
+        if (tid < h.nbNodes) {
+            const double *q = args.coord + (size_t)nodes[tid] * 3;
+            c[0] = __ldg (q); c[1] = __ldg (q + 1); c[2] = __ldg (q + 2);
         }
     };
+    auto store_coords = [&] (const unsigned char *head, const double c[3]) {
+        const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
+        if (tid < h.nbNodes) { sX[tid] = c[0]; sY[tid] = c[1]; sZ[tid] = c[2]; }
+    };
 
-    // prologue: heads of this CTA's first three tiles, tail and coordinates of the first.  Thread 0 keeps the
-    // packed offset of the next head to fetch in a register, loaded a whole tile before it is needed.
-    uint64_t offAhead = 0;
-    if (tid == 0) {
-        for (int k = 0; k < 3 && k < nbMine; k++) fetch_head (P.tileOffset[firstTile + k * tileStep], k);
-        if (nbMine > 3) offAhead = P.tileOffset[firstTile + 3 * tileStep];
+    // thread 0 keeps the packed offsets of this tile and the next in registers and loads the one after
+    // that a whole tile ahead, so that issuing the copies never waits on global memory
+    uint64_t offCur = 0, offNext = 0;
+    if (tid == 0 && firstTile < args.lastTile) {
+        offCur = P.tileOffset[firstTile];
+        if (firstTile + tileStep < args.lastTile) offNext = P.tileOffset[firstTile + tileStep];
     }
-    wait_head (0);
-    if (tid == 0) {
-        fetch_tail (0);
-        if (nbMine > 1) { wait_head (1); fetch_tail (1); }
+    // prologue: head, tail and coordinates of this CTA's first tile
+    if (firstTile < args.lastTile) {
+        if (tid == 0) fetch_head (offCur, 0);
+        ring_mbar_wait (headFull, 0);
+        if (tid == 0) fetch_tail (offCur, sHead0);
+        double c[3] = {0.0, 0.0, 0.0};
+        load_coords (sHead0, c);
+        store_coords (sHead0, c);
     }
-    gather_coords (sHead0, planes0);
-    ring_cp_async_wait_all ();
     __syncthreads ();
 
-    for (int k = 0; k < nbMine; k++) {
-        const unsigned char *sHead = head_of (k);
+    // Fused preconditioner of one finished tile: its diagonal blocks and row tags are in sDiag / sMeta.
+    // Run by the last two warps, one lane per row.
+    auto prec_pass = [&] (int nbRowsDone) {
+        for (int r = (warp - (nWarps - 2)) * 32 + lane; r < nbRowsDone; r += 64) {
+            const int meta = sMeta[r];                                // RingRow::node | hasDiag << 27
+            const int node = meta & kRingNodeMask;
+            const bool isInterface = meta < 0, hasDiag = (meta & (1 << 27)) != 0;
+            if (OPDIM == 1) {
+                const double dgl = sDiag[r];
+                args.prec[node] = isInterface ? dgl : 1.0 / dgl;
+            }
+            else {
+                double b[9];
+                #pragma unroll
+                for (int q = 0; q < 9; q++) b[q] = sDiag[r * 9 + q];
+                if (!isInterface) {
+                    mask_block (b, (meta >> 28) & 1, (meta >> 29) & 1, (meta >> 30) & 1);
+                    if (hasDiag) {
+                        // cofactors over the determinant; a singular or non-finite block takes LAPACK's LU instead
+                        // (its infinities and NaNs are the reference's)
+                        double inv[9];
+                        if (invert3_adj (b, inv, [] (double x) { return ring_rcp (x); })) {
+                            #pragma unroll
+                            for (int q = 0; q < 9; q++) b[q] = inv[q];
+                        }
+                        else invert3_lu (b);
+                    }
+                }
+                double *dst = args.prec + (size_t)node * 9;
+                #pragma unroll
+                for (int q = 0; q < 9; q++) dst[q] = b[q];
+            }
+        }
+    };
+    const bool precWarp = args.fusePrec && warp >= nWarps - 2;
+    int rowsDone = 0;             // rows of the previous tile whose preconditioner blocks are still to be written
+
+    int k = 0;
+    for (int tile = firstTile; tile < args.lastTile; tile += tileStep, k++) {
+        const unsigned char *sHead = sHead0 + (k & 1) * headBytes;
         const RingTileHeader &hdr = *reinterpret_cast<const RingTileHeader*> (sHead);
+        const bool hasNext = tile + tileStep < args.lastTile;
+        // ---- 0. the next tile's head starts travelling ----------------------------------------
+        uint64_t offAfter = 0;
+        if (tid == 0) {
+            if (tile + 2 * tileStep < args.lastTile) offAfter = P.tileOffset[tile + 2 * tileStep];   // used next iteration
+            if (hasNext) fetch_head (offNext, k + 1);
+        }
         const int nbRows = hdr.nbRows, nbBatches = hdr.nbBatches;
         const RingRow *sRows = reinterpret_cast<const RingRow*> (sHead + sizeof (RingTileHeader));
-        const unsigned char *sTail = sTail0 + (unsigned)(k & 1) * L.tailBytes;
         const RingBatch *batches = reinterpret_cast<const RingBatch*> (sTail);
         const uint64_t *jobs = reinterpret_cast<const uint64_t*> (sTail + (hdr.offJobs - hdr.headBytes));
         const uint64_t *codes = reinterpret_cast<const uint64_t*> (sTail + (hdr.offCodes - hdr.headBytes));
-        const double *sX = planes0 + (k & 1) * (3 * planeStride), *sY = sX + planeStride, *sZ = sY + planeStride;
-        double *slab = slab0 + (k & 1) * slabDoubles;
 
-        // ---- 0. the next tile's coordinates start travelling into the other plane set -------------------
-        // (its head came in two tiles ago; the readers of that plane set, the jobs of tile k - 1, are behind
-        // the previous block barrier)
-        if (k + 1 < nbMine) {
-            wait_head (k + 1);
-            gather_coords (head_of (k + 1), planes0 + ((k + 1) & 1) * (3 * planeStride));
-        }
+        // ---- 0b. preconditioner blocks of the previous tile (its write-out ended at the block barrier) ----
+        if (precWarp) prec_pass (rowsDone);
+        rowsDone = nbRows;
 
         // ---- 1. job phase: one lane per mesh edge ----------------------------------------------
-        ring_mbar_wait (tailFull + (k & 1), (unsigned)(k >> 1) & 1u);
+        ring_mbar_wait (tailFull, k & 1);
         for (int b = warp; b < nbBatches; b += nWarps) {
             const RingBatch rb = batches[b];
             const uint64_t job = jobs[b * 32 + lane];
@@ -284,30 +308,30 @@ ring_assembly_kernel (const RingArgs args)
                 }
                 // two steps per trip, u and w changing roles: no register copies between steps
                 double w[3];
-                auto load_node = [&] (int s, double v[3]) {
-                    if ((s & 7) == 0) word = cw[(s >> 3) * 32]; else word >>= 8;
+                auto load_node = [&] (int k, double v[3]) {
+                    if ((k & 7) == 0) word = cw[(k >> 3) * 32]; else word >>= 8;
                     const int id = (int)(word & 0xFF);
                     v[0] = sX[id] - xi[0]; v[1] = sY[id] - xi[1]; v[2] = sZ[id] - xi[2];
                 };
-                int s = 1;
-                for (; s + 1 < nbSteps; s += 2) {
-                    load_node (s, w);
-                    ring_accumulate<OPDIM> (d, u, w, acc, s < len);
-                    load_node (s + 1, u);
-                    ring_accumulate<OPDIM> (d, w, u, acc, s + 1 < len);
+                int k = 1;
+                for (; k + 1 < nbSteps; k += 2) {
+                    load_node (k, w);
+                    ring_accumulate<OPDIM> (d, u, w, acc, k < len);
+                    load_node (k + 1, u);
+                    ring_accumulate<OPDIM> (d, w, u, acc, k + 1 < len);
                 }
-                if (s < nbSteps) {
-                    load_node (s, w);
-                    ring_accumulate<OPDIM> (d, u, w, acc, s < len);
+                if (k < nbSteps) {
+                    load_node (k, w);
+                    ring_accumulate<OPDIM> (d, u, w, acc, k < len);
                 }
             }
             else {
                 // general batch: chains separated by breaks
                 bool have = false;
-                for (int s = 0; s < nbSteps; s++) {
-                    if ((s & 7) == 0) word = cw[(s >> 3) * 32]; else word >>= 8;
+                for (int k = 0; k < nbSteps; k++) {
+                    if ((k & 7) == 0) word = cw[(k >> 3) * 32]; else word >>= 8;
                     const int id = (int)(word & 0xFF);
-                    if (s >= len) continue;
+                    if (k >= len) continue;
                     if (id == kRingBreak) { have = false; continue; }
                     const double w[3] = {sX[id] - xi[0], sY[id] - xi[1], sZ[id] - xi[2]};
                     if (have) ring_accumulate<OPDIM> (d, u, w, acc);
@@ -323,35 +347,36 @@ ring_assembly_kernel (const RingArgs args)
                 else {
                     double blk[9];
                     ring_block (acc, blk);
-                    double *dst = slab + sIJ * 9;
-                    #pragma unroll
-                    for (int q = 0; q < 9; q++) dst[q] = blk[q];
+                    double2 *dst = reinterpret_cast<double2*> (slab + sIJ * SLAB);
+                    dst[0] = make_double2 (blk[0], blk[1]); dst[1] = make_double2 (blk[2], blk[3]);
+                    dst[2] = make_double2 (blk[4], blk[5]); dst[3] = make_double2 (blk[6], blk[7]);
+                    slab[sIJ * SLAB + 8] = blk[8];
                     if (sJI != 0xFFFF) {                    // K_ji = K_ij^T
-                        double *dstT = slab + sJI * 9;
-                        #pragma unroll
-                        for (int q = 0; q < 9; q++) dstT[ring_transposed (q)] = blk[q];
+                        double2 *dstT = reinterpret_cast<double2*> (slab + sJI * SLAB);
+                        dstT[0] = make_double2 (blk[0], blk[3]); dstT[1] = make_double2 (blk[6], blk[1]);
+                        dstT[2] = make_double2 (blk[4], blk[7]); dstT[3] = make_double2 (blk[2], blk[5]);
+                        slab[sJI * SLAB + 8] = blk[8];
                     }
                 }
             }
         }
-        if (OPDIM == 9) ring_fence_async ();   // this thread's slab stores, for the bulk stores of the write-out
-        ring_cp_async_wait_all ();             // this thread's share of the next tile's coordinates is in
-        ring_bulk_wait_read ();                // this thread's bulk stores of the previous tile have read the other slab
-        __syncthreads ();      // the slab is complete; tail and coordinates of this tile are dead; the other slab is free
+        __syncthreads ();      // the slab is complete; tail and coordinates of this tile are dead
 
-        // ---- 2. the tail two tiles ahead and the head three tiles ahead start travelling (TMA) ---------
-        if (tid == 0) {
-            if (k + 2 < nbMine) { wait_head (k + 2); fetch_tail (k + 2); }     // into the buffer of this tile's tail
-            if (k + 3 < nbMine) {
-                fetch_head (offAhead, k + 3);            // buffer of tile k - 1, whose write-out ended before the barrier
-                if (k + 4 < nbMine) offAhead = P.tileOffset[firstTile + (k + 4) * tileStep];
-            }
+        // ---- 2. next tile's tail (TMA) and coordinates (plain loads) start travelling -------------
+        double nextCoord[3] = {0.0, 0.0, 0.0};
+        if (hasNext) {
+            const unsigned char *nextHead = sHead0 + ((k + 1) & 1) * headBytes;
+            ring_mbar_wait (headFull + ((k + 1) & 1), ((k + 1) >> 1) & 1);
+            if (tid == 0) fetch_tail (offNext, nextHead);
+            load_coords (nextHead, nextCoord);               // stored at the end of the write-out
         }
 
         // ---- 3. write-out: the diagonal entry of a row is minus the sum of the row's run ------------
         if (OPDIM == 1) {
             // Laplacian: one lane per row walks its entries (rows are short and the whole matrix is an eighth of
-            // the elasticity one: 8-byte stores to 32 different rows per instruction are affordable).
+            // the elasticity one: 8-byte stores to 32 different rows per instruction are affordable; the four
+            // entries of a sector come from the same lane in consecutive trips).  Row starts 1 (mod 8) slots
+            // apart keep the slab reads of a half-warp in different banks.
             for (int r = warp * 32 + lane; r < nbRows; r += nWarps * 32) {
                 const RingRow rr = sRows[r];
                 const int len = rr.len, diagOff = rr.diagOff;         // 0xFFFF never equals a position
@@ -363,89 +388,40 @@ ring_assembly_kernel (const RingArgs args)
                 }
                 const double diag = 0.0 - a;
                 if (diagOff != 0xFFFF) out[diagOff] = diag;
-                if (args.fusePrec) args.prec[rr.node & kRingNodeMask] = rr.node < 0 ? diag : 1.0 / diag;
+                sDiag[r] = diag;
+                sMeta[r] = rr.node | (diagOff != 0xFFFF ? (1 << 27) : 0);
             }
         }
         else {
-            // Elasticity: three consecutive rows per warp side by side, nine lanes each (lanes 0..26); a lane
-            // walks the entries of its row and sums its component, so the row sum needs no exchange between
-            // lanes.  Lanes 27..29 issue the bulk stores of the three rows.
-            const bool worker = lane < 27;
-            const int grp = worker ? lane / 9 : lane - 27;            // row of the group this lane works for (3, 4: none)
-            const int comp = worker ? lane - 9 * grp : 0;
-            const int ca = comp / 3, cb = comp - 3 * ca;              // component (ca, cb) of the 3x3 block
-            const int base = worker ? 9 * grp : lane;                 // first lane of the row's nine; idle lanes read themselves
-            for (int r0 = warp * kRingStoreGroup; r0 < nbRows; r0 += nWarps * kRingStoreGroup) {
+            // Elasticity: three consecutive rows per warp side by side, ten lanes each (nine components and an
+            // idle lane); a lane walks the entries of its row, so the row sum needs no exchange between lanes.
+            // The slab starts of consecutive rows are 1 (mod 8) slots apart (ring_row_padding): the three
+            // 72-byte pieces read in one instruction fall into disjoint banks.
+            const int grp = lane / 10, comp = lane - 10 * grp;        // lanes 9, 19, 29, 30, 31 idle
+            for (int r0 = warp * 3; r0 < nbRows; r0 += nWarps * 3) {
                 const int r = r0 + grp;
-                const bool rowOk = grp < kRingStoreGroup && r < nbRows;
-                int4 rw = make_int4 (0, 0, 0, 0xFFFF);                // node, valueStart, localStart | len << 16, diagOff | segEntries << 16
-                if (rowOk) rw = *reinterpret_cast<const int4*> (sRows + r);
-                const int node = rw.x, len = (int)((unsigned)rw.z >> 16), diagOff = rw.w & 0xFFFF;
-                double *row = slab + (unsigned)(rw.z & 0xFFFF) * 9u;
-                double diag = 0.0;
-                if (worker) {
-                    double *sp = row + comp;
-                    if (diagOff != 0xFFFF) sp[diagOff * 9] = 0.0;     // no job writes the diagonal slot: summed as a zero
+                if (grp < 3 && comp < 9 && r < nbRows) {
+                    const RingRow rr = sRows[r];
+                    const int len = rr.len, diagOff = rr.diagOff;     // 0xFFFF never equals a position
+                    const double *sp = slab + (size_t)rr.localStart * SLAB + comp;
+                    double *out = args.values + (size_t)rr.valueStart * 9 + comp, *op = out;
                     double a = 0.0;
-                    #pragma unroll 4
-                    for (int q = 0; q < len; q++) a += sp[q * 9];
-                    diag = 0.0 - a;
-                    if (diagOff != 0xFFFF) sp[diagOff * 9] = diag;
-                }
-                if (args.fusePrec) {
-                    // prec_init + prec_inversion (src/preconditioner.cc:25-87, src/Fortran/elasclpr.f:19-53) by the nine
-                    // lanes that hold the block: Dirichlet rows / columns to identity, then cofactor / determinant
-                    const bool masked = ((node >> (28 + ca)) | (node >> (28 + cb))) & 1;
-                    const double m = masked ? (ca == cb ? 1.0 : 0.0) : diag;
-                    const double x1 = __shfl_sync (0xffffffffu, m, base + adj_src (cb + 1, ca + 1));
-                    const double x2 = __shfl_sync (0xffffffffu, m, base + adj_src (cb + 2, ca + 2));
-                    const double x3 = __shfl_sync (0xffffffffu, m, base + adj_src (cb + 1, ca + 2));
-                    const double x4 = __shfl_sync (0xffffffffu, m, base + adj_src (cb + 2, ca + 1));
-                    const double m0 = __shfl_sync (0xffffffffu, m, base + ca);      // M(0, ca), used where cb == 0
-                    const double t = x3 * x4;
-                    const double cof = fma (x1, x2, -t);
-                    const double p = m0 * cof;
-                    const double p0 = __shfl_sync (0xffffffffu, p, base);
-                    const double p1 = __shfl_sync (0xffffffffu, p, base + 3);
-                    const double p2 = __shfl_sync (0xffffffffu, p, base + 6);
-                    const double det = (p0 + p1) + p2;
-                    const bool isInterface = node < 0;
-                    const bool invert = worker && rowOk && !isInterface && diagOff != 0xFFFF;
-                    const bool regular = fabs (det) > 0.0 && fabs (det) < 1.0e300;
-                    double out = isInterface ? diag : m;
-                    if (invert && regular) out = cof * ring_rcp (det);
-                    if (__any_sync (0xffffffffu, invert && !regular)) {
-                        // a singular or non-finite block: the infinities and NaNs of LAPACK's LU, not of the cofactors
-                        double blk[9];
-                        #pragma unroll
-                        for (int q = 0; q < 9; q++) blk[q] = __shfl_sync (0xffffffffu, m, base + q);
-                        if (invert && !regular) {
-                            invert3_lu (blk);
-                            #pragma unroll
-                            for (int q = 0; q < 9; q++) if (q == comp) out = blk[q];
-                        }
+                    for (int q = 0; q < len; q++, sp += SLAB, op += 9) {
+                        if (q != diagOff) { const double v = *sp; a += v; *op = v; }
                     }
-                    if (worker && rowOk) args.prec[(size_t)(node & kRingNodeMask) * 9 + comp] = out;
+                    const double diag = 0.0 - a;
+                    if (diagOff != 0xFFFF) out[diagOff * 9] = diag;
+                    sDiag[r * 9 + comp] = diag;
+                    if (comp == 0) sMeta[r] = rr.node | (diagOff != 0xFFFF ? (1 << 27) : 0);
                 }
-                ring_fence_async ();           // the diagonal blocks, for the async proxy
-                __syncwarp ();
-                const unsigned seg = (unsigned)rw.w >> 16;
-                if (!worker && seg) {
-                    // one run of rows, consecutive in the matrix and in the slab: 8-byte pieces at the ends where
-                    // the run does not start / end on a 16-byte boundary, one bulk store in between
-                    double *g = args.values + (size_t)rw.y * 9;
-                    const double *s = row;
-                    unsigned n = seg * 9u;
-                    if (rw.y & 1) { *g = *s; g++; s++; n--; }
-                    if (n & 1) { g[n - 1] = s[n - 1]; n--; }
-                    if (n) ring_bulk_store (g, s, n * (unsigned)sizeof (double));
-                }
-                ring_bulk_commit ();
             }
         }
-        // no barrier: the next tile's jobs fill the other slab
+
+        offCur = offNext; offNext = offAfter;
+        if (hasNext) store_coords (sHead0 + ((k + 1) & 1) * headBytes, nextCoord);   // this tile's jobs, the planes' readers, are behind the barrier
+        __syncthreads ();           // every reader of this tile's slab / head is done; sDiag / sMeta and the next coordinates are complete
     }
-    ring_bulk_wait_all ();      // shared memory must outlive the bulk stores
+    if (precWarp) prec_pass (rowsDone);     // the CTA's last tile
 }
 
 #ifndef MFB_RING_HOST_EMULATION
@@ -493,7 +469,8 @@ cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTi
     if (nbTiles <= 0) return cudaSuccess;
     RingArgs args;
     args.plan = plan; args.smem = ring_smem_layout (operatorID, plan);
-    args.coord = coord; args.values = values; args.prec = prec; args.fusePrec = fusePrec;
+    args.coord = coord; args.values = values; args.prec = prec;
+    args.fusePrec = fusePrec;
     args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
     const int grid = std::max (1, std::min (ctas, nbTiles));
     if (threads == 384) {

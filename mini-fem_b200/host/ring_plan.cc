@@ -24,7 +24,6 @@ struct RingJob {
 
 // Everything one thread needs to plan one tile; vectors are reused from tile to tile.
 struct TileWork {
-    std::vector<int> rowOrder;        // owned rows in increasing node id
     std::vector<int> nodes;           // global ids, owned rows first
     std::vector<RingRow> rows;
     std::vector<RingJob> jobs;
@@ -155,18 +154,13 @@ struct HalfWarpBanks {
 };
 
 // Plans one tile.  Global -> tile maps are thread-private dense arrays, reset on exit.
-void plan_tile (int nbRows, const int *rowNodesIn, const int *elemToNode, const int *row, const int *col,
+void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const int *row, const int *col,
                 const int *n2eIndex, const int *n2eValue, const uint8_t *isInterface, const int *checkBounds, int nbNodes,
                 const RingPlanLimits &lim,
                 std::vector<int> &nodeLocal, std::vector<int> &colStamp, TileWork &w, TileResult &out)
 {
     w.clear ();
     out = TileResult ();
-    // rows in increasing node id: rows that are consecutive in the matrix become neighbours in the slab and
-    // leave in one bulk store
-    w.rowOrder.assign (rowNodesIn, rowNodesIn + nbRows);
-    std::sort (w.rowOrder.begin (), w.rowOrder.end ());
-    const int *rowNodes = w.rowOrder.data ();
     // ---- nodes: owned rows first, then every node of an element that touches an owned row ----
     for (int r = 0; r < nbRows; r++) { nodeLocal[rowNodes[r]] = r; w.nodes.push_back (rowNodes[r]); }
     for (int r = 0; r < nbRows; r++) {
@@ -184,8 +178,8 @@ void plan_tile (int nbRows, const int *rowNodesIn, const int *elemToNode, const 
     if ((int)w.nodes.size () > kRingMaxNodes) out.bad = 3;
     if (out.bad) { release (); return; }
 
-    // ---- row table: the slab is an image of the rows as they lie in the matrix ---------------------
-    int localStart = 0, segHead = -1;
+    // ---- row table ------------------------------------------------------------------------
+    int localStart = 0;
     for (int r = 0; r < nbRows; r++) {
         const int n = rowNodes[r], begin = row[n], end = row[n + 1];
         RingRow rr;
@@ -197,19 +191,12 @@ void plan_tile (int nbRows, const int *rowNodesIn, const int *elemToNode, const 
             for (int c = 0; c < 3; c++) if (checkBounds[(size_t)c * nbNodes + n] != 0) rr.node |= 1 << (28 + c);
         }
         rr.valueStart = begin;
-        // a row that follows its predecessor in the matrix follows it in the slab (the parities agree) and,
-        // inside a group of rows the write-out handles together, extends its store segment
-        const bool follows = r > 0 && begin == w.rows[r - 1].valueStart + w.rows[r - 1].len;
-        localStart = ring_row_start (localStart, begin);
         rr.localStart = (uint16_t)localStart;
         rr.len = (uint16_t)(end - begin);
         rr.diagOff = 0xFFFF;
         for (int l = begin; l < end; l++) if (col[l] == n + 1) { rr.diagOff = (uint16_t)(l - begin); break; }
-        if (follows && r % kRingStoreGroup != 0 && segHead >= 0) w.rows[segHead].segEntries = (uint16_t)(w.rows[segHead].segEntries + rr.len);
-        else if (rr.len > 0) { segHead = r; rr.segEntries = rr.len; }
-        else segHead = -1;
         w.rows.push_back (rr);
-        localStart += end - begin;
+        localStart += (end - begin) + ring_row_padding (end - begin);
     }
     out.nbRows = nbRows;
     out.nbEntries = localStart;
@@ -286,32 +273,31 @@ void plan_tile (int nbRows, const int *rowNodesIn, const int *elemToNode, const 
     // slab banks — fewer slab conflicts, but more gather conflicts than they save.)
     std::stable_sort (w.order.begin (), w.order.end (), [&] (int a, int b) { return w.jobs[a].codeLen > w.jobs[b].codeLen; });
     while (w.order.size () % 32) w.order.push_back (-1);
-    if (lim.bankAware && lim.slabSplit) {
-        // The 32 jobs of a batch are dealt to its two half-warps so that the slab slots a half-warp stores to
-        // differ mod 16 as far as possible (nine 64-bit stores per block: a collision costs nine wavefronts);
-        // inside a half the jobs keep their order.
-        for (size_t b0 = 0; b0 < w.order.size (); b0 += 32) {
-            int group[2][16], count[2] = {0, 0};
-            unsigned loadIJ[2][16] = {{0}}, loadJI[2][16] = {{0}};
-            for (int l = 0; l < 32; l++) {
-                const int k = w.order[b0 + l];
+    if (lim.bankAware) {
+        // Lane order inside a half-warp is free as far as the gather goes (its conflicts depend on which
+        // jobs share the half-warp, not on their lanes), so use it for the slab: split the 16 jobs into
+        // the two quarter-warps so that the slots a quarter stores to differ mod 8 as far as possible.
+        for (size_t h0 = 0; h0 < w.order.size (); h0 += 16) {
+            int group[2][8], count[2] = {0, 0};
+            unsigned loadIJ[2][8] = {{0}}, loadJI[2][8] = {{0}};
+            for (int l = 0; l < 16; l++) {
+                const int k = w.order[h0 + l];
                 int best = count[0] <= count[1] ? 0 : 1;
                 if (k >= 0) {
                     const RingJob &jb = w.jobs[k];
                     long bestCost = 1l << 60;
                     for (int q = 0; q < 2; q++) {
-                        if (count[q] >= 16) continue;
-                        // stay with the half that the plain order would give unless a collision is at stake
-                        long cost = 64l * loadIJ[q][jb.slotIJ & 15] + (jb.slotJI != 0xFFFF ? 64l * loadJI[q][jb.slotJI & 15] : 0) + (q != l / 16 ? 1 : 0);
+                        if (count[q] >= 8) continue;
+                        long cost = 16l * loadIJ[q][jb.slotIJ & 7] + (jb.slotJI != 0xFFFF ? 16l * loadJI[q][jb.slotJI & 7] : 0) + count[q];
                         if (cost < bestCost) { bestCost = cost; best = q; }
                     }
-                    loadIJ[best][jb.slotIJ & 15]++;
-                    if (jb.slotJI != 0xFFFF) loadJI[best][jb.slotJI & 15]++;
+                    loadIJ[best][jb.slotIJ & 7]++;
+                    if (jb.slotJI != 0xFFFF) loadJI[best][jb.slotJI & 7]++;
                 }
-                else if (count[best] >= 16) best ^= 1;
+                else if (count[best] >= 8) best ^= 1;
                 group[best][count[best]++] = k;
             }
-            for (int q = 0; q < 2; q++) for (int l = 0; l < 16; l++) w.order[b0 + (size_t)q * 16 + l] = group[q][l];
+            for (int q = 0; q < 2; q++) for (int l = 0; l < 8; l++) w.order[h0 + (size_t)q * 8 + l] = group[q][l];
         }
     }
     const int nbBatches = (int)w.order.size () / 32;
@@ -386,9 +372,9 @@ void plan_tile (int nbRows, const int *rowNodesIn, const int *elemToNode, const 
         for (int h = 0; h < nbHalf; h++) {
             const int nbSteps = w.batches[h / 2].nbSteps;
             banks.reset (nbSteps + 2);
-            // slab stores are 64-bit, one per block component, entry stride 72 bytes: within a half-warp two lanes
-            // collide when their slots agree mod 16
-            unsigned loadIJ[16] = {0}, loadJI[16] = {0};
+            // slab stores are 128-bit (entry stride 80 bytes): a quarter-warp of 8 lanes per wavefront,
+            // conflict-free when its slots differ mod 8
+            unsigned loadIJ[2][8] = {{0}}, loadJI[2][8] = {{0}};
             auto choose = [&] (RingJob &jb) {      // best start / direction of the job's ring against the banks taken so far
                 uint8_t *codes = w.codes.data () + jb.codeStart;
                 const int len = jb.codeLen;
@@ -438,8 +424,8 @@ void plan_tile (int nbRows, const int *rowNodesIn, const int *elemToNode, const 
                 banks.add (0, w.newId[jb.i]);
                 banks.add (1, w.newId[jb.j]);
                 place (jb, true);
-                loadIJ[jb.slotIJ & 15]++;
-                if (jb.slotJI != 0xFFFF) loadJI[jb.slotJI & 15]++;
+                loadIJ[l >> 3][jb.slotIJ & 7]++;
+                if (jb.slotJI != 0xFFFF) loadJI[l >> 3][jb.slotJI & 7]++;
             }
             // coordinate descent: every lane in turn is taken out and re-placed against all the others
             for (int sweep = 0; sweep < (lim.bankAware ? lim.rotationSweeps : 0); sweep++) {
@@ -458,10 +444,12 @@ void plan_tile (int nbRows, const int *rowNodesIn, const int *elemToNode, const 
                 out.gatherWf += 3 * wf;
                 out.gatherIdeal += 3 * (wf > 0);
             }
-            unsigned mIJ = 0, mJI = 0;
-            for (int c = 0; c < 16; c++) { mIJ = std::max (mIJ, loadIJ[c]); mJI = std::max (mJI, loadJI[c]); }
-            out.slabWf += mIJ + mJI;
-            out.slabIdeal += (mIJ ? 1 : 0) + (mJI ? 1 : 0);
+            for (int quarter = 0; quarter < 2; quarter++) {
+                unsigned mIJ = 0, mJI = 0;
+                for (int c = 0; c < 8; c++) { mIJ = std::max (mIJ, loadIJ[quarter][c]); mJI = std::max (mJI, loadJI[quarter][c]); }
+                out.slabWf += mIJ + mJI;
+                out.slabIdeal += (mIJ ? 1 : 0) + (mJI ? 1 : 0);
+            }
         }
     };
     // With the rotations fixed, the loads that really meet in one half-warp step are known: move
@@ -651,7 +639,7 @@ int cut_node_tiles_rcb (int nbNodes, const int *elemToNode, const int *row, cons
                 }
             }
             addRefs += (int)fresh.size ();
-            const int slots = ring_row_start (entries, row[n]) - entries + rowLen;      // the slab keeps the idle slots too
+            const int slots = rowLen + ring_row_padding (rowLen);      // the slab keeps the padding too
             // an edge to a row the tile already owns is that row's job (it gains the transposed block)
             int addJobs = 0;
             for (int l = row[n]; l < row[n + 1]; l++) addJobs += (col[l] - 1 != n && ownedStamp[col[l] - 1] != stamp);
@@ -697,7 +685,7 @@ int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         error = "ring plan limits out of range";
         return -1;
     }
-    if (nbNodes > kRingMaxNodeId) { error = "more than 2^28 nodes in one subdomain (the row tags keep four flag bits)"; return -1; }
+    if (nbNodes > kRingMaxNodeId) { error = "more than 2^27 nodes in one subdomain (the row tags keep five flag bits)"; return -1; }
     std::vector<int> n2eIndex ((size_t)nbNodes + 1), n2eValue ((size_t)nbElem * kDimElem);
     node_to_elem (elemToNode, nbElem, nbNodes, n2eIndex.data (), n2eValue.data ());
     std::vector<int> nodeOrder, tileStart;
@@ -753,7 +741,6 @@ int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
     for (int k = 0; k < nbTiles; k++) {
         TileResult &r = results[execOrder[k]];
         memcpy (plan.blob.data () + plan.tileOffset[k], r.blob.data (), r.blob.size ());
-        reinterpret_cast<RingTileHeader*> (plan.blob.data () + plan.tileOffset[k])->selfOffset = plan.tileOffset[k];
         std::vector<uint8_t> ().swap (r.blob);
     }
     return 0;
@@ -773,7 +760,6 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
     for (int t = 0; t < plan.nbTiles; t++) {
         const uint8_t *base = plan.blob.data () + plan.tileOffset[t];
         const RingTileHeader &h = *plan.header (t);
-        if (h.selfOffset != plan.tileOffset[t]) { error = "selfOffset"; return -1; }
         if (h.blobBytes != plan.tileOffset[t + 1] - plan.tileOffset[t] || (plan.tileOffset[t] & 15) || (h.headBytes & 15) ||
             (h.offJobs & 15) || (h.offCodes & 15) || (h.blobBytes & 15)) { error = "record size / alignment"; return -1; }
         if (h.hasInterface && interiorSeen) { error = "interface tiles must come first"; return -1; }
@@ -789,35 +775,22 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
         for (int q = 0; q < h.nbNodes; q++) if (tileNodes[q] < 0 || tileNodes[q] >= nbNodes) { error = "node list out of range"; return -1; }
         // slab slot -> global CSR entry
         std::vector<int> slotEntry ((size_t)h.nbEntries, -1);
-        int expectStart = 0, segLeft = 0;
+        int expectStart = 0;
         for (int r = 0; r < h.nbRows; r++) {
             const RingRow &rr = rows[r];
             const int n = rr.node & kRingNodeMask;
             if (n < 0 || n >= nbNodes || rowSeen[n]) { error = "row owned twice or out of range"; return -1; }
-            rowSeen[n] = 1;
-            rowsTotal++;
-            expectStart = ring_row_start (expectStart, row[n]);
-            if (rr.valueStart != row[n] || rr.len != row[n + 1] - row[n] || rr.localStart != expectStart) { error = "row table differs from nodeToNodeRow"; return -1; }
-            if (((rr.localStart ^ rr.valueStart) & 1) != 0) { error = "slab slot and CSR entry of a row differ in parity"; return -1; }
+            if (rr.node & (1 << 27)) { error = "bit 27 of a row tag must be clear"; return -1; }
             if (checkBounds) {
                 for (int c = 0; c < 3; c++) {
                     if (((rr.node >> (28 + c)) & 1) != (checkBounds[(size_t)c * nbNodes + n] != 0)) { error = "Dirichlet mask bits differ from checkBounds"; return -1; }
                 }
             }
-            // store segments: runs of rows of one group, consecutive in the matrix and in the slab
-            if (rr.segEntries) {
-                if (segLeft != 0) { error = "store segment starts inside another"; return -1; }
-                if (rr.segEntries < rr.len) { error = "store segment shorter than its first row"; return -1; }
-                segLeft = rr.segEntries - rr.len;
-            }
-            else {
-                if (rr.len > segLeft) { error = "row outside any store segment"; return -1; }
-                if (rr.len > 0 && (r % kRingStoreGroup == 0 || rr.valueStart != rows[r - 1].valueStart + rows[r - 1].len ||
-                                   rr.localStart != rows[r - 1].localStart + rows[r - 1].len)) { error = "store segment is not contiguous / crosses a row group"; return -1; }
-                segLeft -= rr.len;
-            }
+            rowSeen[n] = 1;
+            rowsTotal++;
+            if (rr.valueStart != row[n] || rr.len != row[n + 1] - row[n] || rr.localStart != expectStart) { error = "row table differs from nodeToNodeRow"; return -1; }
             for (int l = 0; l < rr.len; l++) slotEntry[(size_t)expectStart + l] = rr.valueStart + l;
-            expectStart += rr.len;
+            expectStart += rr.len + ring_row_padding (rr.len);
             if (expectStart > h.nbEntries) { error = "rows exceed the slab"; return -1; }
             int diag = 0xFFFF;
             for (int l = 0; l < rr.len; l++) if (col[rr.valueStart + l] == n + 1) { diag = l; break; }
@@ -827,7 +800,6 @@ int verify_ring_plan (const RingPlan &plan, int nbNodes, int nbElem, const int *
                 entrySeen[(size_t)rr.valueStart + diag] = 1;
             }
         }
-        if (segLeft != 0) { error = "store segment runs past the last row"; return -1; }
         if (expectStart != h.nbEntries) { error = "entry count mismatch"; return -1; }
         for (int b = 0; b < h.nbBatches; b++) {
             const RingBatch &rb = batches[b];

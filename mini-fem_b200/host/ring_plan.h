@@ -18,13 +18,11 @@
 //   * when j is owned by the same tile the job also writes K_ji = K_ij^T: every interior edge
 //     is computed once;
 //   * jobs are independent of rows, so they are sorted by ring length and packed 32 to a warp;
-//   * finished blocks go to a tile-wide shared slab that is a byte-for-byte image of the tile's CSR rows
-//     (72-byte elasticity blocks, no padding inside a row).  The element matrices have zero row sums (the
-//     four gradients of an element add up to zero), hence K_ii = -sum_{j != i} K_ij: the write-out sums each
-//     row of the slab, puts the diagonal block into its slot, inverts it into the preconditioner on the spot,
-//     and hands the rows to the TMA unit, which copies them to global memory as bulk stores (one per run of
-//     rows that are consecutive in the matrix).  A row starts at a slab slot of the same parity as its first
-//     CSR entry, so that shared and global addresses agree modulo 16 bytes (bulk copies need both aligned).
+//   * finished blocks go to a tile-wide shared slab laid out like the tile's CSR rows; the
+//     write-out streams each row to global memory as one contiguous run and sums it on the way:
+//     the element matrices have zero row sums (the four gradients of an element add up to
+//     zero), hence K_ii = -sum_{j != i} K_ij — the diagonal entry and the preconditioner block
+//     come from the run that is being written anyway.
 //
 // Per tile the plan is one contiguous record: HEAD = header, row table, node list (needed one
 // tile ahead for the coordinate prefetch and during the write-out), TAIL = batches, jobs, ring
@@ -42,39 +40,37 @@ constexpr int kRingBreak = 0xFE;   // code byte: the chain of elements is interr
 constexpr int kRingBatchGeneral = 1; // RingBatch::flags: some job of the batch holds a break (the kernel's general loop)
 constexpr int kRingMaxNodes = 254; // tile-local node ids 0 .. 253
 
-struct RingTileHeader {            // 48 bytes
-    uint16_t nbRows, nbNodes, nbBatches, nbEntries, hasInterface, pad0;   // nbEntries = slab slots, idle ones included
+struct RingTileHeader {            // 32 bytes
+    uint16_t nbRows, nbNodes, nbBatches, nbEntries, hasInterface, pad0;   // nbEntries = slab slots, padding included
     uint32_t offNodes;             // int[nbNodes]: 0-based global ids by tile-local id (holes name a valid node)
     uint32_t headBytes;            // bytes [0, headBytes) = header + rows + nodes; the tail starts here with RingBatch[nbBatches]
     uint32_t offJobs;              // uint64[32 * nbBatches]
     uint32_t offCodes;             // uint64[]: per batch [word][32 lanes], 8 code bytes per word, low byte first;
                                    // a job's bytes beyond its length name a valid node (they are loaded and masked)
     uint32_t blobBytes;
-    uint64_t selfOffset;           // byte offset of this record in RingPlan::blob (the kernel fetches the tail from the head)
-    uint64_t pad1;
 };
 
-// RingRow::node: 0-based global node id in the low 28 bits; bits 28..30 = Dirichlet mask of the components x, y, z
-// (checkBounds[c * nbNodes + node] != 0: src/Fortran/e_cgmelissa.F, applied by ela_invert_prec,
-// src/Fortran/elasclpr.f:19-27); bit 31 = interface node (its block leaves the fused kernel raw, for the halo sum).
-constexpr int kRingNodeMask = 0x0FFFFFFF;
+// RingRow::node: 0-based global node id in the low 27 bits; bit 27 is free for the kernel (it tags rows that
+// hold a diagonal entry); bits 28..30 = Dirichlet mask of the components x, y, z (checkBounds[c * nbNodes + node]
+// != 0: src/Fortran/e_cgmelissa.F, applied by ela_invert_prec, src/Fortran/elasclpr.f:19-27); bit 31 = interface
+// node (its block leaves the fused kernel raw, for the halo sum).
+constexpr int kRingNodeMask = 0x07FFFFFF;
 constexpr int kRingMaxNodeId = kRingNodeMask;
-constexpr int kRingStoreGroup = 3;   // rows the write-out handles side by side; a store segment never crosses a group
 
 struct RingRow {                   // 16 bytes per owned row, right after the header
     int node;                      // see above
     int valueStart;                // nodeToNodeRow[node]
-    uint16_t localStart;           // slab slot (entry units) of the row's first entry: ring_row_start ()
+    uint16_t localStart;           // slab slot of the row's first entry; consecutive rows start 1 (mod 8) slots apart
+                                   // (ring_row_padding), so that three rows can stream out side by side
     uint16_t len;                  // entries of the row
     uint16_t diagOff;              // position of the diagonal entry inside the row, 0xFFFF = none
-    uint16_t segEntries;           // > 0: this row starts a store segment of that many entries — this row and the
-                                   // following rows of its group of kRingStoreGroup, consecutive in the matrix and
-                                   // therefore in the slab; 0: the row belongs to the segment of an earlier row
+    uint16_t pad0;
 };
 
-// Slab slot of a row whose first CSR entry is `valueStart`, given the first free slot: the same parity as
-// valueStart (one idle slot at most).  A row that follows its predecessor in the matrix follows it in the slab.
-inline int ring_row_start (int firstFree, int valueStart) { return firstFree + ((firstFree ^ valueStart) & 1); }
+// Idle slab slots after a row of `len` entries: the next row starts at a slot = 1 (mod 8) past this row's
+// start.  The write-out lets three groups of ten lanes copy three consecutive rows at once, entry q of each
+// in the same instruction; with 80-byte slab entries the three 72-byte pieces then fall into disjoint banks.
+inline int ring_row_padding (int len) { return ((1 - len) % 8 + 8) % 8; }
 
 struct RingBatch {                 // 8 bytes per warp batch of 32 jobs
     uint32_t codeBase;             // first code word of the batch (index into the codes section)
@@ -93,13 +89,12 @@ inline uint64_t ring_job (int i, int j, int slotIJ, int slotJI, int len)
 
 struct RingPlanLimits {
     int maxRows = 36;              // rows per tile (<= 255)
-    int maxEntries = 640;          // slab slots per tile: CSR entries plus the idle slots between rows (with the Morton
-                                   // cut the cap applies to the entries alone)
+    int maxEntries = 640;          // slab slots per tile: CSR entries plus the padding between rows (with the Morton
+                                   // cut the cap applies to the entries alone); 640 x 80 bytes keeps three CTAs per SM
     int maxNodes = kRingMaxNodes;  // tile-local nodes (<= 254: one code byte per node)
     int maxJobs = 1 << 30;         // jobs (mesh edges with an owned end) per tile: a multiple of 32 x the CTA's warps lets the
-                                   // job phase finish in whole rounds of warp batches (no warp idles at the block barrier)
+                                   // job phase finish in whole rounds of warp batches
     bool bankAware = true;         // node numbering + ring rotation chosen against bank conflicts
-    bool slabSplit = true;         // deal the jobs of a batch to its half-warps against bank conflicts of the slab stores
     int rotationSweeps = 1;        // coordinate-descent sweeps over the lanes of a half-warp after the greedy rotation choice
     bool bisection = true;         // tiles = leaves of a recursive coordinate bisection (false: runs of the Morton curve, as TILED)
     int refinePasses = 1;          // renumber-and-rotate rounds after the first numbering.  Modelled gather conflict
@@ -113,8 +108,8 @@ struct RingPlan {
     uint32_t maxBlobBytes = 0, maxHeadBytes = 0, maxTailBytes = 0;
     int64_t nbJobs = 0, nbSymmetricJobs = 0, nbRingSteps = 0, nbPaddedSteps = 0, nbBreaks = 0;
     // shared-memory model, in wavefronts of 128 bytes.  gather: the LDS.64 of the coordinate planes, one
-    // wavefront per half-warp and plane without conflicts.  slab: per half-warp and per 64-bit store of a
-    // finished block (an elasticity block = 9 such stores; two lanes collide when their slots agree mod 16)
+    // wavefront per half-warp and plane without conflicts.  slab: per quarter-warp (8 lanes) and per 128-bit
+    // store of a finished block (an elasticity block = 4 such stores + one 64-bit one)
     int64_t gatherWavefronts = 0, gatherIdeal = 0, slabWriteWavefronts = 0, slabWriteIdeal = 0;
     std::vector<uint64_t> tileOffset;   // nbTiles + 1 byte offsets into `blob`
     std::vector<uint8_t> blob;

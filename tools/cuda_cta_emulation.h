@@ -3,7 +3,7 @@
 // protocol of csrc/kernels_ring.cu can be checked without a GPU (tools/ring_kernel_host.cc).
 // What it emulates: threadIdx / blockIdx / blockDim / gridDim, dynamic shared memory,
 // __syncthreads / __syncwarp (real barriers), warp shuffles (exchange through a per-warp buffer
-// between two warp barriers), mbarriers with transaction counts, TMA bulk copies (loads and stores) and cp.async.
+// between two warp barriers), mbarriers with transaction counts, TMA bulk copies and cp.async.
 // The asynchronous copies are performed AT ISSUE — the earliest moment the hardware could touch
 // the destination — so a reader that has not been ordered before the issue shows up as a data
 // race, and a reader that does not wait for the mbarrier / the block barrier is unordered with the
@@ -80,24 +80,6 @@ inline void bulk_load (void *dst, const void *src, unsigned bytes, uint64_t *bar
     __atomic_store_n (bar, v - ((uint64_t)bytes << 32), __ATOMIC_RELEASE);
     mbar_complete_if_idle (bar);
 }
-// bulk copy shared -> global, performed at issue (the earliest moment the TMA unit could read the source)
-inline void bulk_store (void *dst, const void *src, unsigned bytes)
-{
-    if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15) || (bytes & 15)) { fprintf (stderr, "cta_emu: bulk store not 16-byte aligned\n"); abort (); }
-    memcpy (dst, src, bytes);
-}
-inline bool any_sync (bool pred)
-{
-    Cta &c = *tls.cta;
-    const int warp = (int)(tls.threadIdx.x >> 5), lane = (int)(tls.threadIdx.x & 31);
-    double *x = c.xchg.data () + (size_t)warp * 32;
-    x[lane] = pred ? 1.0 : 0.0;
-    pthread_barrier_wait (&c.warpBarrier[warp]);
-    bool r = false;
-    for (int l = 0; l < 32; l++) r = r || x[l] != 0.0;
-    pthread_barrier_wait (&c.warpBarrier[warp]);
-    return r;
-}
 inline void mbar_wait (uint64_t *bar, unsigned parity)          // returns once the phase of that parity has completed
 {
     for (long spin = 0; spin < (1l << 26); spin++) {
@@ -151,8 +133,6 @@ inline unsigned char *dynamic_smem ()          // 128-byte aligned like the kern
 #define __syncwarp() cta_emu::syncwarp ()
 #define __shfl_xor_sync(mask, v, off) cta_emu::shfl ((v), (int)(threadIdx.x & 31) ^ (off))
 #define __shfl_down_sync(mask, v, delta) cta_emu::shfl ((v), (int)(threadIdx.x & 31) + (delta))
-#define __shfl_sync(mask, v, src) cta_emu::shfl ((v), (src))
-#define __any_sync(mask, pred) cta_emu::any_sync (pred)
 #define __ldg(p) (*(p))
 #define __trap() abort ()
 using std::max;

@@ -30,7 +30,6 @@ int main (int argc, char **argv)
     if (getenv ("RING_NOBANK")) lim.bankAware = false;
     if (getenv ("RING_PASSES")) lim.refinePasses = atoi (getenv ("RING_PASSES"));
     if (getenv ("RING_SWEEPS")) lim.rotationSweeps = atoi (getenv ("RING_SWEEPS"));
-    if (getenv ("RING_NOSPLIT")) lim.slabSplit = false;
     if (getenv ("RING_MAXJOBS")) lim.maxJobs = atoi (getenv ("RING_MAXJOBS"));
     const int warps = getenv ("RING_WARPS") ? atoi (getenv ("RING_WARPS")) : 8;      // warps per CTA: rounds of the job phase / write-out
     RingPlan plan;
@@ -42,7 +41,7 @@ int main (int argc, char **argv)
     }
     const double seconds = std::chrono::duration<double> (std::chrono::steady_clock::now () - t0).count ();
     const double E = m.nbElem, Z = row[m.nbNodes];
-    const double gather = plan.gatherWavefronts / E, slabW = 9.0 * plan.slabWriteWavefronts / E;
+    const double gather = plan.gatherWavefronts / E, slabW = 4.5 * plan.slabWriteWavefronts / E;
     const double slabR = 2.0 * (Z - m.nbNodes) / 3.0 / E;             // 3 entries per warp iteration, 2 wavefronts
     const double misc = (plan.nbPaddedSteps / 32.0 / 7.0 * 4.0 + plan.nbTiles * 3.0 * plan.maxNodes * 8.0 / 128.0) / E;
     printf ("%s: E %d N %d Z %.0f | rows<=%d entries<=%d | build %.2f s | tiles %d | plan %.1f MB (%.1f B/elem)\n", what, m.nbElem, m.nbNodes, Z,

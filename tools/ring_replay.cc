@@ -24,7 +24,7 @@ static int replay (const RingPlan &plan, const double *coord, const int *checkBo
                    double *values, double *prec)
 {
     const double kNaN = std::numeric_limits<double>::quiet_NaN ();
-    constexpr int SLAB = OPDIM;                        // the slab is an image of the CSR rows: no padding inside an entry
+    constexpr int SLAB = OPDIM == 9 ? 10 : 1;          // doubles per slab entry, as in the kernel (ring_slab_stride)
     std::vector<double> X, Y, Z, slab, sDiag;
     for (int t = 0; t < plan.nbTiles; t++) {
         const uint8_t *base = plan.blob.data () + plan.tileOffset[t];
