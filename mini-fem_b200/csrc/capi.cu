@@ -360,7 +360,11 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
         isIntf.assign ((size_t)p->nbNodes, 0);
         for (int j = 0; j < p->nbIntfNodes; j++) isIntf[p->intfNodes[j] - 1] = 1;
     }
+    // two slabs per CTA: 30 rows / 510 slots keep two 384-thread CTAs per SM, 64 rows / 1100 slots fit the
+    // single 768-thread CTA
     RingPlanLimits lim;
+    lim.maxRows = c->threads == 768 ? 64 : 30;
+    lim.maxEntries = c->threads == 768 ? 1100 : 510;
     if (o && o->tileRows > 0) lim.maxRows = o->tileRows;
     if (o && o->tileElems > 0) lim.maxEntries = o->tileElems;          // RING: tileElems caps the slab slots of a tile
     lim.bankAware = !(o && o->bankAware < 0);
@@ -606,7 +610,8 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     if (c->path == MFB_PATH_RING) {          // a write-once path like TILED: same stages, same fused iteration
         c->ring = true;
         c->path = MFB_PATH_TILED;
-        if (c->threads != 256 && c->threads != 384) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 256 or 384 threads per CTA");
+        if (!(o && o->threads > 0)) c->threads = 384;
+        if (c->threads != 384 && c->threads != 768) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 384 (two CTAs per SM) or 768 (one) threads per CTA");
     }
     if (!c->ring && c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {
         return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256], or the pipelined kernel's CTA size");

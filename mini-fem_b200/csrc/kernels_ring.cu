@@ -40,8 +40,8 @@ static_assert (sizeof (RingTileHeader) == 32 && sizeof (RingRow) == 16 && sizeof
 // Byte offsets of the kernel's shared-memory sections, computed once on the host and passed as kernel
 // arguments (constant bank): the compiler otherwise rebuilds them from the plan maxima inside the loops.
 struct RingSmemLayout {
-    unsigned headBytes;          // size of one head buffer; head 0 at 0, head 1 at headBytes
-    unsigned tail, planes, slab, diag, meta, bars, total;
+    unsigned headBytes;          // size of one head buffer; head b at b * headBytes
+    unsigned tail, tailBytes, planes, slab, slabBytes, bars, total;
 };
 
 struct RingArgs {
@@ -61,11 +61,12 @@ __device__ __forceinline__ unsigned ring_record_head_bytes (uint64_t packed) { r
 #ifdef MFB_RING_HOST_EMULATION
 // tools/ring_kernel_host.cc compiles this file with g++ and runs the kernel below on host threads
 // (tools/cuda_cta_emulation.h): the PTX helpers become their emulated counterparts.
-inline void ring_mbar_init (uint64_t *bar, unsigned) { cta_emu::mbar_init (bar); }
+inline void ring_mbar_init (uint64_t *bar, unsigned count) { cta_emu::mbar_init (bar, count); }
 inline void ring_mbar_expect_tx (uint64_t *bar, unsigned bytes) { cta_emu::mbar_expect_tx (bar, bytes); }
-inline void ring_mbar_arrive (uint64_t *bar) { cta_emu::mbar_expect_tx (bar, 0); }
+inline void ring_mbar_arrive (uint64_t *bar) { cta_emu::mbar_arrive (bar); }
 inline void ring_mbar_wait (uint64_t *bar, unsigned parity) { cta_emu::mbar_wait (bar, parity); }
 inline void ring_bulk_load (void *dst, const void *src, unsigned bytes, uint64_t *bar) { cta_emu::bulk_load (dst, src, bytes, bar); }
+inline void ring_bar_sync (int id, int count) { cta_emu::bar_sync (id, count); }
 inline void ring_cp_async_f64 (double *dst, const double *src) { *dst = *src; }
 inline void ring_cp_async_wait_all () {}
 #else
@@ -91,13 +92,13 @@ __device__ __forceinline__ void ring_mbar_arrive (uint64_t *bar)
 __device__ __forceinline__ void ring_mbar_wait (uint64_t *bar, unsigned parity)
 {
     unsigned done = 0;
-    for (long spin = 0; spin < (1l << 22); spin++) {
+    for (long spin = 0; spin < (1l << 18); spin++) {
         asm volatile (
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(ring_smem_u32 (bar)), "r"(parity) : "memory");
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"     // suspended (no issue slots) until the phase
+            "selp.u32 %0, 1, 0, p;\n"                                          // completes or the hint (ns) runs out
+            "}\n" : "=r"(done) : "r"(ring_smem_u32 (bar)), "r"(parity), "r"(20000u) : "memory");
         if (done) return;
     }
     __trap ();
@@ -108,6 +109,12 @@ __device__ __forceinline__ void ring_bulk_load (void *dst, const void *src, unsi
 {
     asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                   :: "r"(ring_smem_u32 (dst)), "l"(src), "r"(bytes), "r"(ring_smem_u32 (bar)) : "memory");
+}
+
+// named barrier among `count` threads (the write-out warps)
+__device__ __forceinline__ void ring_bar_sync (int id, int count)
+{
+    asm volatile ("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
 }
 
 __device__ __forceinline__ void ring_cp_async_f64 (double *dst, const double *src)
@@ -126,20 +133,34 @@ constexpr int kRingPlane = 256;
 // doubles per slab entry: an elasticity block is padded to 80 bytes so that it is 16-byte aligned
 __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim == 9 ? 10 : 1; }
 
-// THREADS / MINB: 256 threads, three CTAs per SM (default) or 384 threads, two CTAs per SM (larger tiles:
-// mfb_options.threads = 384 with tileRows / tileElems raised, e.g. 54 / 960) — 24 warps per SM either way.
+// Warp-specialised kernel (round 2).  The ncu captures of the round-1 kernel (profiles/r2_ring_ela_*.txt) show
+// no pipe above 55 %: 19 % of the warp time is spent at the two block barriers of a tile, 11 % waiting for the
+// next tile's coordinates, and because all warps of a CTA are in the same phase the FP64 pipe idles during
+// every write-out and the load/store unit during every job phase; a second and a third CTA per SM recover
+// only part of it (0.81 / 0.54 / 0.46 ms with one / two / three CTAs per SM).  Here the two phases run side
+// by side, each on its own warps, decoupled by mbarriers and a double-buffered slab:
+//   * JOB warps (two thirds of the CTA) only walk rings: tile k's jobs fill slab k & 1; a job warp arrives
+//     on full[k & 1] after its last batch of the tile and goes on to tile k + 1 without waiting for anyone;
+//   * WRITE-OUT warps wait for full[k & 1], stream the tile's rows to global memory (row sums -> diagonal
+//     entry -> fused preconditioner block, as before) and arrive on ready[k & 1]; they also feed the job
+//     warps: at the start of tile k's write-out they request the tail (TMA) and load the coordinates of tile
+//     k + 2, whose buffers (those of tile k) the job warps have just released — a whole job phase ahead of
+//     their use — and the plan head of tile k + 3.
+// No block barrier after the prologue.  THREADS = 384: 7 job warps + 5 write-out warps (elasticity), two CTAs per SM.
+constexpr int kRingHeadBuffers = 4;
+
 inline RingSmemLayout ring_smem_layout (int operatorID, const DeviceRingPlan &plan)
 {
     const int opDim = operatorID == 0 ? 1 : 9;
     RingSmemLayout L;
     L.headBytes = ring_align128 (plan.maxHeadBytes);
-    L.tail = 2 * L.headBytes;
-    L.planes = L.tail + ring_align128 (plan.maxTailBytes);
-    L.slab = L.planes + 3 * kRingPlane * (unsigned)sizeof (double);
-    L.diag = L.slab + ring_align128 ((unsigned)plan.maxEntries * ring_slab_stride (opDim) * (unsigned)sizeof (double));
-    L.meta = L.diag + (((unsigned)plan.maxRows * opDim * (unsigned)sizeof (double) + 15u) & ~15u);
-    L.bars = L.meta + (((unsigned)plan.maxRows * (unsigned)sizeof (int) + 15u) & ~15u);
-    L.total = L.bars + 3 * (unsigned)sizeof (uint64_t);
+    L.tail = kRingHeadBuffers * L.headBytes;
+    L.tailBytes = ring_align128 (plan.maxTailBytes);
+    L.planes = L.tail + 2 * L.tailBytes;
+    L.slab = L.planes + 2 * 3 * kRingPlane * (unsigned)sizeof (double);
+    L.slabBytes = ring_align128 ((unsigned)plan.maxEntries * ring_slab_stride (opDim) * (unsigned)sizeof (double));
+    L.bars = L.slab + 2 * L.slabBytes;
+    L.total = L.bars + (kRingHeadBuffers + 6) * (unsigned)sizeof (uint64_t);
     return L;
 }
 
@@ -152,276 +173,307 @@ ring_assembly_kernel (const RingArgs args)
 #else
     extern __shared__ __align__(128) unsigned char smemRaw[];
 #endif
+    // job warps out of 12: measured on the EIB mesh (ms per iteration, 384 threads) elasticity 8: 0.494, 7: 0.449,
+    // 6: 0.456; the Laplacian has an eighth of the write-out work per row and wants more job warps (8: 0.260,
+    // 10: 0.280; 768 threads, 20 + 4: 0.252).  A single 768-thread CTA per SM does best with an even split (0.450).
+#ifdef MFB_RING_JOB_WARPS_OF_12
+    constexpr int kJobOf12 = MFB_RING_JOB_WARPS_OF_12;
+#else
+    constexpr int kJobOf12 = OPDIM == 1 ? (THREADS == 768 ? 10 : 8) : (THREADS == 768 ? 6 : 7);
+#endif
+    constexpr int NWARPS = THREADS / 32, NJOB = NWARPS * kJobOf12 / 12, NOUT = NWARPS - NJOB;
+    constexpr int NSTAGE = (kRingMaxNodes + NOUT * 32 - 1) / (NOUT * 32);    // nodes each write-out thread stages
     const DeviceRingPlan &P = args.plan;
-    const int tid = threadIdx.x, nThreads = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nWarps = nThreads >> 5;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
 
-    // shared memory: [head 0][head 1][tail][X Y Z][slab][diagonal blocks][row tags][3 mbarriers]
+    // shared memory: [head 0..3][tail 0, 1][X Y Z even tiles][X Y Z odd tiles][slab 0][slab 1][10 mbarriers]
     const RingSmemLayout &L = args.smem;
     const unsigned headBytes = L.headBytes;
     constexpr int planeStride = kRingPlane;                           // planes start on a 128-byte line: bank = id mod 16;
                                                                       // a constant, so that Y and Z are immediate offsets from X
     constexpr int SLAB = ring_slab_stride (OPDIM);
-    unsigned char *sHead0 = smemRaw, *sTail = smemRaw + L.tail;
-    double *sX = reinterpret_cast<double*> (smemRaw + L.planes), *sY = sX + planeStride, *sZ = sY + planeStride;
-    double *slab = reinterpret_cast<double*> (smemRaw + L.slab);
-    double *sDiag = reinterpret_cast<double*> (smemRaw + L.diag);
-    int *sMeta = reinterpret_cast<int*> (smemRaw + L.meta);           // node | interface << 31 | hasDiag << 30
+    unsigned char *sHead0 = smemRaw, *sTail0 = smemRaw + L.tail;
+    double *planes0 = reinterpret_cast<double*> (smemRaw + L.planes);
+    double *slab0 = reinterpret_cast<double*> (smemRaw + L.slab);
+    const unsigned slabDoubles = L.slabBytes / (unsigned)sizeof (double);
     uint64_t *bars = reinterpret_cast<uint64_t*> (smemRaw + L.bars);
-    uint64_t *headFull = bars, *tailFull = bars + 2;                  // headFull[2], tailFull
-
-    if (tid == 0) { ring_mbar_init (headFull, 1); ring_mbar_init (headFull + 1, 1); ring_mbar_init (tailFull, 1); }
-    __syncthreads ();
+    uint64_t *headFull = bars, *tailFull = bars + kRingHeadBuffers, *full = tailFull + 2, *ready = full + 2;
 
     const int firstTile = args.firstTile + blockIdx.x, tileStep = gridDim.x;
-    auto fetch_head = [&] (uint64_t packed, int k) {                  // thread 0 only
-        const unsigned bytes = ring_record_head_bytes (packed);
-        ring_mbar_expect_tx (headFull + (k & 1), bytes);
-        ring_bulk_load (sHead0 + (k & 1) * headBytes, P.blob + ring_record_offset (packed), bytes, headFull + (k & 1));
-    };
-    auto fetch_tail = [&] (uint64_t packed, const unsigned char *head) {   // thread 0 only, `head` has landed
-        const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
-        const unsigned bytes = h.blobBytes - h.headBytes;
-        if (bytes) {
-            ring_mbar_expect_tx (tailFull, bytes);
-            ring_bulk_load (sTail, P.blob + ring_record_offset (packed) + h.headBytes, bytes, tailFull);
-        }
-        else ring_mbar_arrive (tailFull);                               // a tile without jobs: the phase completes at once
-    };
-    // Node coordinates of a tile: thread n loads node n (three 8-byte loads from global memory) and later
-    // stores it into the planes with the warp's 32 nodes side by side — two wavefronts per store.  (An 8-byte
-    // cp.async per coordinate costs one shared-memory wavefront EACH when the data come back: ~20 M of the
-    // 77 M wavefronts of an EIB iteration in the round-1 kernel, profiles/r2_ring_ela_ncu_full.txt.)
-    static_assert (THREADS >= kRingMaxNodes, "one node per thread");
-    auto load_coords = [&] (const unsigned char *head, double c[3]) {
-        const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
-        const int *nodes = reinterpret_cast<const int*> (head + h.offNodes);
-        if (tid < h.nbNodes) {
-            const double *q = args.coord + (size_t)nodes[tid] * 3;
-            c[0] = __ldg (q); c[1] = __ldg (q + 1); c[2] = __ldg (q + 2);
-        }
-    };
-    auto store_coords = [&] (const unsigned char *head, const double c[3]) {
-        const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head);
-        if (tid < h.nbNodes) { sX[tid] = c[0]; sY[tid] = c[1]; sZ[tid] = c[2]; }
-    };
+    const int nbMine = firstTile < args.lastTile ? (args.lastTile - firstTile + tileStep - 1) / tileStep : 0;
+    if (nbMine == 0) return;
 
-    // thread 0 keeps the packed offsets of this tile and the next in registers and loads the one after
-    // that a whole tile ahead, so that issuing the copies never waits on global memory
-    uint64_t offCur = 0, offNext = 0;
-    if (tid == 0 && firstTile < args.lastTile) {
-        offCur = P.tileOffset[firstTile];
-        if (firstTile + tileStep < args.lastTile) offNext = P.tileOffset[firstTile + tileStep];
+    if (tid == 0) {
+        for (int b = 0; b < kRingHeadBuffers; b++) ring_mbar_init (headFull + b, 1);
+        for (int b = 0; b < 2; b++) { ring_mbar_init (tailFull + b, 1); ring_mbar_init (full + b, NJOB); ring_mbar_init (ready + b, NOUT); }
     }
-    // prologue: head, tail and coordinates of this CTA's first tile
-    if (firstTile < args.lastTile) {
-        if (tid == 0) fetch_head (offCur, 0);
-        ring_mbar_wait (headFull, 0);
-        if (tid == 0) fetch_tail (offCur, sHead0);
-        double c[3] = {0.0, 0.0, 0.0};
-        load_coords (sHead0, c);
-        store_coords (sHead0, c);
-    }
-    __syncthreads ();
+    __syncthreads ();          // the only block barrier
 
-    // Fused preconditioner of one finished tile: its diagonal blocks and row tags are in sDiag / sMeta.
-    // Run by the last two warps, one lane per row.
-    auto prec_pass = [&] (int nbRowsDone) {
-        for (int r = (warp - (nWarps - 2)) * 32 + lane; r < nbRowsDone; r += 64) {
-            const int meta = sMeta[r];                                // RingRow::node | hasDiag << 27
-            const int node = meta & kRingNodeMask;
-            const bool isInterface = meta < 0, hasDiag = (meta & (1 << 27)) != 0;
-            if (OPDIM == 1) {
-                const double dgl = sDiag[r];
-                args.prec[node] = isInterface ? dgl : 1.0 / dgl;
-            }
-            else {
-                double b[9];
+    auto head_of = [&] (int k) { return sHead0 + (unsigned)(k & (kRingHeadBuffers - 1)) * headBytes; };
+    auto wait_head = [&] (int k) { ring_mbar_wait (headFull + (k & (kRingHeadBuffers - 1)), (unsigned)(k / kRingHeadBuffers) & 1u); };
+
+    if (warp < NJOB) {
+        // =============================== job warps ===============================================
+        for (int k = 0; k < nbMine; k++) {
+            wait_head (k);
+            const unsigned char *sHead = head_of (k);
+            const RingTileHeader &hdr = *reinterpret_cast<const RingTileHeader*> (sHead);
+            const int nbBatches = hdr.nbBatches;
+            const unsigned char *sTail = sTail0 + (unsigned)(k & 1) * L.tailBytes;
+            const RingBatch *batches = reinterpret_cast<const RingBatch*> (sTail);
+            const uint64_t *jobs = reinterpret_cast<const uint64_t*> (sTail + (hdr.offJobs - hdr.headBytes));
+            const uint64_t *codes = reinterpret_cast<const uint64_t*> (sTail + (hdr.offCodes - hdr.headBytes));
+            const double *sX = planes0 + (k & 1) * (3 * planeStride), *sY = sX + planeStride, *sZ = sY + planeStride;
+            double *slab = slab0 + (k & 1) * slabDoubles;
+            const unsigned phase = (unsigned)(k >> 1) & 1u;
+            ring_mbar_wait (ready + (k & 1), phase);        // slab k & 1 drained (tile k - 2), coordinates of tile k in place
+            ring_mbar_wait (tailFull + (k & 1), phase);
+            // the batches of a tile go round the job warps, starting where the previous tile stopped
+            for (int b = (warp + NJOB - (k * 5) % NJOB) % NJOB; b < nbBatches; b += NJOB) {
+                const RingBatch rb = batches[b];
+                const uint64_t job = jobs[b * 32 + lane];
+                const int i = (int)(job & 0xFF), j = (int)((job >> 8) & 0xFF);
+                const int sIJ = (int)((job >> 16) & 0xFFFF), sJI = (int)((job >> 32) & 0xFFFF);
+                const double xi[3] = {sX[i], sY[i], sZ[i]};
+                const double d[3] = {sX[j] - xi[0], sY[j] - xi[1], sZ[j] - xi[2]};
+                const int len = (int)(job >> 48), nbSteps = rb.nbSteps;
+                double acc[OPDIM], u[3] = {0.0, 0.0, 0.0};
                 #pragma unroll
-                for (int q = 0; q < 9; q++) b[q] = sDiag[r * 9 + q];
-                if (!isInterface) {
-                    mask_block (b, (meta >> 28) & 1, (meta >> 29) & 1, (meta >> 30) & 1);
-                    if (hasDiag) {
-                        // cofactors over the determinant; a singular or non-finite block takes LAPACK's LU instead
-                        // (its infinities and NaNs are the reference's)
-                        double inv[9];
-                        if (invert3_adj (b, inv, [] (double x) { return ring_rcp (x); })) {
-                            #pragma unroll
-                            for (int q = 0; q < 9; q++) b[q] = inv[q];
-                        }
-                        else invert3_lu (b);
+                for (int q = 0; q < OPDIM; q++) acc[q] = 0.0;
+                const uint64_t *cw = codes + rb.codeBase + lane;
+                uint64_t word = 0;
+                if (rb.flags == 0) {
+                    // regular batch (every mesh without non-manifold edges): one chain per job.  Byte 0 names its
+                    // first node, every further byte adds one element; bytes beyond the job's length name a valid
+                    // node and their contribution is masked — no branch inside the step.
+                    if (nbSteps > 0) {
+                        word = cw[0];
+                        const int id = (int)(word & 0xFF);
+                        u[0] = sX[id] - xi[0]; u[1] = sY[id] - xi[1]; u[2] = sZ[id] - xi[2];
                     }
-                }
-                double *dst = args.prec + (size_t)node * 9;
-                #pragma unroll
-                for (int q = 0; q < 9; q++) dst[q] = b[q];
-            }
-        }
-    };
-    const bool precWarp = args.fusePrec && warp >= nWarps - 2;
-    int rowsDone = 0;             // rows of the previous tile whose preconditioner blocks are still to be written
-
-    int k = 0;
-    for (int tile = firstTile; tile < args.lastTile; tile += tileStep, k++) {
-        const unsigned char *sHead = sHead0 + (k & 1) * headBytes;
-        const RingTileHeader &hdr = *reinterpret_cast<const RingTileHeader*> (sHead);
-        const bool hasNext = tile + tileStep < args.lastTile;
-        // ---- 0. the next tile's head starts travelling ----------------------------------------
-        uint64_t offAfter = 0;
-        if (tid == 0) {
-            if (tile + 2 * tileStep < args.lastTile) offAfter = P.tileOffset[tile + 2 * tileStep];   // used next iteration
-            if (hasNext) fetch_head (offNext, k + 1);
-        }
-        const int nbRows = hdr.nbRows, nbBatches = hdr.nbBatches;
-        const RingRow *sRows = reinterpret_cast<const RingRow*> (sHead + sizeof (RingTileHeader));
-        const RingBatch *batches = reinterpret_cast<const RingBatch*> (sTail);
-        const uint64_t *jobs = reinterpret_cast<const uint64_t*> (sTail + (hdr.offJobs - hdr.headBytes));
-        const uint64_t *codes = reinterpret_cast<const uint64_t*> (sTail + (hdr.offCodes - hdr.headBytes));
-
-        // ---- 0b. preconditioner blocks of the previous tile (its write-out ended at the block barrier) ----
-        if (precWarp) prec_pass (rowsDone);
-        rowsDone = nbRows;
-
-        // ---- 1. job phase: one lane per mesh edge ----------------------------------------------
-        ring_mbar_wait (tailFull, k & 1);
-        for (int b = warp; b < nbBatches; b += nWarps) {
-            const RingBatch rb = batches[b];
-            const uint64_t job = jobs[b * 32 + lane];
-            const int i = (int)(job & 0xFF), j = (int)((job >> 8) & 0xFF);
-            const int sIJ = (int)((job >> 16) & 0xFFFF), sJI = (int)((job >> 32) & 0xFFFF);
-            const double xi[3] = {sX[i], sY[i], sZ[i]};
-            const double d[3] = {sX[j] - xi[0], sY[j] - xi[1], sZ[j] - xi[2]};
-            const int len = (int)(job >> 48), nbSteps = rb.nbSteps;
-            double acc[OPDIM], u[3] = {0.0, 0.0, 0.0};
-            #pragma unroll
-            for (int q = 0; q < OPDIM; q++) acc[q] = 0.0;
-            const uint64_t *cw = codes + rb.codeBase + lane;
-            uint64_t word = 0;
-            if (rb.flags == 0) {
-                // regular batch (every mesh without non-manifold edges): one chain per job.  Byte 0 names its
-                // first node, every further byte adds one element; bytes beyond the job's length name a valid
-                // node and their contribution is masked — no branch inside the step.
-                if (nbSteps > 0) {
-                    word = cw[0];
-                    const int id = (int)(word & 0xFF);
-                    u[0] = sX[id] - xi[0]; u[1] = sY[id] - xi[1]; u[2] = sZ[id] - xi[2];
-                }
-                // two steps per trip, u and w changing roles: no register copies between steps
-                double w[3];
-                auto load_node = [&] (int k, double v[3]) {
-                    if ((k & 7) == 0) word = cw[(k >> 3) * 32]; else word >>= 8;
-                    const int id = (int)(word & 0xFF);
-                    v[0] = sX[id] - xi[0]; v[1] = sY[id] - xi[1]; v[2] = sZ[id] - xi[2];
-                };
-                int k = 1;
-                for (; k + 1 < nbSteps; k += 2) {
-                    load_node (k, w);
-                    ring_accumulate<OPDIM> (d, u, w, acc, k < len);
-                    load_node (k + 1, u);
-                    ring_accumulate<OPDIM> (d, w, u, acc, k + 1 < len);
-                }
-                if (k < nbSteps) {
-                    load_node (k, w);
-                    ring_accumulate<OPDIM> (d, u, w, acc, k < len);
-                }
-            }
-            else {
-                // general batch: chains separated by breaks
-                bool have = false;
-                for (int k = 0; k < nbSteps; k++) {
-                    if ((k & 7) == 0) word = cw[(k >> 3) * 32]; else word >>= 8;
-                    const int id = (int)(word & 0xFF);
-                    if (k >= len) continue;
-                    if (id == kRingBreak) { have = false; continue; }
-                    const double w[3] = {sX[id] - xi[0], sY[id] - xi[1], sZ[id] - xi[2]};
-                    if (have) ring_accumulate<OPDIM> (d, u, w, acc);
-                    u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
-                    have = true;
-                }
-            }
-            if (sIJ != 0xFFFF) {
-                if (OPDIM == 1) {
-                    slab[sIJ] = acc[0];
-                    if (sJI != 0xFFFF) slab[sJI] = acc[0];
+                    // two steps per trip, u and w changing roles: no register copies between steps
+                    double w[3];
+                    auto load_node = [&] (int s, double v[3]) {
+                        if ((s & 7) == 0) word = cw[(s >> 3) * 32]; else word >>= 8;
+                        const int id = (int)(word & 0xFF);
+                        v[0] = sX[id] - xi[0]; v[1] = sY[id] - xi[1]; v[2] = sZ[id] - xi[2];
+                    };
+                    int s = 1;
+                    for (; s + 1 < nbSteps; s += 2) {
+                        load_node (s, w);
+                        ring_accumulate<OPDIM> (d, u, w, acc, s < len);
+                        load_node (s + 1, u);
+                        ring_accumulate<OPDIM> (d, w, u, acc, s + 1 < len);
+                    }
+                    if (s < nbSteps) {
+                        load_node (s, w);
+                        ring_accumulate<OPDIM> (d, u, w, acc, s < len);
+                    }
                 }
                 else {
-                    double blk[9];
-                    ring_block (acc, blk);
-                    double2 *dst = reinterpret_cast<double2*> (slab + sIJ * SLAB);
-                    dst[0] = make_double2 (blk[0], blk[1]); dst[1] = make_double2 (blk[2], blk[3]);
-                    dst[2] = make_double2 (blk[4], blk[5]); dst[3] = make_double2 (blk[6], blk[7]);
-                    slab[sIJ * SLAB + 8] = blk[8];
-                    if (sJI != 0xFFFF) {                    // K_ji = K_ij^T
-                        double2 *dstT = reinterpret_cast<double2*> (slab + sJI * SLAB);
-                        dstT[0] = make_double2 (blk[0], blk[3]); dstT[1] = make_double2 (blk[6], blk[1]);
-                        dstT[2] = make_double2 (blk[4], blk[7]); dstT[3] = make_double2 (blk[2], blk[5]);
-                        slab[sJI * SLAB + 8] = blk[8];
+                    // general batch: chains separated by breaks
+                    bool have = false;
+                    for (int s = 0; s < nbSteps; s++) {
+                        if ((s & 7) == 0) word = cw[(s >> 3) * 32]; else word >>= 8;
+                        const int id = (int)(word & 0xFF);
+                        if (s >= len) continue;
+                        if (id == kRingBreak) { have = false; continue; }
+                        const double w[3] = {sX[id] - xi[0], sY[id] - xi[1], sZ[id] - xi[2]};
+                        if (have) ring_accumulate<OPDIM> (d, u, w, acc);
+                        u[0] = w[0]; u[1] = w[1]; u[2] = w[2];
+                        have = true;
+                    }
+                }
+                if (sIJ != 0xFFFF) {
+                    if (OPDIM == 1) {
+                        slab[sIJ] = acc[0];
+                        if (sJI != 0xFFFF) slab[sJI] = acc[0];
+                    }
+                    else {
+                        double blk[9];
+                        ring_block (acc, blk);
+                        double2 *dst = reinterpret_cast<double2*> (slab + sIJ * SLAB);
+                        dst[0] = make_double2 (blk[0], blk[1]); dst[1] = make_double2 (blk[2], blk[3]);
+                        dst[2] = make_double2 (blk[4], blk[5]); dst[3] = make_double2 (blk[6], blk[7]);
+                        slab[sIJ * SLAB + 8] = blk[8];
+                        if (sJI != 0xFFFF) {                    // K_ji = K_ij^T
+                            double2 *dstT = reinterpret_cast<double2*> (slab + sJI * SLAB);
+                            dstT[0] = make_double2 (blk[0], blk[3]); dstT[1] = make_double2 (blk[6], blk[1]);
+                            dstT[2] = make_double2 (blk[4], blk[7]); dstT[3] = make_double2 (blk[2], blk[5]);
+                            slab[sJI * SLAB + 8] = blk[8];
+                        }
                     }
                 }
             }
+            __syncwarp ();
+            if (lane == 0) ring_mbar_arrive (full + (k & 1));   // this warp's share of tile k is in the slab; it no longer
+                                                                // reads the tile's tail, coordinates or head
         }
-        __syncthreads ();      // the slab is complete; tail and coordinates of this tile are dead
-
-        // ---- 2. next tile's tail (TMA) and coordinates (plain loads) start travelling -------------
-        double nextCoord[3] = {0.0, 0.0, 0.0};
-        if (hasNext) {
-            const unsigned char *nextHead = sHead0 + ((k + 1) & 1) * headBytes;
-            ring_mbar_wait (headFull + ((k + 1) & 1), ((k + 1) >> 1) & 1);
-            if (tid == 0) fetch_tail (offNext, nextHead);
-            load_coords (nextHead, nextCoord);               // stored at the end of the write-out
-        }
-
-        // ---- 3. write-out: the diagonal entry of a row is minus the sum of the row's run ------------
-        if (OPDIM == 1) {
-            // Laplacian: one lane per row walks its entries (rows are short and the whole matrix is an eighth of
-            // the elasticity one: 8-byte stores to 32 different rows per instruction are affordable; the four
-            // entries of a sector come from the same lane in consecutive trips).  Row starts 1 (mod 8) slots
-            // apart keep the slab reads of a half-warp in different banks.
-            for (int r = warp * 32 + lane; r < nbRows; r += nWarps * 32) {
-                const RingRow rr = sRows[r];
-                const int len = rr.len, diagOff = rr.diagOff;         // 0xFFFF never equals a position
-                double *out = args.values + (size_t)rr.valueStart;
-                const double *src = slab + (size_t)rr.localStart;
-                double a = 0.0;
-                for (int q = 0; q < len; q++) {
-                    if (q != diagOff) { const double v = src[q]; a += v; out[q] = v; }
-                }
-                const double diag = 0.0 - a;
-                if (diagOff != 0xFFFF) out[diagOff] = diag;
-                sDiag[r] = diag;
-                sMeta[r] = rr.node | (diagOff != 0xFFFF ? (1 << 27) : 0);
-            }
-        }
-        else {
-            // Elasticity: three consecutive rows per warp side by side, ten lanes each (nine components and an
-            // idle lane); a lane walks the entries of its row, so the row sum needs no exchange between lanes.
-            // The slab starts of consecutive rows are 1 (mod 8) slots apart (ring_row_padding): the three
-            // 72-byte pieces read in one instruction fall into disjoint banks.
-            const int grp = lane / 10, comp = lane - 10 * grp;        // lanes 9, 19, 29, 30, 31 idle
-            for (int r0 = warp * 3; r0 < nbRows; r0 += nWarps * 3) {
-                const int r = r0 + grp;
-                if (grp < 3 && comp < 9 && r < nbRows) {
-                    const RingRow rr = sRows[r];
-                    const int len = rr.len, diagOff = rr.diagOff;     // 0xFFFF never equals a position
-                    const double *sp = slab + (size_t)rr.localStart * SLAB + comp;
-                    double *out = args.values + (size_t)rr.valueStart * 9 + comp, *op = out;
-                    double a = 0.0;
-                    for (int q = 0; q < len; q++, sp += SLAB, op += 9) {
-                        if (q != diagOff) { const double v = *sp; a += v; *op = v; }
-                    }
-                    const double diag = 0.0 - a;
-                    if (diagOff != 0xFFFF) out[diagOff * 9] = diag;
-                    sDiag[r * 9 + comp] = diag;
-                    if (comp == 0) sMeta[r] = rr.node | (diagOff != 0xFFFF ? (1 << 27) : 0);
-                }
-            }
-        }
-
-        offCur = offNext; offNext = offAfter;
-        if (hasNext) store_coords (sHead0 + ((k + 1) & 1) * headBytes, nextCoord);   // this tile's jobs, the planes' readers, are behind the barrier
-        __syncthreads ();           // every reader of this tile's slab / head is done; sDiag / sMeta and the next coordinates are complete
     }
-    if (precWarp) prec_pass (rowsDone);     // the CTA's last tile
+    else {
+        // =============================== write-out warps =========================================
+        const int ow = warp - NJOB, otid = tid - NJOB * 32;          // 0 .. NOUT * 32 - 1
+        auto tile_of = [&] (int k) { return firstTile + k * tileStep; };
+        auto fetch_head = [&] (uint64_t packed, int k) {              // one thread
+            const unsigned bytes = ring_record_head_bytes (packed);
+            uint64_t *bar = headFull + (k & (kRingHeadBuffers - 1));
+            ring_mbar_expect_tx (bar, bytes);
+            ring_bulk_load (head_of (k), P.blob + ring_record_offset (packed), bytes, bar);
+        };
+        auto fetch_tail = [&] (uint64_t packed, int k) {              // one thread, head k has landed
+            const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (head_of (k));
+            const unsigned bytes = h.blobBytes - h.headBytes;
+            uint64_t *bar = tailFull + (k & 1);
+            if (bytes) {
+                ring_mbar_expect_tx (bar, bytes);
+                ring_bulk_load (sTail0 + (unsigned)(k & 1) * L.tailBytes, P.blob + ring_record_offset (packed) + h.headBytes, bytes, bar);
+            }
+            else ring_mbar_arrive (bar);                                // a tile without jobs: the phase completes at once
+        };
+        // the loader (first write-out thread) keeps the packed record offsets of tiles k + 2 and k + 3 in
+        // registers and loads the next one a whole tile before it is needed
+        uint64_t offA = 0, offB = 0;
+        if (otid == 0) {
+            for (int q = 0; q < 3 && q < nbMine; q++) fetch_head (P.tileOffset[tile_of (q)], q);
+            offA = P.tileOffset[tile_of (0)];
+            if (nbMine > 1) offB = P.tileOffset[tile_of (1)];
+        }
+        // k = -2, -1: nothing to write out yet, only the first two tiles to stage
+        for (int k = -2; k < nbMine; k++) {
+            ring_bar_sync (1, NOUT * 32);      // every write-out warp has finished tile k - 1: its head buffer is free
+            if (k >= 0) ring_mbar_wait (full + (k & 1), (unsigned)(k >> 1) & 1u);   // the job warps are done with tile k
+            // ---- staging for tile k + 2 (into the buffers of tile k) -------------------------------------
+            const int kn = k + 2;
+            double cs[NSTAGE][3];
+            #pragma unroll
+            for (int q = 0; q < NSTAGE; q++) cs[q][0] = cs[q][1] = cs[q][2] = 0.0;
+            int nbNodesNext = 0;
+            if (kn < nbMine) {
+                wait_head (kn);
+                const unsigned char *nh = head_of (kn);
+                const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (nh);
+                if (otid == 0) fetch_tail (offA, kn);
+                nbNodesNext = h.nbNodes;
+                const int *nodes = reinterpret_cast<const int*> (nh + h.offNodes);
+                #pragma unroll
+                for (int q = 0; q < NSTAGE; q++) {
+                    const int n = otid + q * NOUT * 32;
+                    if (n < nbNodesNext) {
+                        const double *g = args.coord + (size_t)nodes[n] * 3;
+                        cs[q][0] = __ldg (g); cs[q][1] = __ldg (g + 1); cs[q][2] = __ldg (g + 2);
+                    }
+                }
+            }
+            if (otid == 0) {
+                // head of tile k + 3 into the buffer of tile k - 1 (its write-out ended before the named barrier, its
+                // jobs before full[] of the previous round)
+                if (k + 3 >= 3 && k + 3 < nbMine) fetch_head (offB, k + 3);
+                offA = offB;
+                offB = k + 4 < nbMine ? P.tileOffset[tile_of (k + 4)] : 0;
+            }
+            // ---- write-out of tile k: the diagonal entry of a row is minus the sum of the row's run ---------
+            if (k >= 0) {
+                const unsigned char *sHead = head_of (k);
+                const RingTileHeader &hdr = *reinterpret_cast<const RingTileHeader*> (sHead);
+                const int nbRows = hdr.nbRows;
+                const RingRow *sRows = reinterpret_cast<const RingRow*> (sHead + sizeof (RingTileHeader));
+                const double *slab = slab0 + (k & 1) * slabDoubles;
+                if (OPDIM == 1) {
+                    // Laplacian: one lane per row walks its entries (rows are short and the whole matrix is an eighth
+                    // of the elasticity one).  Row starts 1 (mod 8) slots apart keep the slab reads in different banks.
+                    for (int r = ow * 32 + lane; r < nbRows; r += NOUT * 32) {
+                        const RingRow rr = sRows[r];
+                        const int len = rr.len, diagOff = rr.diagOff;         // 0xFFFF never equals a position
+                        double *out = args.values + (size_t)rr.valueStart;
+                        const double *src = slab + (size_t)rr.localStart;
+                        double a = 0.0;
+                        for (int q = 0; q < len; q++) {
+                            if (q != diagOff) { const double v = src[q]; a += v; out[q] = v; }
+                        }
+                        const double diag = 0.0 - a;
+                        if (diagOff != 0xFFFF) out[diagOff] = diag;
+                        if (args.fusePrec) args.prec[rr.node & kRingNodeMask] = rr.node < 0 ? diag : 1.0 / diag;
+                    }
+                }
+                else {
+                    // Elasticity: three consecutive rows per warp side by side, ten lanes each (nine components and an
+                    // idle lane); a lane walks the entries of its row, so the row sum needs no exchange between lanes.
+                    // The slab starts of consecutive rows are 1 (mod 8) slots apart (ring_row_padding): the three
+                    // 72-byte pieces read in one instruction fall into disjoint banks.
+                    const int grp = lane / 10, comp = lane - 10 * grp;        // lanes 9, 19, 29, 30, 31 idle
+                    const bool worker = grp < 3 && comp < 9;
+                    const int ca = comp / 3, cb = comp - 3 * ca;              // component (ca, cb) of the 3x3 block
+                    const int base = worker ? 10 * grp : lane;                // first lane of the row's nine; idle lanes read themselves
+                    for (int r0 = ow * 3; r0 < nbRows; r0 += NOUT * 3) {
+                        const int r = r0 + grp;
+                        const bool rowOk = worker && r < nbRows;
+                        int node = 0, diagOff = 0xFFFF;
+                        double diag = 0.0;
+                        if (rowOk) {
+                            const RingRow rr = sRows[r];
+                            const int len = rr.len;
+                            node = rr.node; diagOff = rr.diagOff;             // 0xFFFF never equals a position
+                            const double *sp = slab + (size_t)rr.localStart * SLAB + comp;
+                            double *out = args.values + (size_t)rr.valueStart * 9 + comp, *op = out;
+                            double a = 0.0;
+                            for (int q = 0; q < len; q++, sp += SLAB, op += 9) {
+                                if (q != diagOff) { const double v = *sp; a += v; *op = v; }
+                            }
+                            diag = 0.0 - a;
+                            if (diagOff != 0xFFFF) out[diagOff * 9] = diag;
+                        }
+                        if (args.fusePrec) {
+                            // prec_init + prec_inversion (src/preconditioner.cc:25-87, src/Fortran/elasclpr.f:19-53) by the
+                            // nine lanes that hold the block: Dirichlet rows / columns to identity, then cofactor / determinant
+                            const bool masked = ((node >> (28 + ca)) | (node >> (28 + cb))) & 1;
+                            const double m = masked ? (ca == cb ? 1.0 : 0.0) : diag;
+                            const double x1 = __shfl_sync (0xffffffffu, m, base + adj_src (cb + 1, ca + 1));
+                            const double x2 = __shfl_sync (0xffffffffu, m, base + adj_src (cb + 2, ca + 2));
+                            const double x3 = __shfl_sync (0xffffffffu, m, base + adj_src (cb + 1, ca + 2));
+                            const double x4 = __shfl_sync (0xffffffffu, m, base + adj_src (cb + 2, ca + 1));
+                            const double m0 = __shfl_sync (0xffffffffu, m, base + ca);      // M(0, ca), used where cb == 0
+                            const double t = x3 * x4;
+                            const double cof = fma (x1, x2, -t);
+                            const double p = m0 * cof;
+                            const double p0 = __shfl_sync (0xffffffffu, p, base);
+                            const double p1 = __shfl_sync (0xffffffffu, p, base + 3);
+                            const double p2 = __shfl_sync (0xffffffffu, p, base + 6);
+                            const double det = (p0 + p1) + p2;
+                            const bool isInterface = node < 0;
+                            const bool invert = rowOk && !isInterface && diagOff != 0xFFFF;
+                            const bool regular = fabs (det) > 0.0 && fabs (det) < 1.0e300;
+                            double out = isInterface ? diag : m;
+                            if (invert && regular) out = cof * ring_rcp (det);
+                            if (__any_sync (0xffffffffu, invert && !regular)) {
+                                // a singular or non-finite block: the infinities and NaNs of LAPACK's LU, not of the cofactors
+                                double blk[9];
+                                #pragma unroll
+                                for (int q = 0; q < 9; q++) blk[q] = __shfl_sync (0xffffffffu, m, base + q);
+                                if (invert && !regular) {
+                                    invert3_lu (blk);
+                                    #pragma unroll
+                                    for (int q = 0; q < 9; q++) if (q == comp) out = blk[q];
+                                }
+                            }
+                            if (rowOk) args.prec[(size_t)(node & kRingNodeMask) * 9 + comp] = out;
+                        }
+                    }
+                }
+            }
+            // ---- coordinates of tile k + 2 into the plane set the job warps released with tile k ----------------
+            if (kn < nbMine) {
+                double *pl = planes0 + (kn & 1) * (3 * planeStride);
+                #pragma unroll
+                for (int q = 0; q < NSTAGE; q++) {
+                    const int n = otid + q * NOUT * 32;
+                    if (n < nbNodesNext) { pl[n] = cs[q][0]; pl[planeStride + n] = cs[q][1]; pl[2 * planeStride + n] = cs[q][2]; }
+                }
+                __syncwarp ();
+                if (lane == 0) ring_mbar_arrive (ready + (kn & 1));     // tile k + 2 may start: slab drained, coordinates in
+            }
+        }
+    }
 }
 
 #ifndef MFB_RING_HOST_EMULATION
@@ -445,21 +497,21 @@ cudaError_t ring_configure (int operatorID)
 {
     cudaError_t e;
     if (operatorID == 0) {
-        if ((e = ring_opt_in (ring_assembly_kernel<1, 256, 3>)) != cudaSuccess) return e;
-        return ring_opt_in (ring_assembly_kernel<1, 384, 2>);
+        if ((e = ring_opt_in (ring_assembly_kernel<1, 384, 2>)) != cudaSuccess) return e;
+        return ring_opt_in (ring_assembly_kernel<1, 768, 1>);
     }
-    if ((e = ring_opt_in (ring_assembly_kernel<9, 256, 3>)) != cudaSuccess) return e;
-    return ring_opt_in (ring_assembly_kernel<9, 384, 2>);
+    if ((e = ring_opt_in (ring_assembly_kernel<9, 384, 2>)) != cudaSuccess) return e;
+    return ring_opt_in (ring_assembly_kernel<9, 768, 1>);
 }
 
 cudaError_t ring_ctas_per_sm (int operatorID, int threads, size_t smemBytes, int *ctas)
 {
-    if (threads == 384) {
-        return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 384, 2>, 384, smemBytes)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 384, 2>, 384, smemBytes);
+    if (threads == 768) {
+        return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 768, 1>, 768, smemBytes)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 768, 1>, 768, smemBytes);
     }
-    return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 256, 3>, 256, smemBytes)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 256, 3>, 256, smemBytes);
+    return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 384, 2>, 384, smemBytes)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 384, 2>, 384, smemBytes);
 }
 
 cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,
@@ -473,13 +525,13 @@ cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTi
     args.fusePrec = fusePrec;
     args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
     const int grid = std::max (1, std::min (ctas, nbTiles));
-    if (threads == 384) {
-        if (operatorID == 0) ring_assembly_kernel<1, 384, 2><<<grid, 384, smemBytes, stream>>> (args);
-        else                 ring_assembly_kernel<9, 384, 2><<<grid, 384, smemBytes, stream>>> (args);
+    if (threads == 768) {
+        if (operatorID == 0) ring_assembly_kernel<1, 768, 1><<<grid, 768, smemBytes, stream>>> (args);
+        else                 ring_assembly_kernel<9, 768, 1><<<grid, 768, smemBytes, stream>>> (args);
     }
     else {
-        if (operatorID == 0) ring_assembly_kernel<1, 256, 3><<<grid, 256, smemBytes, stream>>> (args);
-        else                 ring_assembly_kernel<9, 256, 3><<<grid, 256, smemBytes, stream>>> (args);
+        if (operatorID == 0) ring_assembly_kernel<1, 384, 2><<<grid, 384, smemBytes, stream>>> (args);
+        else                 ring_assembly_kernel<9, 384, 2><<<grid, 384, smemBytes, stream>>> (args);
     }
     return cudaGetLastError ();
 }

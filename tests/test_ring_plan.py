@@ -221,7 +221,7 @@ def kernel_host():
     return lib
 
 
-def run_kernel_on_host(lib, setup, rows=0, entries=0, ctas=3, fuse=1, interface=None, threads=256):
+def run_kernel_on_host(lib, setup, rows=0, entries=0, ctas=3, fuse=1, interface=None, threads=384):
     m = setup.mesh
     dim = setup.operatorDim
     values = np.full(setup.nbEdges * dim, np.nan)
@@ -247,8 +247,8 @@ def test_ring_kernel_source_on_host_threads(kernel_host, oracle, op, grid, rows,
 
 @pytest.mark.parametrize("op", ["ela", "lap"])
 def test_ring_kernel_source_equals_replay_bit_for_bit(ringlib, kernel_host, op):
-    """Two independent readings of the plan — the sequential replay and the kernel's own source on 256
-    host threads per CTA — give identical bits (both test aids are built without FMA contraction)."""
+    """Two independent readings of the plan — the sequential replay and the kernel's own source on 384
+    host threads per CTA (8 job warps, 4 write-out warps) — give identical bits (both test aids are built without FMA contraction)."""
     mesh = mfb.Mesh.generate(9, 8, 7, seed=8)
     setup = mfb.Setup(mesh, op)
     v_replay, p_replay, _ = replay(ringlib, setup)
@@ -257,11 +257,11 @@ def test_ring_kernel_source_equals_replay_bit_for_bit(ringlib, kernel_host, op):
 
 
 @pytest.mark.parametrize("op", ["ela", "lap"])
-def test_ring_kernel_source_384_threads(kernel_host, oracle, op):
-    """The two-CTAs-per-SM instantiation (12 warps, larger tiles)."""
+def test_ring_kernel_source_768_threads(kernel_host, oracle, op):
+    """The one-CTA-per-SM instantiation (16 job warps + 8 write-out warps, larger tiles)."""
     mesh = mfb.Mesh.generate(9, 8, 8, seed=9)
     setup = mfb.Setup(mesh, op)
-    values, prec = run_kernel_on_host(kernel_host, setup, rows=54, entries=960, ctas=2, threads=384)
+    values, prec = run_kernel_on_host(kernel_host, setup, rows=54, entries=960, ctas=2, threads=768)
     check_against_oracle(oracle, setup, values, prec)
 
 
@@ -345,5 +345,5 @@ def test_ring_kernel_source_randomized_against_replay(ringlib, kernel_host):
             assert "exceeds the tile caps" in str(refused) or "254 nodes" in str(refused)
             continue
         v_kernel, p_kernel = run_kernel_on_host(kernel_host, setup, rows, entries, int(rng.integers(1, 5)), 1, interface,
-                                                int(rng.choice([256, 256, 384])))
+                                                int(rng.choice([384, 384, 768])))
         assert np.array_equal(v_replay, v_kernel, equal_nan=True) and np.array_equal(p_replay, p_kernel, equal_nan=True)

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -27,8 +28,13 @@
 
 namespace cta_emu {
 
+struct MbarState { uint64_t *addr; unsigned expected, pending; uint64_t bytes; };
+struct NamedBarrier { int id; pthread_barrier_t *barrier; };
 struct Cta {
     int threads = 0;
+    std::mutex mbarMutex;
+    std::vector<MbarState> mbars;
+    std::vector<NamedBarrier> named;
     pthread_barrier_t blockBarrier;
     std::vector<pthread_barrier_t> warpBarrier;
     std::vector<double> xchg;                 // 32 doubles per warp
@@ -57,28 +63,68 @@ inline double shfl (double v, int srcLane)
     return r;
 }
 
-// mbarrier with one expected arrival: low 32 bits = completed phases, high 32 bits = pending bytes
-inline void mbar_init (uint64_t *bar) { __atomic_store_n (bar, 0ull, __ATOMIC_RELEASE); }
-inline void mbar_complete_if_idle (uint64_t *bar)
+// mbarriers: the 8-byte object in shared memory only holds the number of completed phases; expected arrivals,
+// pending arrivals and pending transaction bytes live in a side table of the CTA, under its mutex (which also
+// gives ThreadSanitizer the happens-before edges of release / acquire).
+inline MbarState &mbar_state (uint64_t *bar)
 {
-    uint64_t v = __atomic_load_n (bar, __ATOMIC_ACQUIRE);
-    if ((v >> 32) == 0) __atomic_store_n (bar, (uint64_t)(uint32_t)(v + 1), __ATOMIC_RELEASE);
+    for (MbarState &m : tls.cta->mbars) if (m.addr == bar) return m;
+    fprintf (stderr, "cta_emu: mbarrier used before init\n"); abort ();
 }
-inline void mbar_expect_tx (uint64_t *bar, unsigned bytes)      // arrive (the only one) + expect `bytes`
+inline void mbar_complete_if_done (MbarState &m)
 {
-    const uint64_t v = __atomic_load_n (bar, __ATOMIC_ACQUIRE);
-    if (v >> 32) { fprintf (stderr, "cta_emu: expect_tx on a barrier with bytes in flight\n"); abort (); }
-    __atomic_store_n (bar, (v & 0xffffffffull) | ((uint64_t)bytes << 32), __ATOMIC_RELEASE);
-    if (bytes == 0) mbar_complete_if_idle (bar);
+    if (m.pending == 0 && m.bytes == 0) { __atomic_store_n (m.addr, *m.addr + 1, __ATOMIC_RELEASE); m.pending = m.expected; }
+}
+inline void mbar_init (uint64_t *bar, unsigned count = 1)
+{
+    std::lock_guard<std::mutex> lock (tls.cta->mbarMutex);
+    tls.cta->mbars.push_back ({bar, count, count, 0});
+    __atomic_store_n (bar, 0ull, __ATOMIC_RELEASE);
+}
+inline void mbar_arrive (uint64_t *bar)
+{
+    std::lock_guard<std::mutex> lock (tls.cta->mbarMutex);
+    MbarState &m = mbar_state (bar);
+    if (m.pending == 0) { fprintf (stderr, "cta_emu: more arrivals than expected\n"); abort (); }
+    m.pending--;
+    mbar_complete_if_done (m);
+}
+inline void mbar_expect_tx (uint64_t *bar, unsigned bytes)      // arrive + expect `bytes`
+{
+    std::lock_guard<std::mutex> lock (tls.cta->mbarMutex);
+    MbarState &m = mbar_state (bar);
+    if (m.pending == 0) { fprintf (stderr, "cta_emu: more arrivals than expected\n"); abort (); }
+    m.pending--;
+    m.bytes += bytes;
+    mbar_complete_if_done (m);
 }
 inline void bulk_load (void *dst, const void *src, unsigned bytes, uint64_t *bar)
 {
     if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15) || (bytes & 15)) { fprintf (stderr, "cta_emu: bulk copy not 16-byte aligned\n"); abort (); }
     memcpy (dst, src, bytes);
-    const uint64_t v = __atomic_load_n (bar, __ATOMIC_ACQUIRE);
-    if ((v >> 32) < bytes) { fprintf (stderr, "cta_emu: more bytes copied than expected\n"); abort (); }
-    __atomic_store_n (bar, v - ((uint64_t)bytes << 32), __ATOMIC_RELEASE);
-    mbar_complete_if_idle (bar);
+    std::lock_guard<std::mutex> lock (tls.cta->mbarMutex);
+    MbarState &m = mbar_state (bar);
+    if (m.bytes < bytes) { fprintf (stderr, "cta_emu: more bytes copied than expected\n"); abort (); }
+    m.bytes -= bytes;
+    mbar_complete_if_done (m);
+}
+// bulk copy shared -> global, performed at issue (the earliest moment the TMA unit could read the source)
+inline void bulk_store (void *dst, const void *src, unsigned bytes)
+{
+    if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15) || (bytes & 15)) { fprintf (stderr, "cta_emu: bulk store not 16-byte aligned\n"); abort (); }
+    memcpy (dst, src, bytes);
+}
+inline bool any_sync (bool pred)
+{
+    Cta &c = *tls.cta;
+    const int warp = (int)(tls.threadIdx.x >> 5), lane = (int)(tls.threadIdx.x & 31);
+    double *x = c.xchg.data () + (size_t)warp * 32;
+    x[lane] = pred ? 1.0 : 0.0;
+    pthread_barrier_wait (&c.warpBarrier[warp]);
+    bool r = false;
+    for (int l = 0; l < 32; l++) r = r || x[l] != 0.0;
+    pthread_barrier_wait (&c.warpBarrier[warp]);
+    return r;
 }
 inline void mbar_wait (uint64_t *bar, unsigned parity)          // returns once the phase of that parity has completed
 {
@@ -89,6 +135,22 @@ inline void mbar_wait (uint64_t *bar, unsigned parity)          // returns once 
     }
     fprintf (stderr, "cta_emu: mbarrier wait timed out (block %u thread %u)\n", tls.blockIdx.x, tls.threadIdx.x);
     abort ();
+}
+// named barrier (bar.sync id, count): one pthread barrier per (id, count), created on first use
+inline void bar_sync (int id, int count)
+{
+    Cta &c = *tls.cta;
+    pthread_barrier_t *b = nullptr;
+    {
+        std::lock_guard<std::mutex> lock (c.mbarMutex);
+        for (auto &nb : c.named) if (nb.id == id) b = nb.barrier;
+        if (!b) {
+            b = new pthread_barrier_t;
+            pthread_barrier_init (b, nullptr, (unsigned)count);
+            c.named.push_back ({id, b});
+        }
+    }
+    pthread_barrier_wait (b);
 }
 
 // Runs kernel() for every thread of every CTA of the grid; CTAs one after the other.
@@ -133,6 +195,8 @@ inline unsigned char *dynamic_smem ()          // 128-byte aligned like the kern
 #define __syncwarp() cta_emu::syncwarp ()
 #define __shfl_xor_sync(mask, v, off) cta_emu::shfl ((v), (int)(threadIdx.x & 31) ^ (off))
 #define __shfl_down_sync(mask, v, delta) cta_emu::shfl ((v), (int)(threadIdx.x & 31) + (delta))
+#define __shfl_sync(mask, v, src) cta_emu::shfl ((v), (src) & 31)
+#define __any_sync(mask, pred) cta_emu::any_sync (pred)
 #define __ldg(p) (*(p))
 #define __trap() abort ()
 using std::max;

@@ -50,13 +50,13 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
         if (nbTiles <= 0) return;
         args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
         grid = std::max (1, std::min (grid, nbTiles));
-        if (threads == 384) {
-            if (operatorID == 0) cta_emu::launch (grid, 384, smem, [&] () { ring_assembly_kernel<1, 384, 2> (args); });
-            else                 cta_emu::launch (grid, 384, smem, [&] () { ring_assembly_kernel<9, 384, 2> (args); });
+        if (threads == 768) {
+            if (operatorID == 0) cta_emu::launch (grid, 768, smem, [&] () { ring_assembly_kernel<1, 768, 1> (args); });
+            else                 cta_emu::launch (grid, 768, smem, [&] () { ring_assembly_kernel<9, 768, 1> (args); });
         }
         else {
-            if (operatorID == 0) cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<1, 256, 3> (args); });
-            else                 cta_emu::launch (grid, 256, smem, [&] () { ring_assembly_kernel<9, 256, 3> (args); });
+            if (operatorID == 0) cta_emu::launch (grid, 384, smem, [&] () { ring_assembly_kernel<1, 384, 2> (args); });
+            else                 cta_emu::launch (grid, 384, smem, [&] () { ring_assembly_kernel<9, 384, 2> (args); });
         }
     };
     const int grid = ctas > 0 ? ctas : 3;
