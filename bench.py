@@ -12,10 +12,13 @@ workload at N = 1 is the EIB-like elasticity case BASELINE.json quotes its metri
 only interface preconditioner values cross NVLink (NCCL), as in the reference's domain
 decomposition.  Prints ONE JSON line (rank 0).
 
---path auto (the default) measures the TILED path unless the RING path first agrees
-with it to 1e-12 on this very mesh and is faster, checked by rank 0 in a process of its own
-(choose_path / probe_ring); the verdict travels in the line as "path_selection" and the path that
-was measured is config.path.
+The measured path is RING (mini-fem_b200/csrc/kernels_ring.cu), the default write-once path; the line also
+carries, outside every timed region: `parity` (values and prec of the measured contexts against the CPU
+oracle on the same subdomains, at every N — at N > 1 the oracle's interface values travel through
+torch.distributed in the message pattern of halo.cc), `strong` (N > 1: the 100^3 mesh cut into N
+subdomains, next to the same mesh on one GPU), `configs` (N = 1: the other configurations of
+BASELINE.json — LM6 lap / ela, EIB lap, 200^3 ela — and an unstructured Delaunay mesh, every path),
+`other_paths`, and the CPU baselines (the reference's own FEM_loop from oracle/_ref).
 """
 import argparse
 import json
@@ -42,10 +45,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, nargs=3, default=[100, 100, 100], help="cubes per GPU block")
     ap.add_argument("--op", default="ela", choices=["ela", "lap"])
-    ap.add_argument("--path", default="auto", choices=["auto", "tiled", "atomic", "color", "ring"],
-                    help="auto = TILED, unless the RING path proves itself on this box first (see choose_path)")
-    ap.add_argument("--probe-ring", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--device", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--path", default="ring", choices=["ring", "tiled", "atomic", "color"])
+    ap.add_argument("--configs", default="all", choices=["all", "fast", "none"],
+                    help="N = 1: also time the other BASELINE.json configurations (fast: without the 200^3 and Delaunay meshes)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--tile-elems", type=int, default=0)
@@ -140,24 +144,45 @@ def load_traffic(key):
 
 # ------------------------------------------------------------------ reference arm (CPU)
 
-def run_reference_cpu(op, grid, nb_iter, ranks):
+class RefSetup:
+    """What main.cc builds between read_input_data and FEM_loop, by the reference's own compiled functions
+    (oracle/_ref: create_nodeToNode, create_elemToEdge, dqmrd4_ / e_essbcm_) — the reference arm uses this
+    repository's library for nothing but generating the synthetic mesh."""
+
+    def __init__(self, ref, mesh, op, elem_to_edge=False):
+        self.mesh = mesh
+        self.operatorID = {"lap": 0, "ela": 1}[op]
+        self.operatorDim = 1 if self.operatorID == 0 else 9
+        self.elemToNode = mesh.elemToNode.copy()
+        self.colorToElem, self.nbTotalColors, self.colorPerm = None, 0, None
+        self.row, self.col = ref.create_nodeToNode(self.elemToNode, mesh.nbNodes)
+        self.nbEdges = int(self.row[-1])
+        self.elemToEdge = ref.create_elemToEdge(self.row, self.col, self.elemToNode) if elem_to_edge else None
+        self.checkBounds = ref.boundary_mask(mesh.boundNodesCode)
+
+
+def run_reference_cpu(op, grid, nb_iter, ranks, kind="ref"):
     """The reference's own FEM_loop (oracle/_ref, REF build = pure MPI, one rank per
-    subdomain, ranks as threads) on the EIB-like mesh cut into `ranks` blocks.  Falls back
+    subdomain, ranks as threads) on the EIB-like mesh cut into `ranks` blocks.  kind = "ref_opt": the same
+    with -DOPTIMIZED (elemToEdge instead of the row search, build/CMakeLists.txt:67-69).  Falls back
     to the C oracle port when oracle/_ref was not built."""
     import minifem_b200 as mfb
     from oracle_lib import Oracle, Reference, ref_available
     blocks = mfb.choose_blocks(*grid, ranks)
     n = blocks[0] * blocks[1] * blocks[2]
     meshes = [mfb.Mesh.generate(*grid, blocks=blocks, rank=r, seed=1) for r in range(n)]
-    setups = [mfb.Setup(m, op) for m in meshes]
     elements = sum(m.nbElem for m in meshes)
-    if ref_available("ref"):
-        ref = Reference("ref")
+    if ref_available(kind):
+        ref = Reference(kind)
+        setups = [RefSetup(ref, m, op, elem_to_edge=kind.endswith("_opt")) for m in meshes]
         _, _, cycles, hz = ref.fem_loop(setups, nb_iter)
         seconds = sum(cycles) / hz                                   # FEM.cc:132: total of the 4 stage averages
-        kind, detail = "reference", "oracle/_ref libminifem_ref_ref.so (src/*.cc, -O2 -mavx, REF build, search path as shipped)"
+        detail = (f"oracle/_ref libminifem_ref_{kind}.so (src/*.cc, -O2 -mavx, REF build, " +
+                  ("-DOPTIMIZED: elemToEdge)" if kind.endswith("_opt") else "search path as shipped)"))
+        kind = "reference"
     else:
         oracle = Oracle()
+        setups = [mfb.Setup(m, op) for m in meshes]
         t0 = time.perf_counter()
         for s in setups:
             oracle.fem_iteration(s)
@@ -193,6 +218,8 @@ def reference_main(args, rank, world):
     whole = mfb.Mesh.generate(*grid, seed=1)                      # header counts of the undivided mesh
     t0 = time.perf_counter()
     value, n, kind, detail, elements, blocks = run_reference_cpu(args.op, grid, nb_timed + 1, min(cores, 64))
+    # the same element count as the GPU arm at N > 1 is not attempted: the reference arm always runs ONE mesh of the
+    # --grid size on the host cores (rates are comparable, the work is not) — said in config.arm
     wall = time.perf_counter() - t0
     sample = (f"{grid[0]}x{grid[1]}x{grid[2]}-cube EIB-like mesh ({elements} elements) in {blocks[0]}x{blocks[1]}x{blocks[2]} "
               f"subdomains, {nb_timed} timed iterations after 1 untimed (FEM.cc:182); {detail}")
@@ -200,105 +227,119 @@ def reference_main(args, rank, world):
             "steps": nb_timed, "warmup": 1, "ms_per_step": 1e3 * elements / value, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_text(grid, args.op, whole.nbElem, whole.nbNodes, whole.nbEdges),
-                       "arm": "the reference's CPU implementation on the host cores (no GPU work)"},
+                       "arm": "the reference's CPU implementation on the host cores (no GPU work); always ONE mesh of the --grid size, "
+                              "whatever --gpus says (the GPU arm's weak scaling multiplies the mesh by N)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": n, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------ path selection (GPU)
+# ------------------------------------------------------------------ checks and side measurements (GPU)
 
-def _host_exchange(ctxs, meshes, dim):
-    """MPI_halo_exchange's message pattern (halo.cc:52-116) between contexts of one process."""
-    import numpy as np
-    send = [c.halo_pack_host() for c in ctxs]
-    for r, (c, m) in enumerate(zip(ctxs, meshes)):
-        recv = np.zeros_like(send[r])
-        for i in range(m.nbIntf):
-            s = int(m.neighborsList[i]) - 1
-            o = meshes[s]
-            q = [k for k in range(o.nbIntf) if o.neighborsList[k] - 1 == r][0]
-            recv[m.intfIndex[i] * dim:m.intfIndex[i + 1] * dim] = send[s][o.intfIndex[q] * dim:o.intfIndex[q + 1] * dim]
-        c.halo_add_host(recv)
-
-
-def probe_ring(args):
-    """Runs in a process of its own (choose_path): the RING kernel against the TILED kernel — which the
-    GPU tests hold to the oracle — on the bench mesh itself, entry by entry, and on a 4-subdomain case
-    with the fused interface split; then both are timed.  Prints one JSON line."""
-    import numpy as np
-    import minifem_b200 as mfb
-    from helpers import RTOL, block_scaled_error, row_scaled_error
-    out = {"ok": False}
-    try:
-        dim = 9 if args.op == "ela" else 1
-        meshes = [mfb.Mesh.generate(9, 8, 7, blocks=(2, 2, 1), rank=r, seed=5) for r in range(4)]
-        setups = [mfb.Setup(m, args.op) for m in meshes]
-        results = {}
-        for path in ("tiled", "ring"):
-            ctxs = [mfb.Context(s, path=path, device=args.device, nbBlocks=4, rank=r, tile_rows=16,
-                                tile_elems=300 if path == "tiled" else 260) for r, s in enumerate(setups)]
-            for c in ctxs:
-                c.assembly_fused()
-            _host_exchange(ctxs, meshes, dim)
-            for c in ctxs:
-                c.prec_inversion_interface()
-            results[path] = [c.download() for c in ctxs]
-            for c in ctxs:
-                c.close()
-        out["split_err"] = max(max(row_scaled_error(results["ring"][r][0], results["tiled"][r][0], setups[r].row, dim),
-                                   block_scaled_error(results["ring"][r][1], results["tiled"][r][1], dim)) for r in range(4))
-        mesh = mfb.Mesh.generate(*args.grid, seed=1)
-        setup = mfb.Setup(mesh, args.op)
-        res = {}
-        for path in ("tiled", "ring"):
-            ctx = mfb.Context(setup, path=path, device=args.device)
-            for _ in range(3):
-                ctx.iteration()
-            ctx.sync()
-            ms = ctx.run_timed(30) / 30
-            v, p = ctx.download()
-            ctx.iteration()
-            v2, p2 = ctx.download()
-            res[path] = (v, p)
-            out[path + "_ms"] = ms
-            out[path + "_reproducible"] = bool(np.array_equal(v, v2) and np.array_equal(p, p2, equal_nan=True))
-            ctx.close()
-        out["values_err"] = row_scaled_error(res["ring"][0], res["tiled"][0], setup.row, dim)
-        out["prec_err"] = block_scaled_error(res["ring"][1], res["tiled"][1], dim)
-        out["rtol"] = RTOL
-        out["ok"] = bool(out["values_err"] <= RTOL and out["prec_err"] <= RTOL and out["split_err"] <= RTOL and
-                         out["ring_reproducible"])
-    except Exception as e:                                   # noqa: BLE001 (the verdict must be printed)
-        out["error"] = repr(e)[:300]
-    print("PROBE " + json.dumps(out), flush=True)
-
-
-def choose_path(args, rank, local):
-    """--path auto.  TILED is the path this repository has measured and profiled.  RING
-    removes most of TILED's shared-memory traffic but had not run on hardware when it was committed, so it
-    has to earn its place on every box: rank 0 runs probe_ring in a subprocess (a fault there cannot touch
-    this process); RING is used only if it agrees with TILED to 1e-12 on the bench mesh and on the
-    multi-subdomain split, repeats bit for bit, and is faster.  The verdict is part of the JSON line."""
-    import subprocess
+def oracle_parity(ctx, setup, mesh, world):
+    """values and prec held by `ctx` (its last iteration) against the CPU oracle on the same subdomain
+    (oracle/minifem_oracle.c, bit-equal to the reference's compiled sources: tests/test_oracle_vs_reference.py).
+    At N > 1 the oracle's prec_init values of the interface nodes are exchanged between the ranks through
+    torch.distributed in the message pattern of MPI_halo_exchange (halo.cc:52-116) and added in its order.
+    Outside every timed region.  Returns the max over ranks."""
     from minifem_b200 import dist as mdist
-    verdict = {"probe": None, "chosen": "tiled"}
-    if rank == 0:
-        cmd = [sys.executable, os.path.abspath(__file__), "--probe-ring", "--device", str(local), "--op", args.op,
-               "--grid"] + [str(g) for g in args.grid]
+    from helpers import RTOL, block_scaled_error, row_scaled_error
+    from oracle_lib import Oracle
+    oracle = Oracle()
+    dim = setup.operatorDim
+    t0 = time.perf_counter()
+    want_v = oracle.assembly(mesh.coord, setup.row, setup.col, setup.elemToNode, setup.operatorID, setup.elemToEdge, setup.colorToElem)
+    p0 = np.ascontiguousarray(oracle.prec_init(want_v, setup.row, setup.col, mesh.nbNodes, dim))
+    if world > 1 and mesh.nbIntfNodes > 0:
+        nodes = np.asarray(mesh.intfNodes, np.int64) - 1
+        send = np.ascontiguousarray(p0.reshape(-1, dim)[nodes]).ravel()          # halo.cc:77-80, pre-exchange values
+        recv = mdist.exchange_host(send, mesh.intfIndex, mesh.neighborsList, dim)
+        np.add.at(p0.reshape(-1, dim), nodes, recv.reshape(-1, dim))             # halo.cc:113-116, in list order
+    want_p = oracle.prec_inversion(p0, setup.row, setup.col, setup.checkBounds, mesh.nbNodes, setup.operatorID)
+    v, p = ctx.download()
+    ev = mdist.max_over_ranks(row_scaled_error(v, want_v, setup.row, dim))
+    ep = mdist.max_over_ranks(block_scaled_error(p, want_p, dim))
+    return {"values_err": ev, "prec_err": ep, "rtol": RTOL, "ok": bool(ev <= RTOL and ep <= RTOL), "ranks": world,
+            "against": "oracle/minifem_oracle.c on every rank's own subdomain, entry by entry (row / block scaled, tests/helpers.py)"
+                       + ("; interface prec summed across ranks as in halo.cc:52-116" if world > 1 else ""),
+            "seconds": round(time.perf_counter() - t0, 1)}
+
+
+def time_paths(mfb, mesh, op, paths, device, steps=20, peak=None):
+    """ms per fused iteration of each path on one GPU for one mesh (side measurements of the `configs` record)."""
+    out = {}
+    E, N = mesh.nbElem, mesh.nbNodes
+    for path in paths:
+        t0 = time.perf_counter()
+        setup = mfb.Setup(mesh, op, coloring=(path == "color"))
+        ctx = mfb.Context(setup, path=path, device=device, use_graph=(path == "color"))
+        build_s = time.perf_counter() - t0
+        for _ in range(3):
+            ctx.iteration()
+        ctx.sync()
+        ms = ctx.run_timed(steps) / steps
+        alg = algorithmic_bytes(op, E, setup.nbEdges, N)
+        out[path] = {"ms_per_step": ms, "value": E / (ms * 1e-3), "frac": alg / (ms * 1e-3) / 1e9 / peak if peak else None,
+                     "setup_s": round(build_s, 2)}
+        if path == "color":
+            out[path]["colors"] = setup.nbTotalColors
+        ctx.close()
+    return out
+
+
+def other_configs(mfb, args, device, peak):
+    """BASELINE.json's configurations 1, 2, 3, 5 and an unstructured mesh, N = 1, every path, with the reference's
+    CPU builds where BASELINE.json names them."""
+    from oracle_lib import Reference, ref_available
+    out = {}
+    paths = ["ring", "tiled", "atomic", "color"]
+    cores = os.cpu_count() or 1
+    lm6 = mfb.Mesh.generate(25, 25, 40, seed=1)
+    for op, key in (("lap", "1_LM6_lap"), ("ela", "2_LM6_ela")):
+        rec = {"workload": workload_text((25, 25, 40), op, lm6.nbElem, lm6.nbNodes, lm6.nbEdges),
+               "gpu": time_paths(mfb, lm6, op, paths, device, 50, peak)}
         try:
-            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
-            lines = [l for l in res.stdout.splitlines() if l.startswith("PROBE ")]
-            verdict["probe"] = json.loads(lines[-1][6:]) if lines else {"ok": False, "error": "no verdict; rc=%d: %s" % (res.returncode, res.stdout[-300:])}
-        except Exception as e:                               # noqa: BLE001
-            verdict["probe"] = {"ok": False, "error": repr(e)[:300]}
-        pr = verdict["probe"]
-        if pr.get("ok") and pr.get("ring_ms", 1e9) < pr.get("tiled_ms", 0.0):
-            verdict["chosen"] = "ring"
-    use_ring = mdist.max_over_ranks(1.0 if verdict["chosen"] == "ring" else 0.0) > 0.5
-    verdict["chosen"] = "ring" if use_ring else "tiled"
-    return verdict
+            if ref_available("ref"):
+                ref = Reference("ref")
+                _, _, cycles, hz = ref.fem_loop([RefSetup(ref, lm6, op)], 10)
+                rec["cpu_ref_np1"] = {"value": lm6.nbElem / (sum(cycles) / hz), "unit": UNIT, "cores": 1,
+                                      "sample": "mpirun -np 1 equivalent: one rank thread, 10 iterations (9 timed, FEM.cc:182), oracle/_ref REF build"}
+            col = run_reference_coloring(op, (25, 25, 40), 10)
+            if col:
+                rec["cpu_coloring"] = {"value": col[0], "unit": UNIT, "cores": cores, "colors": col[1],
+                                       "sample": "one rank, OMP_NUM_THREADS = host cores, 10 iterations; COLORING build as shipped"}
+        except Exception as e:                                   # noqa: BLE001
+            rec["cpu_error"] = repr(e)[:200]
+        out[key] = rec
+    eib = mfb.Mesh.generate(*args.grid, seed=1)
+    out["3_EIB_lap"] = {"workload": workload_text(args.grid, "lap", eib.nbElem, eib.nbNodes, eib.nbEdges),
+                        "gpu": time_paths(mfb, eib, "lap", paths, device, 20, peak),
+                        "note": "colour-by-colour (coloring.cc's colours, one launch per colour in a CUDA graph) against native FP64 atomics; "
+                                "ncu DRAM figures of both kernels: profiles/r2_scatter_ncu.txt"}
+    del eib
+    if args.configs == "all":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from delaunay_mesh import delaunay_arrays
+            from helpers import ArrayMesh
+            coord, e2n, codes = delaunay_arrays(200000, seed=4)
+            dm = ArrayMesh(coord, e2n, coord.size // 3, codes)
+            g = time_paths(mfb, dm, "ela", ["ring", "tiled", "atomic"], device, 20, peak)
+            out["unstructured_delaunay_200k_ela"] = {"workload": f"Delaunay tetrahedralisation of 200,000 random points ({dm.nbElem} elements), elasticity", "gpu": g}
+        except Exception as e:                                   # noqa: BLE001
+            out["unstructured_delaunay_200k_ela"] = {"error": repr(e)[:200]}
+        try:
+            t0 = time.perf_counter()
+            big = mfb.Mesh.generate(200, 200, 200, seed=1)
+            g = time_paths(mfb, big, "ela", ["ring"], device, 10, peak)
+            out["5_8M_ela_1gpu"] = {"workload": workload_text((200, 200, 200), "ela", big.nbElem, big.nbNodes, big.nbEdges), "gpu": g,
+                                    "wall_s": round(time.perf_counter() - t0, 1),
+                                    "note": "the 1-GPU point of the 48 M-tetrahedra sweep; its 8-GPU point is this bench at --gpus 8 "
+                                            "(2 x 2 x 2 blocks of 100^3 cubes = the same 200^3 mesh)"}
+        except Exception as e:                                   # noqa: BLE001
+            out["5_8M_ela_1gpu"] = {"error": repr(e)[:200]}
+    return out
 
 
 # ------------------------------------------------------------------------ our arm (GPU)
@@ -312,9 +353,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         reference_main(args, rank, world)
-        return
-    if args.probe_ring:
-        probe_ring(args)
         return
     if args.gpus != world:
         if args.gpus > 1:
@@ -330,17 +368,12 @@ def main():
     torch.cuda.set_device(local)
     mdist.init_from_env("nccl")
 
-    selection = None
-    if args.path == "auto":
-        selection = choose_path(args, rank, local)
-        args.path = selection["chosen"]
-        os.environ["MFB_BENCH_AUTO_CHOSE"] = args.path
     grid, blocks = global_layout(args, world)
     t0 = time.perf_counter()
     mesh = mfb.Mesh.generate(*grid, blocks=blocks, rank=rank, seed=1)
     setup = mfb.Setup(mesh, args.op, coloring=(args.path == "color"))
     ctx = mfb.Context(setup, path=args.path, device=local, nbBlocks=world, rank=rank, tile_rows=args.tile_rows,
-                      tile_elems=args.tile_elems, use_graph=(args.path == "color"))
+                      tile_elems=args.tile_elems, use_graph=(args.path == "color" or world > 1))
     if world > 1:
         mdist.comm_init(ctx)
     setup_s = time.perf_counter() - t0
@@ -407,30 +440,61 @@ def main():
 
     stats = ctx.plan_stats() if args.path in ("tiled", "ring") else None
     mesh_bytes, plan_bytes = ctx.device_bytes()
+    parity = None
+    if not args.no_parity:
+        ctx.iteration()
+        ctx.sync()
+        parity = oracle_parity(ctx, setup, mesh, world)
     ctx.close()
 
-    other = {}
+    # strong scaling (N > 1): the N = 1 workload itself — the 100^3 mesh — cut into N subdomains, and, for the
+    # single-GPU time of the same box, the undivided mesh on every GPU at once (no communication)
+    strong = None
+    if world > 1 and not args.no_strong and args.scaling == "weak":
+        sgrid = tuple(args.grid)
+        sblocks = mfb.choose_blocks(*sgrid, world)
+        smesh = mfb.Mesh.generate(*sgrid, blocks=sblocks, rank=rank, seed=1)
+        ssetup = mfb.Setup(smesh, args.op)
+        sctx = mfb.Context(ssetup, path=args.path, device=local, nbBlocks=world, rank=rank, use_graph=True)
+        mdist.comm_init(sctx)
+        for _ in range(5):
+            sctx.iteration()
+        sctx.sync()
+        mdist.barrier(); torch.cuda.synchronize()
+        s_ms = mdist.max_over_ranks(sctx.run_timed(args.steps)) / args.steps
+        sctx.iteration(); sctx.sync()
+        s_par = None if args.no_parity else oracle_parity(sctx, ssetup, smesh, world)
+        sctx.close()
+        whole = mfb.Mesh.generate(*sgrid, seed=1)
+        wsetup = mfb.Setup(whole, args.op)
+        wctx = mfb.Context(wsetup, path=args.path, device=local)
+        for _ in range(5):
+            wctx.iteration()
+        wctx.sync()
+        mdist.barrier(); torch.cuda.synchronize()
+        w_ms = mdist.max_over_ranks(wctx.run_timed(args.steps)) / args.steps
+        wctx.close()
+        strong = {"workload": workload_text(sgrid, args.op, whole.nbElem, whole.nbNodes, whole.nbEdges) + f", cut into {sblocks[0]}x{sblocks[1]}x{sblocks[2]} subdomains",
+                  "n_gpus": world, "ms_per_step": s_ms, "value": whole.nbElem / (s_ms * 1e-3), "unit": UNIT,
+                  "one_gpu_ms_per_step": w_ms, "speedup": w_ms / s_ms, "parallel_efficiency": w_ms / s_ms / world,
+                  "parity": s_par,
+                  "note": "device time (CUDA events), max over ranks; one_gpu = the undivided mesh on every GPU of this run at once"}
+
+    peak, peak_src = measured_peak()
+    other, configs = {}, None
     if world == 1 and not args.no_other_paths:
-        for path in ("tiled", "atomic", "color"):
-            if path == args.path:
-                continue
-            s2 = mfb.Setup(mesh, args.op, coloring=(path == "color"))
-            c2 = mfb.Context(s2, path=path, device=local, use_graph=(path == "color"))
-            for _ in range(3):
-                c2.iteration()
-            c2.sync()
-            other[path] = {"ms_per_step": c2.run_timed(10) / 10}
-            other[path]["value"] = E / (other[path]["ms_per_step"] * 1e-3)
-            if path == "color":
-                other[path]["colors"] = s2.nbTotalColors
-            c2.close()
+        other = time_paths(mfb, mesh, args.op, [q for q in ("ring", "tiled", "atomic", "color") if q != args.path], local, 10, peak)
+    if world == 1 and args.configs != "none" and rank == 0:
+        try:
+            configs = other_configs(mfb, args, local, peak)
+        except Exception as e:                                   # noqa: BLE001 (the bench line must still appear)
+            configs = {"error": repr(e)[:300]}
 
     if world > 1:
         import torch.distributed as tdist
         tdist.destroy_process_group()
     if rank != 0:
         return
-    peak, peak_src = measured_peak()
     alg = algorithmic_bytes(args.op, E, Z, N)
     achieved = alg / (ms_step * 1e-3) / 1e9
     workload = workload_text(args.grid, args.op, E, N, Z)
@@ -447,18 +511,22 @@ def main():
                          "algorithmic_bytes_per_launch": alg,
                          "note": "one fused kernel launch per step at N=1; duration = CUDA events over the timed region / steps"},
             "e2e": e2e, "e2e_device_resident": e2e_resident, "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
-            "other_paths": other}
-    if selection:
-        line["path_selection"] = selection
-    elif os.environ.get("MFB_BENCH_AUTO_CHOSE") == "tiled-after-ring-failure":
-        line["path_selection"] = {"chosen": "tiled", "note": "RING passed its probe but its measurement run failed; see stderr"}
+            "parity": parity, "other_paths": other}
+    if strong:
+        line["strong"] = strong
+    if configs:
+        line["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
         cores = args.cpu_ranks or (os.cpu_count() or 1)
         try:
-            cv, n, kind, detail, elements, cb = run_reference_cpu(args.op, tuple(args.grid), 3, min(cores, 64))
+            cv, n, kind, detail, elements, cb = run_reference_cpu(args.op, tuple(args.grid), 11, min(cores, 64))
             line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": n, "kind": kind,
                                     "sample": f"whole {elements}-element mesh in {cb[0]}x{cb[1]}x{cb[2]} subdomains (one rank thread each), "
-                                              f"2 timed iterations after 1 untimed; {detail}"}
+                                              f"10 timed iterations after 1 untimed; {detail}"}
+            ov, on, okind, odetail, _, _ = run_reference_cpu(args.op, tuple(args.grid), 11, min(cores, 64), kind="ref_opt")
+            if okind == "reference":
+                line["cpu_baseline_optimized"] = {"value": ov, "unit": UNIT, "cores": on, "kind": okind,
+                                                  "sample": f"the same mesh and ranks, 10 timed iterations after 1 untimed; {odetail}"}
             col = run_reference_coloring(args.op, tuple(args.grid), 2)
             if col:
                 line["cpu_baseline_coloring"] = {
@@ -478,15 +546,4 @@ def main():
 
 
 if __name__ == "__main__":
-    try:
-        main()
-    except Exception as exc:                                     # noqa: BLE001
-        # --path auto picked RING after its probe and the measurement still failed: the line must not be
-        # lost to a path that has one round of hardware history less than TILED — start over on TILED in a
-        # fresh process (a CUDA fault leaves this one without a usable context).  Single process only: under
-        # torchrun the other ranks are still inside their collectives.
-        if os.environ.get("MFB_BENCH_AUTO_CHOSE") == "ring" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-            print(f"bench.py: the RING run failed ({exc!r}); measuring TILED instead", file=sys.stderr, flush=True)
-            os.environ["MFB_BENCH_AUTO_CHOSE"] = "tiled-after-ring-failure"
-            os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--path", "tiled"])
-        raise
+    main()

@@ -281,6 +281,8 @@ struct mfb_ctx {
     RingPlan ringStats;             // counters only
     double *dNorm = nullptr;        // [partials][2 results], allocated by the first mfb_ctx_norms
     int haloCoresident = 0;         // multi-GPU overlap scheme, see do_iteration
+    int haloReserveCtas = 8;       // RING: CTAs the persistent interior grid leaves free for the kernels of the exchange
+    int eagerIterations = 0;       // fused iterations run before the multi-GPU graph is captured
     int interiorTilesPerCta = 4;   // measured at N=2: 1 -> 0.71 ms, 4 -> 0.645, 8 -> 0.647 (kernel alone 0.636 in that build)
     int64_t meshBytes = 0, planBytes = 0, launches = 0, graphLaunches = 0;
 
@@ -397,6 +399,7 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     c->ringStats = hp;
     if (const char *v = getenv ("MFB_HALO_OVERLAP")) c->haloCoresident = std::string (v) == "coresident";
     if (const char *v = getenv ("MFB_INTERIOR_TILES_PER_CTA")) c->interiorTilesPerCta = std::max (atoi (v), 1);
+    if (const char *v = getenv ("MFB_HALO_RESERVE_CTAS")) c->haloReserveCtas = std::max (atoi (v), 0);
     c->tiledSmem = ring_smem_bytes (c->operatorID, c->ringPlan);
     if (c->tiledSmem > 227 * 1024) return fail (MFB_ERR_ARG, "ring plan needs more than 227 KB of shared memory per CTA; lower tileRows / tileElems");
     MFB_CUDA (ring_configure (c->operatorID));
@@ -536,7 +539,11 @@ int do_iteration (mfb_ctx *c)
         MFB_CUDA (launch_write_once (c, 0, nIntfTiles, c->tiledCtas, 1, c->stream));
         if (nIntfTiles > 0) c->launches++;
         MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));
-        const int interiorCtas = std::max ((nInterior + c->interiorTilesPerCta - 1) / c->interiorTilesPerCta, 1);
+        // RING: the warp-specialised kernel pipelines plan records three tiles ahead and wants a persistent grid;
+        // it leaves a few SMs free instead (MFB_HALO_RESERVE_CTAS, default 8 CTAs = 4 SMs) so that the pack, NCCL
+        // and add kernels of the exchange start at once.
+        const int interiorCtas = c->ring ? std::max (c->tiledCtas - c->haloReserveCtas, 1)
+                                         : std::max ((nInterior + c->interiorTilesPerCta - 1) / c->interiorTilesPerCta, 1);
         MFB_CUDA (launch_write_once (c, nIntfTiles, nInterior, interiorCtas, 1, c->stream));
         if (nInterior > 0) c->launches++;
         MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
@@ -753,6 +760,18 @@ extern "C" int mfb_ctx_assembly_interval (mfb_ctx *c, int firstElem, int lastEle
     CTX_ENTER (c);
     if (c->path == MFB_PATH_TILED) return fail (MFB_ERR_STATE, "mfb_ctx_assembly_interval: element intervals exist on the ATOMIC / COLOR paths only");
     if (firstElem < 0 || lastElem >= c->nbElem) return fail (MFB_ERR_ARG, "mfb_ctx_assembly_interval: interval out of range");
+    if (c->path == MFB_PATH_COLOR) {
+        // The plain += of the COLOR kernel is only conflict-free inside one colour (coloring.cc): an interval that
+        // spans colours — (0, nbElem - 1), a D&C leaf — is cut at the colorToElem boundaries, one launch per piece,
+        // in colour order like coloring_assembly (src/assembly.cc:593-611).
+        for (int color = 0; color < c->nbTotalColors; color++) {
+            const int lo = std::max (firstElem, c->colorToElem[color]), hi = std::min (lastElem, c->colorToElem[color + 1] - 1);
+            if (lo > hi) continue;
+            const int rc = do_scatter_interval (c, lo, hi - lo + 1);
+            if (rc) return rc;
+        }
+        return MFB_OK;
+    }
     return do_scatter_interval (c, firstElem, lastElem - firstElem + 1);
 }
 
@@ -797,20 +816,33 @@ extern "C" int mfb_ctx_iteration (mfb_ctx *c)
     CTX_ENTER (c);
     int rc = record (c, 4, true);
     if (rc) return rc;
-    const bool graphable = c->useGraph && c->nbBlocks < 2;
+    // The whole iteration as one CUDA graph.  With several subdomains the graph holds both
+    // streams — interface tiles, interior tiles, pack, the NCCL group, add, interface inversion — joined by the two
+    // events; NCCL is given two eager iterations first (it allocates on first use), and a capture it refuses
+    // falls back to eager launches for good.
+    const bool multi = c->nbBlocks > 1 && c->nbIntf > 0;
+    const bool graphable = c->useGraph && (!multi || c->eagerIterations >= 2);
     if (graphable) {
         if (!c->graphExec) {
             cudaGraph_t graph = nullptr;
             const int64_t before = c->launches;
-            MFB_CUDA (cudaStreamBeginCapture (c->stream, cudaStreamCaptureModeThreadLocal));
+            MFB_CUDA (cudaStreamBeginCapture (c->stream, multi ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
             rc = do_iteration (c);
             cudaError_t e = cudaStreamEndCapture (c->stream, &graph);
             c->graphLaunches = c->launches - before;      // kernels one replay runs
             c->launches = before;
-            if (rc) { if (graph) cudaGraphDestroy (graph); return rc; }
-            MFB_CUDA (e);
-            MFB_CUDA (cudaGraphInstantiate (&c->graphExec, graph, 0));
-            cudaGraphDestroy (graph);
+            if (!rc && e == cudaSuccess) e = cudaGraphInstantiate (&c->graphExec, graph, 0);
+            if (graph) cudaGraphDestroy (graph);
+            if (rc || e != cudaSuccess) {
+                if (!multi) { if (rc) return rc; MFB_CUDA (e); }
+                cudaGetLastError ();
+                c->graphExec = nullptr;
+                c->useGraph = 0;                          // eager from now on
+                g_lastError = "mfb_ctx_iteration: graph capture of the multi-GPU iteration refused, running eagerly";
+                rc = do_iteration (c);
+                if (rc) return rc;
+                return record (c, 4, false);
+            }
         }
         MFB_CUDA (cudaGraphLaunch (c->graphExec, c->stream));
         c->launches += c->graphLaunches;
@@ -818,6 +850,7 @@ extern "C" int mfb_ctx_iteration (mfb_ctx *c)
     else {
         rc = do_iteration (c);
         if (rc) return rc;
+        c->eagerIterations++;
     }
     return record (c, 4, false);
 }

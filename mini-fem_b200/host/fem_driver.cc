@@ -8,7 +8,7 @@
 //
 // Compile-time switches of the reference become environment variables:
 //   MINIFEM_DATA_PATH   DATA_PATH of build/iMake:20            (default ./data)
-//   MINIFEM_PATH        tiled | atomic | color | ring          (default tiled; color = the
+//   MINIFEM_PATH        ring | tiled | atomic | color          (default ring; color = the
 //                       COLORING build: colour + permute before the CSR, main.cc:209-236)
 //   MINIFEM_FUSED       1 = one fused launch per iteration, reported like the
 //                       multithreaded-comm build reports (FEM.cc:179-180: everything under
@@ -30,6 +30,8 @@
 #include <iostream>
 #include <string>
 #include <thread>
+#include <sys/stat.h>
+#include <ctime>
 #include <vector>
 #if defined(__x86_64__)
 #include <x86intrin.h>
@@ -130,11 +132,29 @@ string env_str (const char *name, const string &fallback)
     return v ? string (v) : fallback;
 }
 
+// Rendezvous files of one run: named after a token the ranks of a run share (MINIFEM_RUN_TOKEN, else torchrun's
+// run id and port), never older than this process (a file left behind by a crashed run is ignored), and
+// removed by rank 0 when the run ends.
+const time_t kProcessStart = time (nullptr);
+
+string run_token ()
+{
+    const char *t = getenv ("MINIFEM_RUN_TOKEN");
+    if (t) return string ("_") + t;
+    string token;
+    if (const char *id = getenv ("TORCHELASTIC_RUN_ID")) token += string ("_") + id;
+    if (const char *port = getenv ("MASTER_PORT")) token += string ("_") + port;
+    return token;
+}
+
 void wait_for_file (const string &path)
 {
     for (int tries = 0; tries < 60000; tries++) {
-        ifstream f (path, ios::binary);
-        if (f.good ()) return;
+        struct stat st;
+        if (stat (path.c_str (), &st) == 0 && st.st_mtime + 2 >= kProcessStart) {
+            ifstream f (path, ios::binary);
+            if (f.good ()) return;
+        }
         this_thread::sleep_for (chrono::milliseconds (5));
     }
     die ("Error: timed out waiting for " + path);
@@ -148,18 +168,20 @@ void get_average_cycles (const Timer &asmT, const Timer &initT, const Timer &hal
                          invT.get_avg_cycles ()}, global[4];
     memcpy (global, local, sizeof local);
     if (nbBlocks > 1) {
-        const string mine = rendezvous + "/cycles_" + to_string (rank);
+        const string mine = rendezvous + "/cycles" + run_token () + "_" + to_string (rank);
         { ofstream f (mine + ".tmp", ios::binary); f.write ((const char*)local, sizeof local); }
         rename ((mine + ".tmp").c_str (), mine.c_str ());
         if (rank == 0) {
             for (int r = 1; r < nbBlocks; r++) {
-                const string theirs = rendezvous + "/cycles_" + to_string (r);
+                const string theirs = rendezvous + "/cycles" + run_token () + "_" + to_string (r);
                 wait_for_file (theirs);
                 uint64_t other[4];
-                ifstream f (theirs, ios::binary);
-                f.read ((char*)other, sizeof other);
+                { ifstream f (theirs, ios::binary); f.read ((char*)other, sizeof other); }
                 for (int k = 0; k < 4; k++) if (other[k] > global[k]) global[k] = other[k];
+                remove (theirs.c_str ());
             }
+            remove (mine.c_str ());
+            remove ((rendezvous + "/nccl_id" + run_token ()).c_str ());      // every rank has initialised its communicator long ago
         }
     }
     if (rank == 0) {
@@ -260,16 +282,16 @@ int main (int argCount, char **argValue)
     // Process initialization (main.cc:98-114): one process per GPU
     const int nbBlocks = max (env_int ("WORLD_SIZE", 1), 1), rank = env_int ("RANK", 0);
     const string dataPath = env_str ("MINIFEM_DATA_PATH", "./data");
-    const string pathName = env_str ("MINIFEM_PATH", "tiled");
+    const string pathName = env_str ("MINIFEM_PATH", "ring");
     const string rendezvous = env_str ("MINIFEM_RENDEZVOUS", ".");
     const bool fused = env_int ("MINIFEM_FUSED", 0) != 0;
     const int device = env_int ("MINIFEM_DEVICE", env_int ("LOCAL_RANK", 0));
     const bool gpuSetup = env_int ("MINIFEM_GPU_SETUP", 0) != 0;
-    int path = MFB_PATH_TILED;
+    int path = MFB_PATH_RING;
     if (pathName == "atomic") path = MFB_PATH_ATOMIC;
     else if (pathName == "color") path = MFB_PATH_COLOR;
-    else if (pathName == "ring") path = MFB_PATH_RING;
-    else if (pathName != "tiled") die ("Incorrect MINIFEM_PATH \"" + pathName + "\" (tiled, atomic, color or ring).");
+    else if (pathName == "tiled") path = MFB_PATH_TILED;
+    else if (pathName != "ring") die ("Incorrect MINIFEM_PATH \"" + pathName + "\" (tiled, atomic, color or ring).");
 
     Timer timer;
     int nbIter;
@@ -363,8 +385,11 @@ int main (int argCount, char **argValue)
     check (mfb_ctx_create (&prob, &opt, &ctx), "GPU context");
     if (nbBlocks > 1) {
         unsigned char id[MFB_COMM_ID_BYTES];
-        const string idFile = rendezvous + "/nccl_id";
+        // the file names carry a per-run token (torchrun's run id / rendezvous port) so that a second run in
+        // the same directory never reads the files of the first; rank 0 removes them when it is done
+        const string idFile = rendezvous + "/nccl_id" + run_token ();
         if (rank == 0) {
+            remove (idFile.c_str ());                                  // a leftover of an interrupted run
             check (mfb_comm_unique_id (id), "NCCL id");
             { ofstream f (idFile + ".tmp", ios::binary); f.write ((const char*)id, sizeof id); }
             rename ((idFile + ".tmp").c_str (), idFile.c_str ());

@@ -700,7 +700,7 @@ int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
     }
     const int nbTiles = (int)tileStart.size () - 1;
     std::vector<TileResult> results ((size_t)nbTiles);
-    const int team = std::max (1, std::min (omp_get_max_threads (), 16));
+    const int team = plan_team_size ();
     #pragma omp parallel num_threads(team)
     {
         std::vector<int> nodeLocal ((size_t)nbNodes, -1), colStamp ((size_t)nbNodes, 0);
@@ -737,7 +737,7 @@ int build_ring_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         plan.slabWriteWavefronts += r.slabWf; plan.slabWriteIdeal += r.slabIdeal;
     }
     plan.blob.assign ((size_t)plan.tileOffset[nbTiles], 0);
-    #pragma omp parallel for schedule(dynamic, 64)
+    #pragma omp parallel for schedule(dynamic, 64) num_threads(plan_team_size ())
     for (int k = 0; k < nbTiles; k++) {
         TileResult &r = results[execOrder[k]];
         memcpy (plan.blob.data () + plan.tileOffset[k], r.blob.data (), r.blob.size ());

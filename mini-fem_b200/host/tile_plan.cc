@@ -2,6 +2,9 @@
 
 #include <omp.h>
 
+#include <cstdlib>
+#include <thread>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -9,6 +12,17 @@
 #include "mesh_topology.h"
 
 namespace mfb {
+
+int plan_team_size ()
+{
+    if (const char *v = getenv ("MFB_PLAN_THREADS")) return std::max (1, std::min (atoi (v), 256));
+    int hw = (int)std::thread::hardware_concurrency ();
+    if (hw <= 0) hw = omp_get_num_procs ();
+    int local = 1;
+    if (const char *v = getenv ("LOCAL_WORLD_SIZE")) local = std::max (1, atoi (v));
+    return std::max (1, std::min (hw / local, 32));
+}
+
 
 // smallest s = 4 (mod 16) such that s - 4 (the Laplacian's plane pitch) holds maxElems + 3 ids
 // and the 16 zero slots
@@ -201,7 +215,7 @@ int cut_node_tiles (int nbNodes, int nbElem, const int *elemToNode, const int *r
     double extent = std::max ({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-300});
     const double scale = 2097151.0 / extent;
     std::vector<std::pair<uint64_t, int>> order ((size_t)nbNodes);
-    #pragma omp parallel for schedule(static)
+    #pragma omp parallel for schedule(static) num_threads(plan_team_size ())
     for (int n = 0; n < nbNodes; n++) {
         uint64_t q[3];
         for (int a = 0; a < 3; a++) q[a] = (uint64_t)((coord[(size_t)n * 3 + a] - lo[a]) * scale);
@@ -293,7 +307,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
     std::vector<TileScratch> scratch ((size_t)nbTiles);
     // each thread keeps two dense global->local maps; cap the team so that the maps of a
     // 48 M-element mesh stay within a few GB on a many-core host
-    const int team = std::max (1, std::min (omp_get_max_threads (), 16));
+    const int team = plan_team_size ();
     #pragma omp parallel num_threads(team)
     {
         std::vector<int> nodeLocal ((size_t)nbNodes, -1), elemLocal ((size_t)nbElem, -1);
@@ -601,7 +615,7 @@ int build_tile_plan (int nbNodes, int nbElem, const int *elemToNode, const int *
         plan.nbPaddedSteps += s.paddedSteps;
     }
     plan.blob.assign ((size_t)plan.tileOffset[nbTiles], 0);
-    #pragma omp parallel for schedule(dynamic, 64)
+    #pragma omp parallel for schedule(dynamic, 64) num_threads(plan_team_size ())
     for (int k = 0; k < nbTiles; k++) {
         const TileScratch &s = scratch[execOrder[k]];
         uint8_t *base = plan.blob.data () + plan.tileOffset[k];

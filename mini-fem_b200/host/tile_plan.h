@@ -31,6 +31,13 @@
 
 namespace mfb {
 
+// Threads of the plan builders.  Launchers such as torchrun export OMP_NUM_THREADS=1 to every rank, which would
+// make a plan of an EIB-size subdomain take half a minute; the builders are private to this library, so they
+// size their own team: MFB_PLAN_THREADS if set, else the host's hardware threads divided by the ranks of this
+// node (LOCAL_WORLD_SIZE), between 1 and 32.
+int plan_team_size ();
+
+
 // First 48 bytes of a tile blob.  Offsets are in bytes from the start of the blob and
 // multiples of 16.  The row table follows the header immediately.
 struct TileBlobHeader {

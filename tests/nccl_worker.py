@@ -30,9 +30,9 @@ for op in ("lap", "ela"):
                          [m.neighborsList for m in meshes], dim)
     s = setups[rank]
     want_p = oracle.prec_inversion(precs[rank], s.row, s.col, s.checkBounds, s.mesh.nbNodes, s.operatorID)
-    for path in ("tiled", "atomic"):
+    for path in ("ring", "tiled", "atomic"):
         ctx = mfb.Context(s, path=path, device=int(os.environ.get("LOCAL_RANK", rank)), nbBlocks=world, rank=rank,
-                          tile_rows=32, tile_elems=400)
+                          tile_rows=32 if path != "ring" else 16, tile_elems=400 if path != "ring" else 300)
         mdist.comm_init(ctx)
         for mode in ("fused", "staged"):
             if mode == "fused":

@@ -11,11 +11,12 @@ sys.path.insert(0, os.path.join(ROOT, "mini-fem_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import minifem_b200 as mfb                                                          # noqa: E402
-from helpers import RTOL, ArrayMesh, block_scaled_error, random_tet_mesh, row_scaled_error   # noqa: E402
+from helpers import (RTOL, ArrayMesh, assert_close_or_conditioned, assert_prec_close_or_conditioned, block_scaled_error,   # noqa: E402
+                     extended_truth, extended_truth_prec, random_tet_mesh, row_scaled_error)
 from oracle_lib import Oracle                                                       # noqa: E402
 
 
-SLIVER_RTOL = 1e-10      # random 4-subsets of points: arbitrarily flat elements, see tests/test_ring_plan.py
+SLIVER = "sliver"        # random 4-subsets of points: arbitrarily flat elements, judged against helpers.extended_truth
 
 
 def check(oracle, name, setup, fused=True, rtol=RTOL, **ctx_args):
@@ -38,7 +39,13 @@ def check(oracle, name, setup, fused=True, rtol=RTOL, **ctx_args):
     launches = ctx.launch_count()
     ctx.close()
     print(f"ring {name}: values {ev:.2e} prec {ep:.2e} launches {launches}", flush=True)
-    assert ev <= rtol and ep <= rtol and launches > 0, f"{name}: differs from the oracle"
+    assert launches > 0
+    if rtol == SLIVER:
+        truth = extended_truth(setup)
+        assert_close_or_conditioned(v, want_v, truth, setup.row, dim, name)
+        assert_prec_close_or_conditioned(p, want_p, extended_truth_prec(setup, truth), dim, name)
+    else:
+        assert ev <= rtol and ep <= rtol, f"{name}: differs from the oracle"
 
 
 def main():
@@ -61,9 +68,9 @@ def main():
         check(oracle, f"{op} plan order", mfb.Setup(mesh, op), bank_aware=False)
         coord, e2n = random_tet_mesh(rng, 60, 150)
         codes = rng.choice([0, 0, 0, 52, 53, 54, 10], size=60).astype(np.int32)
-        check(oracle, f"{op} random tets", mfb.Setup(ArrayMesh(coord, e2n, 60, codes), op), rtol=SLIVER_RTOL, tile_rows=8, tile_elems=400)
+        check(oracle, f"{op} random tets", mfb.Setup(ArrayMesh(coord, e2n, 60, codes), op), rtol=SLIVER, tile_rows=8, tile_elems=400)
         coord, e2n = random_tet_mesh(rng, 25, 400)
-        check(oracle, f"{op} dense random tets (chains with breaks)", mfb.Setup(ArrayMesh(coord, e2n, 25), op), rtol=SLIVER_RTOL, tile_rows=25, tile_elems=640)
+        check(oracle, f"{op} dense random tets (chains with breaks)", mfb.Setup(ArrayMesh(coord, e2n, 25), op), rtol=SLIVER, tile_rows=25, tile_elems=640)
     # four subdomains on one GPU, interface values through the host halves of the exchange: interface rows
     # leave the fused kernel raw, everything else inverted (as test_gpu_multirank.py does for TILED)
     grid, blocks = (9, 8, 7), (2, 2, 1)
