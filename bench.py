@@ -344,9 +344,31 @@ def other_configs(mfb, args, device, peak):
 
 # ------------------------------------------------------------------------ our arm (GPU)
 
+class Watchdog(threading.Thread):
+    """A step that makes no progress for `limit` seconds ends the process with a message instead of hanging the
+    box (a multi-GPU exchange that never completes would otherwise sit there until the driver's own limit)."""
+
+    def __init__(self, limit=420.0):
+        super().__init__(daemon=True)
+        self.limit, self.last, self.what = limit, time.monotonic(), "start"
+
+    def stage(self, what):
+        self.last, self.what = time.monotonic(), what
+
+    def run(self):
+        while True:
+            time.sleep(2.0)
+            if time.monotonic() - self.last > self.limit:
+                print(f"bench.py: no progress for {self.limit:.0f} s in stage '{self.what}' (rank {os.environ.get('RANK', '0')}); giving up",
+                      file=sys.stderr, flush=True)
+                os._exit(3)
+
+
 def main():
     global METRIC
     args = parse_args()
+    dog = Watchdog()
+    dog.start()
     if args.op == "lap":
         METRIC = "EIB lap assembly+precond elements/s"
     rank = int(os.environ.get("RANK", "0"))
@@ -369,11 +391,12 @@ def main():
     mdist.init_from_env("nccl")
 
     grid, blocks = global_layout(args, world)
+    dog.stage("setup")
     t0 = time.perf_counter()
     mesh = mfb.Mesh.generate(*grid, blocks=blocks, rank=rank, seed=1)
     setup = mfb.Setup(mesh, args.op, coloring=(args.path == "color"))
     ctx = mfb.Context(setup, path=args.path, device=local, nbBlocks=world, rank=rank, tile_rows=args.tile_rows,
-                      tile_elems=args.tile_elems, use_graph=(args.path == "color" or world > 1))
+                      tile_elems=args.tile_elems, use_graph=True)
     if world > 1:
         mdist.comm_init(ctx)
     setup_s = time.perf_counter() - t0
@@ -384,6 +407,7 @@ def main():
     if sampler and sampler.ok:
         sampler.start()
 
+    dog.stage("warm-up and timed region")
     for _ in range(max(args.warmup, 3)):
         ctx.iteration()
     ctx.sync()
@@ -402,6 +426,7 @@ def main():
 
     # end to end through the host-buffer entry point: H2D coord, iteration, D2H values + prec
     e2e, e2e_resident = None, None
+    dog.stage("end-to-end legs")
     if args.e2e_steps > 0:
         pins = [mfb.PinnedArray(N * 3), mfb.PinnedArray(ctx.nbValues), mfb.PinnedArray(ctx.nbPrec)]
         pins[0].array[:] = mesh.coord
@@ -441,6 +466,7 @@ def main():
     stats = ctx.plan_stats() if args.path in ("tiled", "ring") else None
     mesh_bytes, plan_bytes = ctx.device_bytes()
     parity = None
+    dog.stage("parity against the oracle")
     if not args.no_parity:
         ctx.iteration()
         ctx.sync()
@@ -450,6 +476,7 @@ def main():
     # strong scaling (N > 1): the N = 1 workload itself — the 100^3 mesh — cut into N subdomains, and, for the
     # single-GPU time of the same box, the undivided mesh on every GPU at once (no communication)
     strong = None
+    dog.stage("strong scaling")
     if world > 1 and not args.no_strong and args.scaling == "weak":
         sgrid = tuple(args.grid)
         sblocks = mfb.choose_blocks(*sgrid, world)
@@ -481,6 +508,8 @@ def main():
                   "note": "device time (CUDA events), max over ranks; one_gpu = the undivided mesh on every GPU of this run at once"}
 
     peak, peak_src = measured_peak()
+    dog.stage("other paths and configurations")
+    dog.limit = 900.0
     other, configs = {}, None
     if world == 1 and not args.no_other_paths:
         other = time_paths(mfb, mesh, args.op, [q for q in ("ring", "tiled", "atomic", "color") if q != args.path], local, 10, peak)
@@ -516,6 +545,7 @@ def main():
         line["strong"] = strong
     if configs:
         line["configs"] = configs
+    dog.stage("CPU baselines")
     if world == 1 and not args.no_cpu_baseline:
         cores = args.cpu_ranks or (os.cpu_count() or 1)
         try:

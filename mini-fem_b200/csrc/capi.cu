@@ -283,6 +283,7 @@ struct mfb_ctx {
     int haloCoresident = 0;         // multi-GPU overlap scheme, see do_iteration
     int haloReserveCtas = 8;       // RING: CTAs the persistent interior grid leaves free for the kernels of the exchange
     int eagerIterations = 0;       // fused iterations run before the multi-GPU graph is captured
+    bool multiGraph = false;       // MFB_MULTI_GPU_GRAPH=1: capture the two-stream iteration with its NCCL group (opt-in)
     int interiorTilesPerCta = 4;   // measured at N=2: 1 -> 0.71 ms, 4 -> 0.645, 8 -> 0.647 (kernel alone 0.636 in that build)
     int64_t meshBytes = 0, planBytes = 0, launches = 0, graphLaunches = 0;
 
@@ -400,6 +401,7 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     if (const char *v = getenv ("MFB_HALO_OVERLAP")) c->haloCoresident = std::string (v) == "coresident";
     if (const char *v = getenv ("MFB_INTERIOR_TILES_PER_CTA")) c->interiorTilesPerCta = std::max (atoi (v), 1);
     if (const char *v = getenv ("MFB_HALO_RESERVE_CTAS")) c->haloReserveCtas = std::max (atoi (v), 0);
+    if (const char *v = getenv ("MFB_MULTI_GPU_GRAPH")) c->multiGraph = atoi (v) != 0;
     c->tiledSmem = ring_smem_bytes (c->operatorID, c->ringPlan);
     if (c->tiledSmem > 227 * 1024) return fail (MFB_ERR_ARG, "ring plan needs more than 227 KB of shared memory per CTA; lower tileRows / tileElems");
     MFB_CUDA (ring_configure (c->operatorID));
@@ -821,7 +823,7 @@ extern "C" int mfb_ctx_iteration (mfb_ctx *c)
     // events; NCCL is given two eager iterations first (it allocates on first use), and a capture it refuses
     // falls back to eager launches for good.
     const bool multi = c->nbBlocks > 1 && c->nbIntf > 0;
-    const bool graphable = c->useGraph && (!multi || c->eagerIterations >= 2);
+    const bool graphable = c->useGraph && (!multi || (c->multiGraph && c->eagerIterations >= 2));
     if (graphable) {
         if (!c->graphExec) {
             cudaGraph_t graph = nullptr;

@@ -179,7 +179,29 @@ def extended_truth_prec(setup, values_truth):
     return prec.reshape(-1)
 
 
-def assert_prec_close_or_conditioned(got, want, truth, dim, what=""):
+def diag_conditioning(setup, values):
+    """rho_i = max |K_ij| over row i / max |K_ii|: how much larger than the diagonal block the largest block of the
+    row is.  <= ~3 on FEM-quality meshes; unbounded on random tetrahedra (a flat element gives its blunt node a
+    huge gradient, hence huge couplings K_ij next to a moderate K_ii)."""
+    dim = setup.operatorDim
+    row, col = np.asarray(setup.row, np.int64), np.asarray(setup.col, np.int64)
+    blocks = np.abs(np.asarray(values, np.float64).reshape(-1, dim)).max(axis=1)
+    rho = np.zeros(setup.mesh.nbNodes)
+    for i in range(setup.mesh.nbNodes):
+        seg = col[row[i]:row[i + 1]]
+        hit = np.nonzero(seg == i + 1)[0]
+        if hit.size and blocks[row[i] + hit[0]] > 0:
+            rho[i] = blocks[row[i]:row[i + 1]].max() / blocks[row[i] + hit[0]]
+    return rho
+
+
+def assert_prec_close_or_conditioned(got, want, truth, dim, what="", rho=None):
+    """1e-12 against the reference's preconditioner block, or — on ill-shaped meshes — against the 80-bit
+    truth within max(1e-12, SLIVER_FACTOR x the reference's own error) x max(1, rho_i).  The factor rho_i is
+    the RING path's: its diagonal block is minus the sum of the row's off-diagonal blocks (zero row sums of
+    the element matrices), so it inherits the absolute error the row's LARGEST block is allowed, rho_i times
+    larger relative to the diagonal, where the reference sums |grad_i|^2 terms directly
+    (helpers.diag_conditioning: rho <= ~3 on FEM-quality meshes, where every path is held to 1e-12 outright)."""
     direct = block_scaled_error(got, want, dim)
     if direct <= RTOL:
         return direct
@@ -187,11 +209,16 @@ def assert_prec_close_or_conditioned(got, want, truth, dim, what=""):
     def err(x):
         x = np.asarray(x, np.float64).astype(np.longdouble).reshape(-1, dim)
         fin = np.isfinite(t).all(axis=1) & np.isfinite(x).all(axis=1)
-        scale = np.abs(t[fin]).max(axis=1)
-        e = np.abs(x[fin] - t[fin]).max(axis=1)
-        ok = scale > 0
-        return float((e[ok] / scale[ok]).max()) if ok.any() else 0.0
+        scale = np.abs(t).max(axis=1)
+        e = np.zeros(t.shape[0])
+        ok = fin & (scale > 0)
+        e[ok] = (np.abs(x[ok] - t[ok]).max(axis=1) / scale[ok]).astype(np.float64)
+        return e
     e_ref, e_got = err(want), err(got)
-    assert e_ref > RTOL / SLIVER_FACTOR, f"{what}: prec {direct:.2e} from the reference although the reference is within {e_ref:.2e} of the exact formula"
-    assert e_got <= SLIVER_FACTOR * e_ref, f"{what}: prec {e_got:.2e} from the exact formula, the reference {e_ref:.2e}"
+    bound = np.full(t.shape[0], max(RTOL, SLIVER_FACTOR * float(e_ref.max())))
+    if rho is not None:
+        bound = bound * np.maximum(1.0, np.asarray(rho))
+    worst = int(np.argmax(e_got - bound))
+    assert np.all(e_got <= bound), (f"{what}: prec of node {worst} is {e_got[worst]:.2e} from the exact formula (reference: {e_ref[worst]:.2e}, "
+                                    f"rho {0 if rho is None else rho[worst]:.1e}, bound {bound[worst]:.2e})")
     return direct

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import minifem_b200 as mfb                                                          # noqa: E402
 from helpers import (RTOL, ArrayMesh, assert_close_or_conditioned, assert_prec_close_or_conditioned, block_scaled_error,   # noqa: E402
-                     extended_truth, extended_truth_prec, random_tet_mesh, row_scaled_error)
+                     diag_conditioning, extended_truth, extended_truth_prec, random_tet_mesh, row_scaled_error)
 from oracle_lib import Oracle                                                       # noqa: E402
 
 
@@ -43,7 +43,7 @@ def check(oracle, name, setup, fused=True, rtol=RTOL, **ctx_args):
     if rtol == SLIVER:
         truth = extended_truth(setup)
         assert_close_or_conditioned(v, want_v, truth, setup.row, dim, name)
-        assert_prec_close_or_conditioned(p, want_p, extended_truth_prec(setup, truth), dim, name)
+        assert_prec_close_or_conditioned(p, want_p, extended_truth_prec(setup, truth), dim, name, rho=diag_conditioning(setup, want_v))
     else:
         assert ev <= rtol and ep <= rtol, f"{name}: differs from the oracle"
 

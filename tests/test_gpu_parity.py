@@ -10,7 +10,7 @@ import pytest
 
 import minifem_b200 as mfb
 from helpers import (RTOL, ArrayMesh, assert_close_or_conditioned, assert_prec_close_or_conditioned, block_scaled_error,
-                     extended_truth, extended_truth_prec, random_tet_mesh, row_scaled_error)
+                     diag_conditioning, extended_truth, extended_truth_prec, random_tet_mesh, row_scaled_error)
 from oracle_lib import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -43,7 +43,7 @@ def check_against_oracle(oracle, setup, ctx, fused, slivers=False):
     v, p = ctx.download()
     if slivers:
         assert_close_or_conditioned(v, want_v, truth, setup.row, dim)
-        assert_prec_close_or_conditioned(p, want_p, extended_truth_prec(setup, truth), dim)
+        assert_prec_close_or_conditioned(p, want_p, extended_truth_prec(setup, truth), dim, rho=diag_conditioning(setup, want_v))
     else:
         assert row_scaled_error(v, want_v, setup.row, dim) <= RTOL
         assert block_scaled_error(p, want_p, dim) <= RTOL
@@ -95,7 +95,7 @@ def test_reference_fixtures(path, op, name):
         else:
             assert_close_or_conditioned(v, g[f"{build}_{op}_values"], truth, setup.row, dim)
             block_scaled_error(p, g[f"{build}_{op}_prec"], dim)               # incl. the isolated node: inf / masked block coincide
-            assert_prec_close_or_conditioned(p, g[f"{build}_{op}_prec"], truth_p, dim)
+            assert_prec_close_or_conditioned(p, g[f"{build}_{op}_prec"], truth_p, dim, rho=diag_conditioning(setup, g[f"{build}_{op}_values"]))
     ctx.close()
 
 

@@ -12,7 +12,7 @@ import pytest
 
 import minifem_b200 as mfb
 from helpers import (RTOL, ArrayMesh, assert_close_or_conditioned, assert_prec_close_or_conditioned, block_scaled_error,
-                     extended_truth, extended_truth_prec, random_tet_mesh, row_scaled_error)
+                     diag_conditioning, extended_truth, extended_truth_prec, random_tet_mesh, row_scaled_error)
 from oracle_lib import Oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -66,7 +66,7 @@ def check_against_oracle(oracle, setup, values, prec, interface=None, rtol=RTOL)
         truth = extended_truth(setup)
         assert_close_or_conditioned(values, want_v, truth, setup.row, dim)
         assert interface is None
-        assert_prec_close_or_conditioned(prec, want_p, extended_truth_prec(setup, truth), dim)
+        assert_prec_close_or_conditioned(prec, want_p, extended_truth_prec(setup, truth), dim, rho=diag_conditioning(setup, want_v))
         return
     assert row_scaled_error(values, want_v, setup.row, dim) <= rtol
     if interface is None:
