@@ -39,8 +39,9 @@ extern "C" {
 #define MFB_PATH_RING     3   /* write-once like TILED, but every mesh edge walks the ring of elements
                                  around it from the node coordinates: no coefficient planes in shared
                                  memory, interior edges computed once for both (i,j) and (j,i), the
-                                 diagonal block = minus the row sum.  Compiled and replayed on the host
-                                 (tools/ring_replay.cc); first GPU measurement pending */
+                                 diagonal block = minus the row sum.  The default of the driver and of
+                                 bench.py, and the fastest path: a warp-specialised kernel,
+                                 384 threads per CTA (mfb_options.threads = 0 or 384; 768 = one CTA per SM) */
 
 const char *mfb_last_error (void);
 const char *mfb_version (void);
@@ -138,7 +139,7 @@ typedef struct {
     int device;                     /* CUDA device ordinal */
     int tileRows;                   /* TILED: max rows per tile (0 = default) */
     int tileElems;                  /* TILED: max elements per tile; RING: max slab slots per tile = CSR entries + row padding (0 = default) */
-    int threads;                    /* TILED: threads per CTA (0 = default) */
+    int threads;                    /* TILED: threads per CTA (0 = default 256); RING: 0 / 384 (two CTAs per SM) or 768 (one) */
     int useGraph;                   /* capture mfb_ctx_iteration in a CUDA graph */
     int ctas;                       /* TILED: CTAs walking the tiles (0 = default, -1 = one per tile) */
     int bankAware;                  /* TILED: order inside each contribution list: 0 / 1 = chosen against
@@ -153,7 +154,8 @@ void mfb_ctx_destroy (mfb_ctx *ctx);
  * stream; mfb_ctx_sync() or any *_host call waits. */
 int mfb_ctx_assembly (mfb_ctx *ctx);
 /* assembly_{lap,ela}_seq(userArgs, firstElem, lastElem), assembly.h:44,51: scatter-add of
- * an INCLUSIVE element interval without zeroing first (ATOMIC / COLOR element kernels). */
+ * an INCLUSIVE element interval without zeroing first (ATOMIC / COLOR element kernels).  On the COLOR
+ * path an interval that spans colours is cut at the colorToElem boundaries (one launch per piece). */
 int mfb_ctx_assembly_interval (mfb_ctx *ctx, int firstElem, int lastElem);
 int mfb_ctx_zero_values (mfb_ctx *ctx);
 /* prec_init(), preconditioner.h:31-32 / preconditioner.cc:52-87. */
