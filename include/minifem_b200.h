@@ -41,7 +41,7 @@ extern "C" {
                                  memory, interior edges computed once for both (i,j) and (j,i), the
                                  diagonal block = minus the row sum.  The default of the driver and of
                                  bench.py, and the fastest path: a warp-specialised kernel,
-                                 384 threads per CTA (mfb_options.threads = 0 or 384; 768 = one CTA per SM) */
+                                 768 threads per CTA, one CTA per SM (mfb_options.threads = 0 or 768; 384 = two CTAs per SM) */
 
 const char *mfb_last_error (void);
 const char *mfb_version (void);
@@ -139,7 +139,7 @@ typedef struct {
     int device;                     /* CUDA device ordinal */
     int tileRows;                   /* TILED: max rows per tile (0 = default) */
     int tileElems;                  /* TILED: max elements per tile; RING: max slab slots per tile = CSR entries + row padding (0 = default) */
-    int threads;                    /* TILED: threads per CTA (0 = default 256); RING: 0 / 384 (two CTAs per SM) or 768 (one) */
+    int threads;                    /* TILED: threads per CTA (0 = default 256); RING: 0 / 768 (one CTA per SM) or 384 (two) */
     int useGraph;                   /* capture mfb_ctx_iteration in a CUDA graph */
     int ctas;                       /* TILED: CTAs walking the tiles (0 = default, -1 = one per tile) */
     int bankAware;                  /* TILED: order inside each contribution list: 0 / 1 = chosen against

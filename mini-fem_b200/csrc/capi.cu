@@ -281,7 +281,7 @@ struct mfb_ctx {
     RingPlan ringStats;             // counters only
     double *dNorm = nullptr;        // [partials][2 results], allocated by the first mfb_ctx_norms
     int haloCoresident = 0;         // multi-GPU overlap scheme, see do_iteration
-    int haloReserveCtas = 8;       // RING: CTAs the persistent interior grid leaves free for the kernels of the exchange
+    int haloReserveCtas = 8;       // RING: CTAs the persistent interior grid leaves free for the kernels of the exchange (4 SMs)
     int eagerIterations = 0;       // fused iterations run before the multi-GPU graph is captured
     bool multiGraph = false;       // MFB_MULTI_GPU_GRAPH=1: capture the two-stream iteration with its NCCL group (opt-in)
     int interiorTilesPerCta = 4;   // measured at N=2: 1 -> 0.71 ms, 4 -> 0.645, 8 -> 0.647 (kernel alone 0.636 in that build)
@@ -400,6 +400,7 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     c->ringStats = hp;
     if (const char *v = getenv ("MFB_HALO_OVERLAP")) c->haloCoresident = std::string (v) == "coresident";
     if (const char *v = getenv ("MFB_INTERIOR_TILES_PER_CTA")) c->interiorTilesPerCta = std::max (atoi (v), 1);
+    c->haloReserveCtas = c->threads == 768 ? 4 : 8;            // four SMs either way
     if (const char *v = getenv ("MFB_HALO_RESERVE_CTAS")) c->haloReserveCtas = std::max (atoi (v), 0);
     if (const char *v = getenv ("MFB_MULTI_GPU_GRAPH")) c->multiGraph = atoi (v) != 0;
     c->tiledSmem = ring_smem_bytes (c->operatorID, c->ringPlan);
@@ -619,7 +620,7 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     if (c->path == MFB_PATH_RING) {          // a write-once path like TILED: same stages, same fused iteration
         c->ring = true;
         c->path = MFB_PATH_TILED;
-        if (!(o && o->threads > 0)) c->threads = 384;
+        if (!(o && o->threads > 0)) c->threads = 768;
         if (c->threads != 384 && c->threads != 768) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 384 (two CTAs per SM) or 768 (one) threads per CTA");
     }
     if (!c->ring && c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {

@@ -69,6 +69,7 @@ inline void ring_bulk_load (void *dst, const void *src, unsigned bytes, uint64_t
 inline void ring_bar_sync (int id, int count) { cta_emu::bar_sync (id, count); }
 inline void ring_cp_async_f64 (double *dst, const double *src) { *dst = *src; }
 inline void ring_cp_async_wait_all () {}
+inline void ring_cp_async_arrive (uint64_t *bar) { cta_emu::mbar_arrive (bar); }
 #else
 __device__ __forceinline__ unsigned ring_smem_u32 (const void *p) { return (unsigned)__cvta_generic_to_shared (p); }
 
@@ -122,6 +123,11 @@ __device__ __forceinline__ void ring_cp_async_f64 (double *dst, const double *sr
     asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(ring_smem_u32 (dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void ring_cp_async_wait_all () { asm volatile ("cp.async.wait_all;" ::: "memory"); }
+// one arrival on `bar` (counted in its initial count) once this thread's earlier cp.async copies have landed
+__device__ __forceinline__ void ring_cp_async_arrive (uint64_t *bar)
+{
+    asm volatile ("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(ring_smem_u32 (bar)) : "memory");
+}
 
 #endif
 
@@ -146,8 +152,9 @@ __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim ==
 //     warps: at the start of tile k's write-out they request the tail (TMA) and load the coordinates of tile
 //     k + 2, whose buffers (those of tile k) the job warps have just released — a whole job phase ahead of
 //     their use — and the plan head of tile k + 3.
-// No block barrier after the prologue.  THREADS = 384: 7 job warps + 5 write-out warps (elasticity), two CTAs per SM.
-constexpr int kRingHeadBuffers = 4;
+// No block barrier after the prologue.  THREADS = 768 (default): 13 job warps + 11 write-out warps (elasticity), one CTA per SM,
+// tiles of <= 64 rows; THREADS = 384: 7 + 5, two CTAs per SM, tiles of <= 30 rows.
+constexpr int kRingHeadBuffers = 5;      // heads of tiles k - 1 .. k + 3 are alive while the write-out warps work on tile k
 
 inline RingSmemLayout ring_smem_layout (int operatorID, const DeviceRingPlan &plan)
 {
@@ -173,16 +180,15 @@ ring_assembly_kernel (const RingArgs args)
 #else
     extern __shared__ __align__(128) unsigned char smemRaw[];
 #endif
-    // job warps out of 12: measured on the EIB mesh (ms per iteration, 384 threads) elasticity 8: 0.494, 7: 0.449,
-    // 6: 0.456; the Laplacian has an eighth of the write-out work per row and wants more job warps (8: 0.260,
-    // 10: 0.280; 768 threads, 20 + 4: 0.252).  A single 768-thread CTA per SM does best with an even split (0.450).
-#ifdef MFB_RING_JOB_WARPS_OF_12
-    constexpr int kJobOf12 = MFB_RING_JOB_WARPS_OF_12;
+    // job warps out of 24, measured on the EIB mesh (ms per iteration, final pipeline): elasticity, 768 threads: 12: 0.421,
+    // 13: 0.414, 15: 0.439, 16: 0.449; 384 threads (x 2 CTAs): 6 of 12: 0.458, 7: 0.430, 8: 0.482.  The Laplacian has an
+    // eighth of the write-out work per row and wants more job warps (768 threads, 20 + 4: 0.252).
+#ifdef MFB_RING_JOB_WARPS_OF_24
+    constexpr int kJobOf24 = MFB_RING_JOB_WARPS_OF_24;
 #else
-    constexpr int kJobOf12 = OPDIM == 1 ? (THREADS == 768 ? 10 : 8) : (THREADS == 768 ? 6 : 7);
+    constexpr int kJobOf24 = OPDIM == 1 ? (THREADS == 768 ? 20 : 16) : (THREADS == 768 ? 13 : 14);
 #endif
-    constexpr int NWARPS = THREADS / 32, NJOB = NWARPS * kJobOf12 / 12, NOUT = NWARPS - NJOB;
-    constexpr int NSTAGE = (kRingMaxNodes + NOUT * 32 - 1) / (NOUT * 32);    // nodes each write-out thread stages
+    constexpr int NWARPS = THREADS / 32, NJOB = NWARPS * kJobOf24 / 24, NOUT = NWARPS - NJOB;
     const DeviceRingPlan &P = args.plan;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -206,12 +212,13 @@ ring_assembly_kernel (const RingArgs args)
 
     if (tid == 0) {
         for (int b = 0; b < kRingHeadBuffers; b++) ring_mbar_init (headFull + b, 1);
-        for (int b = 0; b < 2; b++) { ring_mbar_init (tailFull + b, 1); ring_mbar_init (full + b, NJOB); ring_mbar_init (ready + b, NOUT); }
+        // tailFull: the loader's TMA (one arrival + its bytes) and every write-out thread's share of the coordinates
+        for (int b = 0; b < 2; b++) { ring_mbar_init (tailFull + b, 1 + NOUT * 32); ring_mbar_init (full + b, NJOB); ring_mbar_init (ready + b, NOUT); }
     }
     __syncthreads ();          // the only block barrier
 
-    auto head_of = [&] (int k) { return sHead0 + (unsigned)(k & (kRingHeadBuffers - 1)) * headBytes; };
-    auto wait_head = [&] (int k) { ring_mbar_wait (headFull + (k & (kRingHeadBuffers - 1)), (unsigned)(k / kRingHeadBuffers) & 1u); };
+    auto head_of = [&] (int k) { return sHead0 + (unsigned)((k + kRingHeadBuffers) % kRingHeadBuffers) * headBytes; };
+    auto wait_head = [&] (int k) { ring_mbar_wait (headFull + k % kRingHeadBuffers, (unsigned)(k / kRingHeadBuffers) & 1u); };
 
     if (warp < NJOB) {
         // =============================== job warps ===============================================
@@ -227,8 +234,9 @@ ring_assembly_kernel (const RingArgs args)
             const double *sX = planes0 + (k & 1) * (3 * planeStride), *sY = sX + planeStride, *sZ = sY + planeStride;
             double *slab = slab0 + (k & 1) * slabDoubles;
             const unsigned phase = (unsigned)(k >> 1) & 1u;
-            ring_mbar_wait (ready + (k & 1), phase);        // slab k & 1 drained (tile k - 2), coordinates of tile k in place
-            ring_mbar_wait (tailFull + (k & 1), phase);
+            ring_mbar_wait (tailFull + (k & 1), phase);     // tail and coordinates of tile k are in (requested two tiles ago)
+            bool slabFree = false;                          // ready[k & 1] (slab drained by the write-out of tile k - 2) is only
+                                                            // needed when the first block is stored, a whole batch from now
             // the batches of a tile go round the job warps, starting where the previous tile stopped
             for (int b = (warp + NJOB - (k * 5) % NJOB) % NJOB; b < nbBatches; b += NJOB) {
                 const RingBatch rb = batches[b];
@@ -285,6 +293,7 @@ ring_assembly_kernel (const RingArgs args)
                         have = true;
                     }
                 }
+                if (!slabFree) { ring_mbar_wait (ready + (k & 1), phase); slabFree = true; }
                 if (sIJ != 0xFFFF) {
                     if (OPDIM == 1) {
                         slab[sIJ] = acc[0];
@@ -306,6 +315,8 @@ ring_assembly_kernel (const RingArgs args)
                     }
                 }
             }
+            if (!slabFree) ring_mbar_wait (ready + (k & 1), phase);   // also without a batch: full[] then implies that every
+                                                                      // write-out warp is done with tile k - 2
             __syncwarp ();
             if (lane == 0) ring_mbar_arrive (full + (k & 1));   // this warp's share of tile k is in the slab; it no longer
                                                                 // reads the tile's tail, coordinates or head
@@ -317,7 +328,7 @@ ring_assembly_kernel (const RingArgs args)
         auto tile_of = [&] (int k) { return firstTile + k * tileStep; };
         auto fetch_head = [&] (uint64_t packed, int k) {              // one thread
             const unsigned bytes = ring_record_head_bytes (packed);
-            uint64_t *bar = headFull + (k & (kRingHeadBuffers - 1));
+            uint64_t *bar = headFull + k % kRingHeadBuffers;
             ring_mbar_expect_tx (bar, bytes);
             ring_bulk_load (head_of (k), P.blob + ring_record_offset (packed), bytes, bar);
         };
@@ -341,33 +352,30 @@ ring_assembly_kernel (const RingArgs args)
         }
         // k = -2, -1: nothing to write out yet, only the first two tiles to stage
         for (int k = -2; k < nbMine; k++) {
-            ring_bar_sync (1, NOUT * 32);      // every write-out warp has finished tile k - 1: its head buffer is free
+            // (no barrier among the write-out warps: full[k & 1] implies that every one of them has finished tile
+            // k - 2 — the job warps could not have stored tile k otherwise — and the head fetched below replaces that of
+            // tile k - 2)
             if (k >= 0) ring_mbar_wait (full + (k & 1), (unsigned)(k >> 1) & 1u);   // the job warps are done with tile k
             // ---- staging for tile k + 2 (into the buffers of tile k) -------------------------------------
             const int kn = k + 2;
-            double cs[NSTAGE][3];
-            #pragma unroll
-            for (int q = 0; q < NSTAGE; q++) cs[q][0] = cs[q][1] = cs[q][2] = 0.0;
-            int nbNodesNext = 0;
             if (kn < nbMine) {
                 wait_head (kn);
                 const unsigned char *nh = head_of (kn);
                 const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (nh);
                 if (otid == 0) fetch_tail (offA, kn);
-                nbNodesNext = h.nbNodes;
+                // coordinates: asynchronous 8-byte copies that signal tailFull[kn & 1] when they have landed (each costs a
+                // shared-memory wavefront on arrival — the kernel is not bound by those — but no register, no wait)
                 const int *nodes = reinterpret_cast<const int*> (nh + h.offNodes);
-                #pragma unroll
-                for (int q = 0; q < NSTAGE; q++) {
-                    const int n = otid + q * NOUT * 32;
-                    if (n < nbNodesNext) {
-                        const double *g = args.coord + (size_t)nodes[n] * 3;
-                        cs[q][0] = __ldg (g); cs[q][1] = __ldg (g + 1); cs[q][2] = __ldg (g + 2);
-                    }
+                double *pl = planes0 + (kn & 1) * (3 * planeStride);
+                for (int n = otid; n < h.nbNodes; n += NOUT * 32) {
+                    const double *g = args.coord + (size_t)nodes[n] * 3;
+                    ring_cp_async_f64 (pl + n, g); ring_cp_async_f64 (pl + planeStride + n, g + 1);
+                    ring_cp_async_f64 (pl + 2 * planeStride + n, g + 2);
                 }
+                ring_cp_async_arrive (tailFull + (kn & 1));
             }
             if (otid == 0) {
-                // head of tile k + 3 into the buffer of tile k - 1 (its write-out ended before the named barrier, its
-                // jobs before full[] of the previous round)
+                // head of tile k + 3 into the buffer of tile k - 2 (five buffers)
                 if (k + 3 >= 3 && k + 3 < nbMine) fetch_head (offB, k + 3);
                 offA = offB;
                 offB = k + 4 < nbMine ? P.tileOffset[tile_of (k + 4)] : 0;
@@ -461,16 +469,10 @@ ring_assembly_kernel (const RingArgs args)
                     }
                 }
             }
-            // ---- coordinates of tile k + 2 into the plane set the job warps released with tile k ----------------
+            // ---- slab k & 1 is drained: tile k + 2 may store into it -----------------------------------------------
             if (kn < nbMine) {
-                double *pl = planes0 + (kn & 1) * (3 * planeStride);
-                #pragma unroll
-                for (int q = 0; q < NSTAGE; q++) {
-                    const int n = otid + q * NOUT * 32;
-                    if (n < nbNodesNext) { pl[n] = cs[q][0]; pl[planeStride + n] = cs[q][1]; pl[2 * planeStride + n] = cs[q][2]; }
-                }
                 __syncwarp ();
-                if (lane == 0) ring_mbar_arrive (ready + (kn & 1));     // tile k + 2 may start: slab drained, coordinates in
+                if (lane == 0) ring_mbar_arrive (ready + (kn & 1));
             }
         }
     }

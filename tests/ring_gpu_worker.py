@@ -61,7 +61,7 @@ def main():
         mesh = mfb.Mesh.generate(14, 12, 10, seed=9)
         check(oracle, f"{op} small tiles", mfb.Setup(mesh, op), tile_rows=7, tile_elems=120)
         check(oracle, f"{op} large tiles", mfb.Setup(mesh, op), tile_rows=64, tile_elems=960)
-        check(oracle, f"{op} 768 threads (one CTA per SM)", mfb.Setup(mesh, op), threads=768)
+        check(oracle, f"{op} 384 threads (two CTAs per SM)", mfb.Setup(mesh, op), threads=384)
         check(oracle, f"{op} 384 threads, small caps", mfb.Setup(mesh, op), threads=384, tile_rows=22, tile_elems=352)
         check(oracle, f"{op} one CTA", mfb.Setup(mesh, op), ctas=1)
         check(oracle, f"{op} one tile per CTA", mfb.Setup(mesh, op), ctas=-1)
