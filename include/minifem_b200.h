@@ -214,6 +214,20 @@ int mfb_ctx_plan_stats (mfb_ctx *ctx, int64_t stats[8]);
 int mfb_comm_unique_id (unsigned char id[MFB_COMM_ID_BYTES]);              /* rank 0, then broadcast */
 int mfb_ctx_comm_init (mfb_ctx *ctx, const unsigned char id[MFB_COMM_ID_BYTES]);
 
+/* Peer-to-peer exchange for the fused RING iteration (csrc/kernels_halo_p2p.cu), replacing the NCCL send / recv
+ * group by stores into the neighbours' receive windows over NVLink plus an epoch flag — the write + notify scheme
+ * of the reference's GASPI variant, src/halo.cc:127-226 (segments created in FEM.cc / main.cc under -DGASPI).
+ * Every subdomain publishes a card (its window's cudaIpc handle, neighbour list and interface offsets); the caller
+ * gathers the cards of all nbBlocks subdomains in rank order (torch.distributed all_gather, files, MPI ...) and
+ * hands them to connect.  Subdomains living in one process are connected through plain device pointers.  All
+ * subdomains must switch together: call mfb_ctx_p2p_enable (ctx, 0) everywhere if connect failed anywhere (NCCL
+ * then carries the exchange, mfb_ctx_comm_init).  A timed-out wait surfaces as MFB_ERR_COMM from mfb_ctx_sync. */
+#define MFB_P2P_CARD_BYTES 1024
+int mfb_ctx_p2p_card (mfb_ctx *ctx, unsigned char card[MFB_P2P_CARD_BYTES]);
+int mfb_ctx_p2p_connect (mfb_ctx *ctx, const unsigned char *cards /* nbBlocks x MFB_P2P_CARD_BYTES */);
+int mfb_ctx_p2p_enable (mfb_ctx *ctx, int on);
+int mfb_ctx_p2p_active (mfb_ctx *ctx);
+
 /* The two halves of the halo exchange with the transport left to the caller (tests, or a
  * host MPI): pack = halo.cc:77-80 into sendBuf[nbIntfNodes*operatorDim]; add = halo.cc:113-116
  * from recvBuf laid out like bufferRecv (segment i at intfIndex[i]*operatorDim). */

@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -255,6 +256,12 @@ cudaError_t upload (T **dst, const T *src, size_t count, int64_t &bytes)
 
 // ----------------------------------------------------------------------- context
 
+namespace {
+constexpr size_t kP2PFlagBytes = 256;                 // 64 flags of 4 bytes
+constexpr int kP2PMaxIntf = 64;
+inline size_t p2p_align (size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+}
+
 struct mfb_ctx {
     int path = MFB_PATH_TILED, device = 0, threads = 256, useGraph = 0;
     int operatorID = 0, operatorDim = 1;
@@ -289,6 +296,17 @@ struct mfb_ctx {
 
     NcclComm comm = nullptr;
     cudaGraphExec_t graphExec = nullptr;
+
+    // peer-to-peer halo (kernels_halo_p2p.cu): this context's window = [64 flags][recv parity 0][recv parity 1]
+    unsigned char *p2pWindow = nullptr;
+    HaloP2PState *p2pState = nullptr;
+    unsigned *p2pStatusHost = nullptr, *p2pStatusDev = nullptr;      // one mapped word
+    double **dPeerRecv = nullptr;
+    unsigned **dPeerFlag = nullptr;
+    int *dIntfIndex = nullptr;
+    std::vector<void*> p2pOpened;  // cudaIpcOpenMemHandle mappings to close
+    bool p2pReady = false;
+    int p2pCtas = 4;
 };
 
 namespace {
@@ -366,8 +384,8 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     // two slabs per CTA: 30 rows / 510 slots keep two 384-thread CTAs per SM, 64 rows / 1100 slots fit the
     // single 768-thread CTA
     RingPlanLimits lim;
-    lim.maxRows = c->threads == 768 ? 64 : 30;
-    lim.maxEntries = c->threads == 768 ? 1100 : 510;
+    lim.maxRows = c->threads >= 768 ? 64 : 30;
+    lim.maxEntries = c->threads >= 768 ? 1100 : 510;
     if (o && o->tileRows > 0) lim.maxRows = o->tileRows;
     if (o && o->tileElems > 0) lim.maxEntries = o->tileElems;          // RING: tileElems caps the slab slots of a tile
     lim.bankAware = !(o && o->bankAware < 0);
@@ -400,7 +418,7 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     c->ringStats = hp;
     if (const char *v = getenv ("MFB_HALO_OVERLAP")) c->haloCoresident = std::string (v) == "coresident";
     if (const char *v = getenv ("MFB_INTERIOR_TILES_PER_CTA")) c->interiorTilesPerCta = std::max (atoi (v), 1);
-    c->haloReserveCtas = c->threads == 768 ? 4 : 8;            // four SMs either way
+    c->haloReserveCtas = c->threads >= 768 ? 4 : 8;            // four SMs either way
     if (const char *v = getenv ("MFB_HALO_RESERVE_CTAS")) c->haloReserveCtas = std::max (atoi (v), 0);
     if (const char *v = getenv ("MFB_MULTI_GPU_GRAPH")) c->multiGraph = atoi (v) != 0;
     c->tiledSmem = ring_smem_bytes (c->operatorID, c->ringPlan);
@@ -517,8 +535,40 @@ int do_iteration (mfb_ctx *c)
     }
     const bool exchange = c->nbBlocks > 1 && c->nbIntf > 0;
     if (!exchange) return do_assembly (c, 1);
-    if (!c->comm) return fail (MFB_ERR_STATE, "mfb_ctx_iteration: call mfb_ctx_comm_init first (nbBlocks > 1)");
+    if (!c->comm && !(c->ring && c->p2pReady)) return fail (MFB_ERR_STATE, "mfb_ctx_iteration: call mfb_ctx_comm_init or mfb_ctx_p2p_connect first (nbBlocks > 1)");
     const int nIntfTiles = c->plan.nbInterfaceTiles, nInterior = c->plan.nbTiles - nIntfTiles;
+    if (c->ring && c->p2pReady) {
+        // Peer-to-peer exchange: TWO launches per iteration.  The exchange kernel (a few CTAs on the high-priority
+        // stream) waits for the assembly kernel's interface tiles — the first tiles of every CTA —, stores their
+        // blocks into the neighbours' windows over NVLink, waits for theirs and sums + inverts; the assembly kernel
+        // takes ALL tiles on the rest of the device (it never waits for the exchange, so the pair cannot deadlock:
+        // its grid leaves haloReserveCtas free and the exchange kernel asks for no more SMs than that).
+        HaloP2PArgs a;
+        a.state = c->p2pState;
+        a.intfTarget = (unsigned)nIntfTiles * (unsigned)ring_write_out_warps (c->operatorID, c->threads);
+        a.status = c->p2pStatusDev;
+        a.prec = c->dPrec;
+        a.nbIntf = c->nbIntf; a.nbUniq = c->nbUniqIntf; a.nbNodes = c->nbNodes;
+        a.intfIndex = c->dIntfIndex; a.intfNodes = c->dIntfNodes;
+        a.peerRecv = c->dPeerRecv; a.peerFlag = c->dPeerFlag;
+        a.localFlags = reinterpret_cast<const unsigned*> (c->p2pWindow);
+        const size_t bufBytes = sizeof (double) * (size_t)c->nbIntfNodes * c->operatorDim;
+        a.localRecv[0] = reinterpret_cast<const double*> (c->p2pWindow + kP2PFlagBytes);
+        a.localRecv[1] = reinterpret_cast<const double*> (c->p2pWindow + kP2PFlagBytes + p2p_align (bufBytes));
+        a.uniqNodes = c->dUniqNodes; a.slotIndex = c->dSlotIndex; a.slots = c->dSlots;
+        a.diagIndex = c->dDiagIndex; a.checkBounds = c->dCheckBounds;
+        MFB_CUDA (cudaEventRecord (c->evIntfDone, c->stream));                 // everything queued so far
+        MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
+        MFB_CUDA (launch_halo_p2p (a, c->operatorDim, c->p2pCtas, c->commStream));
+        c->launches++;
+        const int ctas = std::max (c->tiledCtas - c->haloReserveCtas, 1);
+        MFB_CUDA (launch_ring (c->operatorID, c->ringPlan, 0, c->plan.nbTiles, ctas, c->threads, c->tiledSmem, c->dCoord,
+                               c->dValues, c->dPrec, 1, c->stream, &c->p2pState->intfDone));
+        if (c->plan.nbTiles > 0) c->launches++;
+        MFB_CUDA (cudaEventRecord (c->evCommDone, c->commStream));
+        MFB_CUDA (cudaStreamWaitEvent (c->stream, c->evCommDone, 0));
+        return MFB_OK;
+    }
     if (c->haloCoresident) {
         // MFB_HALO_OVERLAP=coresident: two co-resident kernels.  The high-priority stream takes the
         // tiles that own interface nodes on a small persistent grid, the main stream the interior
@@ -562,6 +612,16 @@ int do_iteration (mfb_ctx *c)
 
 }  // namespace
 
+// A bounded wait of the exchange kernel ran out: the results of that iteration are garbage.
+static int p2p_status (mfb_ctx *c)
+{
+    if (!c->p2pStatusHost || *c->p2pStatusHost == 0) return MFB_OK;
+    const unsigned code = *c->p2pStatusHost;
+    *c->p2pStatusHost = 0;
+    return fail (MFB_ERR_COMM, std::string ("peer-to-peer halo exchange timed out waiting for ") +
+                 ((code & 1u) ? "the interface tiles of the assembly kernel" : "a neighbour's flag (do all ranks run the same iterations?)"));
+}
+
 extern "C" int mfb_device_count (void)
 {
     int n = 0;
@@ -577,6 +637,10 @@ extern "C" void mfb_ctx_destroy (mfb_ctx *c)
     if (c->commStream) cudaStreamSynchronize (c->commStream);
     if (c->comm) { std::string why; NcclApi *api = nccl_api (why); if (api) api->CommDestroy (c->comm); }
     if (c->graphExec) cudaGraphExecDestroy (c->graphExec);
+    for (void *p : c->p2pOpened) cudaIpcCloseMemHandle (p);
+    if (c->p2pStatusHost) cudaFreeHost (c->p2pStatusHost);
+    void *p2pPtrs[] = {c->p2pWindow, c->p2pState, c->dPeerRecv, c->dPeerFlag, c->dIntfIndex};
+    for (void *p : p2pPtrs) if (p) cudaFree (p);
     void *ptrs[] = {c->dCoord, c->dValues, c->dPrec, c->dSend, c->dRecv, c->dElemToNode, c->dRow, c->dCol,
                     c->dElemToEdge, c->dCheckBounds, c->dDiagIndex, c->dIntfNodes, c->dUniqNodes,
                     c->dSlotIndex, c->dSlots, c->dNorm};
@@ -621,7 +685,7 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
         c->ring = true;
         c->path = MFB_PATH_TILED;
         if (!(o && o->threads > 0)) c->threads = 768;
-        if (c->threads != 384 && c->threads != 768) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 384 (two CTAs per SM) or 768 (one) threads per CTA");
+        if (c->threads != 384 && c->threads != 768 && c->threads != 1024) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 384 (two CTAs per SM), 768 or 1024 (one) threads per CTA");
     }
     if (!c->ring && c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {
         return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256], or the pipelined kernel's CTA size");
@@ -863,7 +927,7 @@ extern "C" int mfb_ctx_sync (mfb_ctx *c)
     CTX_ENTER (c);
     MFB_CUDA (cudaStreamSynchronize (c->stream));
     MFB_CUDA (cudaStreamSynchronize (c->commStream));
-    return MFB_OK;
+    return p2p_status (c);
 }
 
 extern "C" int mfb_ctx_download (mfb_ctx *c, double *nodeToNodeValue, double *prec)
@@ -1005,6 +1069,131 @@ extern "C" int mfb_ctx_comm_init (mfb_ctx *c, const unsigned char id[MFB_COMM_ID
     return MFB_OK;
 }
 
+// ---- peer-to-peer windows (kernels_halo_p2p.cu) -----------------------------------------------------------------
+namespace {
+struct P2PCard {                       // what a subdomain publishes; MFB_P2P_CARD_BYTES on the wire
+    uint32_t magic;
+    int32_t rank, device, nbIntf, dim, hasHandle;
+    int64_t pid;
+    uint64_t rawPtr, windowBytes;
+    cudaIpcMemHandle_t handle;
+    int32_t neighbors[kP2PMaxIntf];    // 1-based ranks, as neighborsList
+    int32_t intfIndex[kP2PMaxIntf + 1];
+};
+static_assert (sizeof (P2PCard) <= MFB_P2P_CARD_BYTES, "card does not fit its wire size");
+constexpr uint32_t kP2PMagic = 0x4D465032u;   // "MFP2"
+}
+
+extern "C" int mfb_ctx_p2p_card (mfb_ctx *c, unsigned char card[MFB_P2P_CARD_BYTES])
+{
+    CTX_ENTER (c);
+    if (!card) return fail (MFB_ERR_ARG, "mfb_ctx_p2p_card: NULL card");
+    if (!c->ring) return fail (MFB_ERR_STATE, "mfb_ctx_p2p_card: the peer-to-peer exchange belongs to the fused RING iteration");
+    if (c->nbIntf > kP2PMaxIntf) return fail (MFB_ERR_ARG, "mfb_ctx_p2p_card: more than 64 interfaces; use the NCCL exchange");
+    const size_t bufBytes = sizeof (double) * (size_t)c->nbIntfNodes * c->operatorDim;
+    const size_t windowBytes = kP2PFlagBytes + 2 * p2p_align (bufBytes);
+    if (!c->p2pWindow) {
+        MFB_CUDA (cudaMalloc ((void**)&c->p2pWindow, windowBytes));
+        MFB_CUDA (cudaMemset (c->p2pWindow, 0, windowBytes));
+        MFB_CUDA (cudaMalloc ((void**)&c->p2pState, sizeof (HaloP2PState)));
+        MFB_CUDA (cudaMemset (c->p2pState, 0, sizeof (HaloP2PState)));
+        MFB_CUDA (cudaHostAlloc ((void**)&c->p2pStatusHost, sizeof (unsigned), cudaHostAllocMapped));
+        *c->p2pStatusHost = 0;
+        MFB_CUDA (cudaHostGetDevicePointer ((void**)&c->p2pStatusDev, c->p2pStatusHost, 0));
+        int64_t bytes = 0;
+        MFB_CUDA (upload (&c->dIntfIndex, c->intfIndex.data (), c->intfIndex.size (), bytes));
+        c->meshBytes += (int64_t)windowBytes + bytes;
+    }
+    P2PCard k;
+    memset (&k, 0, sizeof k);
+    k.magic = kP2PMagic; k.rank = c->rank; k.device = c->device; k.nbIntf = c->nbIntf; k.dim = c->operatorDim;
+    k.pid = (int64_t)getpid (); k.rawPtr = (uint64_t)(uintptr_t)c->p2pWindow; k.windowBytes = windowBytes;
+    if (cudaIpcGetMemHandle (&k.handle, c->p2pWindow) == cudaSuccess) k.hasHandle = 1;
+    else cudaGetLastError ();                              // same-process peers still work through rawPtr
+    for (int i = 0; i < c->nbIntf; i++) k.neighbors[i] = c->neighbors[i];
+    for (int i = 0; i <= c->nbIntf; i++) k.intfIndex[i] = c->intfIndex.empty () ? 0 : c->intfIndex[i];
+    memset (card, 0, MFB_P2P_CARD_BYTES);
+    memcpy (card, &k, sizeof k);
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_p2p_connect (mfb_ctx *c, const unsigned char *cards)
+{
+    CTX_ENTER (c);
+    if (!cards) return fail (MFB_ERR_ARG, "mfb_ctx_p2p_connect: NULL cards");
+    if (!c->p2pWindow) return fail (MFB_ERR_STATE, "mfb_ctx_p2p_connect: call mfb_ctx_p2p_card first");
+    c->p2pReady = false;
+    std::vector<double*> peerRecv ((size_t)2 * c->nbIntf, nullptr);
+    std::vector<unsigned*> peerFlag ((size_t)c->nbIntf, nullptr);
+    std::vector<unsigned char*> baseOfRank ((size_t)c->nbBlocks, nullptr);
+    for (int i = 0; i < c->nbIntf; i++) {
+        const int q = c->neighbors[i] - 1;
+        if (q < 0 || q >= c->nbBlocks) return fail (MFB_ERR_ARG, "mfb_ctx_p2p_connect: neighbour rank out of range");
+        P2PCard k;
+        memcpy (&k, cards + (size_t)q * MFB_P2P_CARD_BYTES, sizeof k);
+        if (k.magic != kP2PMagic || k.rank != q) return fail (MFB_ERR_ARG, "mfb_ctx_p2p_connect: rank " + std::to_string (q) + " published no card");
+        if (k.dim != c->operatorDim) return fail (MFB_ERR_ARG, "mfb_ctx_p2p_connect: operator differs between neighbours");
+        int iq = -1;
+        for (int t = 0; t < k.nbIntf; t++) if (k.neighbors[t] - 1 == c->rank) { iq = t; break; }
+        if (iq < 0) return fail (MFB_ERR_ARG, "mfb_ctx_p2p_connect: rank " + std::to_string (q) + " does not list this subdomain as a neighbour");
+        const int mine = c->intfIndex[i + 1] - c->intfIndex[i], theirs = k.intfIndex[iq + 1] - k.intfIndex[iq];
+        if (mine != theirs) return fail (MFB_ERR_ARG, "mfb_ctx_p2p_connect: interface sizes differ between the two sides");
+        if (!baseOfRank[q]) {
+            if (k.pid == (int64_t)getpid ()) {
+                // both subdomains in one process (tests, or a driver that owns several GPUs): plain device pointers
+                if (k.device != c->device) {
+                    int can = 0;
+                    MFB_CUDA (cudaDeviceCanAccessPeer (&can, c->device, k.device));
+                    if (!can) return fail (MFB_ERR_COMM, "mfb_ctx_p2p_connect: no peer access between devices " + std::to_string (c->device) + " and " + std::to_string (k.device));
+                    cudaError_t e = cudaDeviceEnablePeerAccess (k.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) MFB_CUDA (e);
+                    cudaGetLastError ();
+                }
+                baseOfRank[q] = reinterpret_cast<unsigned char*> ((uintptr_t)k.rawPtr);
+            }
+            else {
+                if (!k.hasHandle) return fail (MFB_ERR_COMM, "mfb_ctx_p2p_connect: rank " + std::to_string (q) + " could not export its window (cudaIpcGetMemHandle)");
+                void *ptr = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle (&ptr, k.handle, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) { cudaGetLastError (); return fail (MFB_ERR_COMM, std::string ("mfb_ctx_p2p_connect: cudaIpcOpenMemHandle: ") + cudaGetErrorString (e)); }
+                c->p2pOpened.push_back (ptr);
+                baseOfRank[q] = static_cast<unsigned char*> (ptr);
+            }
+        }
+        const size_t peerBuf = p2p_align (sizeof (double) * (size_t)k.intfIndex[k.nbIntf] * k.dim);
+        for (int par = 0; par < 2; par++) {
+            peerRecv[(size_t)2 * i + par] = reinterpret_cast<double*> (baseOfRank[q] + kP2PFlagBytes + (size_t)par * peerBuf) +
+                                            (size_t)k.intfIndex[iq] * k.dim;
+        }
+        peerFlag[i] = reinterpret_cast<unsigned*> (baseOfRank[q]) + iq;
+    }
+    if (c->dPeerRecv) { cudaFree (c->dPeerRecv); c->dPeerRecv = nullptr; }
+    if (c->dPeerFlag) { cudaFree (c->dPeerFlag); c->dPeerFlag = nullptr; }
+    int64_t bytes = 0;
+    MFB_CUDA (upload (&c->dPeerRecv, peerRecv.data (), peerRecv.size (), bytes));
+    MFB_CUDA (upload (&c->dPeerFlag, peerFlag.data (), peerFlag.size (), bytes));
+    c->p2pCtas = 4;
+    if (const char *v = getenv ("MFB_P2P_CTAS")) c->p2pCtas = std::max (atoi (v), 1);
+    const int ctasPerSM = c->threads >= 768 ? 1 : 2;
+    c->p2pCtas = std::max (1, std::min (c->p2pCtas, c->haloReserveCtas / ctasPerSM));   // never more SMs than the assembly grid leaves free
+    if (c->haloReserveCtas < ctasPerSM) return fail (MFB_ERR_STATE, "mfb_ctx_p2p_connect: MFB_HALO_RESERVE_CTAS leaves no SM to the exchange kernel");
+    c->p2pReady = true;
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_p2p_enable (mfb_ctx *c, int on)
+{
+    CTX_ENTER (c);
+    if (on && !c->dPeerRecv && c->nbIntf > 0) return fail (MFB_ERR_STATE, "mfb_ctx_p2p_enable: not connected");
+    if (on && !c->p2pWindow) return fail (MFB_ERR_STATE, "mfb_ctx_p2p_enable: not connected");
+    MFB_CUDA (cudaStreamSynchronize (c->stream));
+    MFB_CUDA (cudaStreamSynchronize (c->commStream));
+    c->p2pReady = on != 0;
+    return MFB_OK;
+}
+
+extern "C" int mfb_ctx_p2p_active (mfb_ctx *c) { return c && c->p2pReady ? 1 : 0; }
+
 extern "C" int mfb_ctx_halo_pack_host (mfb_ctx *c, double *sendBuf)
 {
     CTX_ENTER (c);
@@ -1068,7 +1257,7 @@ extern "C" int mfb_ctx_run_timed (mfb_ctx *c, int steps, float *ms)
     MFB_CUDA (cudaEventSynchronize (c->evStop[4]));
     MFB_CUDA (cudaEventElapsedTime (ms, c->evStart[4], c->evStop[4]));
     c->stageRan[4] = true;
-    return MFB_OK;
+    return p2p_status (c);
 }
 
 extern "C" int mfb_tile_plan_selfcheck (const mfb_problem *p, int tileRows, int tileElems, int64_t stats[6])

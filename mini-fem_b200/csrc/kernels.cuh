@@ -32,6 +32,29 @@ cudaError_t launch_halo_add (double *prec, const double *recvBuf, const int *uni
                              const int *slotIndex, const int *slots, int dim, int nbUniq,
                              cudaStream_t stream);
 
+// Peer-to-peer halo exchange fused with the interface sum and inversion (kernels_halo_p2p.cu); runs next to the RING
+// assembly kernel of the same iteration.  All pointers are device pointers of THIS process; peerRecv / peerFlag
+// point into the neighbours' windows (cudaIpc mappings or, inside one process, plain device pointers).
+struct HaloP2PState {                 // device memory, zeroed once
+    unsigned intfDone;                // + 1 per (write-out warp, interface tile) of the assembly kernel
+    unsigned packDone, finished;      // CTAs of the exchange kernel past their pack / past their sum
+    unsigned epoch;                   // exchanges completed so far
+};
+struct HaloP2PArgs {
+    HaloP2PState *state;
+    unsigned intfTarget;              // value of state->intfDone when every interface tile is written
+    unsigned *status;                 // mapped host word: bit 0 = the assembly kernel's signal timed out, bit 1 = a neighbour's flag
+    double *prec;
+    int nbIntf, nbUniq, nbNodes;
+    const int *intfIndex, *intfNodes; // halo.cc: interface i holds intfNodes[intfIndex[i] .. intfIndex[i+1]) (1-based ids)
+    double *const *peerRecv;          // [2 * nbIntf]: where interface i's blocks go in the neighbour's window, per epoch parity
+    unsigned *const *peerFlag;        // [nbIntf]: this subdomain's flag in the neighbour's window
+    const unsigned *localFlags;       // [nbIntf]: the neighbours' flags in this window
+    const double *localRecv[2];       // this window's receive buffers, laid out like bufferRecv (segment i at intfIndex[i] * dim)
+    const int *uniqNodes, *slotIndex, *slots, *diagIndex, *checkBounds;
+};
+cudaError_t launch_halo_p2p (const HaloP2PArgs &args, int operatorDim, int ctas, cudaStream_t stream);
+
 // compute_double_norm (FEM.cc:48-56) of a device array; `partials` holds double_norm_scratch_doubles().
 int double_norm_scratch_doubles ();
 cudaError_t launch_double_norm (const double *x, int64_t n, double *partials, double *out, cudaStream_t stream);
@@ -90,7 +113,10 @@ cudaError_t ring_configure (int operatorID);
 cudaError_t ring_ctas_per_sm (int operatorID, int threads, size_t smemBytes, int *ctas);
 cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,
                          int threads, size_t smemBytes, const double *coord, double *values, double *prec,
-                         int fusePrec, cudaStream_t stream);      // the Dirichlet mask travels in the plan (RingRow::node)
+                         int fusePrec, cudaStream_t stream,       // the Dirichlet mask travels in the plan (RingRow::node)
+                         unsigned *intfDone = nullptr);           // peer-to-peer halo: counter of finished (write-out warp, interface tile) pairs
+// write-out warps per CTA: an interface tile adds that many to *intfDone
+int ring_write_out_warps (int operatorID, int threads);
 
 }  // namespace mfb
 

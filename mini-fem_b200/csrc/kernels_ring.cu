@@ -52,6 +52,8 @@ struct RingArgs {
     double *prec;
     int fusePrec;
     int firstTile, lastTile;      // [firstTile, lastTile)
+    unsigned *intfDone;           // peer-to-peer halo (kernels_halo_p2p.cu): every write-out warp adds one after it has
+                                  // written its rows of a tile that owns interface nodes (null: no signal)
 };
 
 // tileOffset entries: byte offset of the record in the low 48 bits, (head bytes / 16) above
@@ -70,6 +72,10 @@ inline void ring_bar_sync (int id, int count) { cta_emu::bar_sync (id, count); }
 inline void ring_cp_async_f64 (double *dst, const double *src) { *dst = *src; }
 inline void ring_cp_async_wait_all () {}
 inline void ring_cp_async_arrive (uint64_t *bar) { cta_emu::mbar_arrive (bar); }
+template <int REGS> inline void ring_regs_inc () {}
+template <int REGS> inline void ring_regs_dec () {}
+inline void ring_signal_add (unsigned *counter) { __atomic_fetch_add (counter, 1u, __ATOMIC_RELEASE); }
+inline void ring_fence_gpu () { __atomic_thread_fence (__ATOMIC_SEQ_CST); }
 #else
 __device__ __forceinline__ unsigned ring_smem_u32 (const void *p) { return (unsigned)__cvta_generic_to_shared (p); }
 
@@ -129,6 +135,19 @@ __device__ __forceinline__ void ring_cp_async_arrive (uint64_t *bar)
     asm volatile ("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(ring_smem_u32 (bar)) : "memory");
 }
 
+// Register reallocation between the warpgroups of a CTA (setmaxnreg, sm_90a+; SASS: USETMAXREG): the 1024-thread
+// kernel is launched with 64 registers per thread; its write-out warpgroups give registers back, its job
+// warpgroups take them.  ptxas allocates each branch within the count named there.
+template <int REGS> __device__ __forceinline__ void ring_regs_inc () { if (REGS > 0) asm volatile ("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(REGS > 0 ? REGS : 24)); }
+template <int REGS> __device__ __forceinline__ void ring_regs_dec () { if (REGS > 0) asm volatile ("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REGS > 0 ? REGS : 24)); }
+
+__device__ __forceinline__ void ring_fence_gpu () { __threadfence (); }
+// one more write-out warp is done with a tile that owns interface nodes: its stores to prec are ordered before the add
+__device__ __forceinline__ void ring_signal_add (unsigned *counter)
+{
+    asm volatile ("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+}
+
 #endif
 
 __host__ __device__ __forceinline__ unsigned ring_align128 (unsigned x) { return (x + 127u) & ~127u; }
@@ -154,6 +173,36 @@ __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim ==
 //     their use — and the plan head of tile k + 3.
 // No block barrier after the prologue.  THREADS = 768 (default): 13 job warps + 11 write-out warps (elasticity), one CTA per SM,
 // tiles of <= 64 rows; THREADS = 384: 7 + 5, two CTAs per SM, tiles of <= 30 rows.
+// Coordinates of tile k + 2: 0 = 8-byte cp.async copies signalled on the tail barrier (no registers, no wait, but every
+// copy costs a shared-memory wavefront on arrival: ~11 M of the 74 M of an EIB iteration); 1 = plain loads issued at the
+// end of the previous tile's write-out, stored side by side (two wavefronts per 32 nodes) once the buffer is free.
+#ifndef MFB_RING_STAGE_LDG
+#define MFB_RING_STAGE_LDG 0
+#endif
+
+// Warps per role.  job warps out of 24, measured on the EIB mesh (ms per iteration, final pipeline): elasticity, 768 threads: 12: 0.421,
+// 13: 0.414, 15: 0.439, 16: 0.449; 384 threads (x 2 CTAs): 6 of 12: 0.458, 7: 0.430, 8: 0.482.  The Laplacian has an
+// eighth of the write-out work per row and wants more job warps (768 threads, 20 + 4: 0.252).
+// 1024 threads: warpgroups (4 warps) change their register count after the prologue — job warps 72, write-out warps 56
+// (elasticity, 16 + 16) resp. 40 (Laplacian, 24 + 8): 32 warps instead of the 24 that 80 registers per thread allow.
+__host__ __device__ constexpr int ring_job_warps (int opDim, int threads)
+{
+#ifdef MFB_RING_JOB_WARPS_OF_24
+    return threads / 32 * MFB_RING_JOB_WARPS_OF_24 / 24;
+#else
+    return threads == 1024 ? (opDim == 1 ? 24 : 16)
+                           : threads / 32 * (opDim == 1 ? (threads == 768 ? 20 : 16) : (threads == 768 ? 13 : 14)) / 24;
+#endif
+}
+#ifndef MFB_RING_JOB_REGS
+#define MFB_RING_JOB_REGS 72
+#endif
+#ifndef MFB_RING_OUT_REGS
+#define MFB_RING_OUT_REGS 56
+#endif
+__host__ __device__ constexpr int ring_job_regs (int opDim, int threads) { return threads == 1024 ? (opDim == 1 ? 72 : MFB_RING_JOB_REGS) : 0; }
+__host__ __device__ constexpr int ring_out_regs (int opDim, int threads) { return threads == 1024 ? (opDim == 1 ? 40 : MFB_RING_OUT_REGS) : 0; }
+
 constexpr int kRingHeadBuffers = 5;      // heads of tiles k - 1 .. k + 3 are alive while the write-out warps work on tile k
 
 inline RingSmemLayout ring_smem_layout (int operatorID, const DeviceRingPlan &plan)
@@ -180,15 +229,9 @@ ring_assembly_kernel (const RingArgs args)
 #else
     extern __shared__ __align__(128) unsigned char smemRaw[];
 #endif
-    // job warps out of 24, measured on the EIB mesh (ms per iteration, final pipeline): elasticity, 768 threads: 12: 0.421,
-    // 13: 0.414, 15: 0.439, 16: 0.449; 384 threads (x 2 CTAs): 6 of 12: 0.458, 7: 0.430, 8: 0.482.  The Laplacian has an
-    // eighth of the write-out work per row and wants more job warps (768 threads, 20 + 4: 0.252).
-#ifdef MFB_RING_JOB_WARPS_OF_24
-    constexpr int kJobOf24 = MFB_RING_JOB_WARPS_OF_24;
-#else
-    constexpr int kJobOf24 = OPDIM == 1 ? (THREADS == 768 ? 20 : 16) : (THREADS == 768 ? 13 : 14);
-#endif
-    constexpr int NWARPS = THREADS / 32, NJOB = NWARPS * kJobOf24 / 24, NOUT = NWARPS - NJOB;
+    constexpr int NWARPS = THREADS / 32, NJOB = ring_job_warps (OPDIM, THREADS), NOUT = NWARPS - NJOB;
+    static_assert (NJOB > 0 && NOUT > 0 && (THREADS != 1024 || (NJOB % 4 == 0 && 32 * (NJOB * ring_job_regs (OPDIM, THREADS) + NOUT * ring_out_regs (OPDIM, THREADS)) <= 65536)),
+                   "setmaxnreg works on whole warpgroups and within the register file");
     const DeviceRingPlan &P = args.plan;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -222,6 +265,7 @@ ring_assembly_kernel (const RingArgs args)
 
     if (warp < NJOB) {
         // =============================== job warps ===============================================
+        ring_regs_inc<ring_job_regs (OPDIM, THREADS)> ();
         for (int k = 0; k < nbMine; k++) {
             wait_head (k);
             const unsigned char *sHead = head_of (k);
@@ -324,6 +368,7 @@ ring_assembly_kernel (const RingArgs args)
     }
     else {
         // =============================== write-out warps =========================================
+        ring_regs_dec<ring_out_regs (OPDIM, THREADS)> ();
         const int ow = warp - NJOB, otid = tid - NJOB * 32;          // 0 .. NOUT * 32 - 1
         auto tile_of = [&] (int k) { return firstTile + k * tileStep; };
         auto fetch_head = [&] (uint64_t packed, int k) {              // one thread
@@ -350,6 +395,26 @@ ring_assembly_kernel (const RingArgs args)
             offA = P.tileOffset[tile_of (0)];
             if (nbMine > 1) offB = P.tileOffset[tile_of (1)];
         }
+#if MFB_RING_STAGE_LDG
+        constexpr int NPT = (kRingMaxNodes + NOUT * 32 - 1) / (NOUT * 32);     // nodes per write-out thread
+        double stage[NPT][3];
+        auto load_coords = [&] (int kq) {                                   // the coordinates tile kq will need, into registers
+            if (kq >= nbMine) return;
+            wait_head (kq);
+            const unsigned char *qh = head_of (kq);
+            const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (qh);
+            const int *nodes = reinterpret_cast<const int*> (qh + h.offNodes);
+            #pragma unroll
+            for (int q = 0; q < NPT; q++) {
+                const int n = otid + q * (NOUT * 32);
+                if (n < h.nbNodes) {
+                    const double *g = args.coord + (size_t)nodes[n] * 3;
+                    stage[q][0] = g[0]; stage[q][1] = g[1]; stage[q][2] = g[2];
+                }
+            }
+        };
+        load_coords (0);
+#endif
         // k = -2, -1: nothing to write out yet, only the first two tiles to stage
         for (int k = -2; k < nbMine; k++) {
             // (no barrier among the write-out warps: full[k & 1] implies that every one of them has finished tile
@@ -363,16 +428,27 @@ ring_assembly_kernel (const RingArgs args)
                 const unsigned char *nh = head_of (kn);
                 const RingTileHeader &h = *reinterpret_cast<const RingTileHeader*> (nh);
                 if (otid == 0) fetch_tail (offA, kn);
-                // coordinates: asynchronous 8-byte copies that signal tailFull[kn & 1] when they have landed (each costs a
-                // shared-memory wavefront on arrival — the kernel is not bound by those — but no register, no wait)
-                const int *nodes = reinterpret_cast<const int*> (nh + h.offNodes);
                 double *pl = planes0 + (kn & 1) * (3 * planeStride);
+#if MFB_RING_STAGE_LDG
+                // coordinates: loaded into registers at the end of the previous write-out (load_coords), stored side by
+                // side now that the job warps have released the planes
+                #pragma unroll
+                for (int q = 0; q < NPT; q++) {
+                    const int n = otid + q * (NOUT * 32);
+                    if (n < h.nbNodes) { pl[n] = stage[q][0]; pl[planeStride + n] = stage[q][1]; pl[2 * planeStride + n] = stage[q][2]; }
+                }
+                ring_mbar_arrive (tailFull + (kn & 1));
+#else
+                // coordinates: asynchronous 8-byte copies that signal tailFull[kn & 1] when they have landed (each costs a
+                // shared-memory wavefront on arrival, but no register, no wait)
+                const int *nodes = reinterpret_cast<const int*> (nh + h.offNodes);
                 for (int n = otid; n < h.nbNodes; n += NOUT * 32) {
                     const double *g = args.coord + (size_t)nodes[n] * 3;
                     ring_cp_async_f64 (pl + n, g); ring_cp_async_f64 (pl + planeStride + n, g + 1);
                     ring_cp_async_f64 (pl + 2 * planeStride + n, g + 2);
                 }
                 ring_cp_async_arrive (tailFull + (kn & 1));
+#endif
             }
             if (otid == 0) {
                 // head of tile k + 3 into the buffer of tile k - 2 (five buffers)
@@ -413,7 +489,9 @@ ring_assembly_kernel (const RingArgs args)
                     const bool worker = grp < 3 && comp < 9;
                     const int ca = comp / 3, cb = comp - 3 * ca;              // component (ca, cb) of the 3x3 block
                     const int base = worker ? 10 * grp : lane;                // first lane of the row's nine; idle lanes read themselves
-                    for (int r0 = ow * 3; r0 < nbRows; r0 += NOUT * 3) {
+                    // (1024 threads: 21 row groups of a 63-row tile over 16 warps — the warps that take two change from tile to tile)
+                    const int ow3 = (THREADS == 1024 ? (ow + NOUT - (k * 5) % NOUT) % NOUT : ow) * 3;
+                    for (int r0 = ow3; r0 < nbRows; r0 += NOUT * 3) {
                         const int r = r0 + grp;
                         const bool rowOk = worker && r < nbRows;
                         int node = 0, diagOff = 0xFFFF;
@@ -474,6 +552,15 @@ ring_assembly_kernel (const RingArgs args)
                 __syncwarp ();
                 if (lane == 0) ring_mbar_arrive (ready + (kn & 1));
             }
+            // ---- peer-to-peer halo: this warp's rows of a tile that owns interface nodes are in global memory ----------
+            if (k >= 0 && args.intfDone != nullptr && reinterpret_cast<const RingTileHeader*> (head_of (k))->hasInterface) {
+                ring_fence_gpu ();
+                __syncwarp ();
+                if (lane == 0) ring_signal_add (args.intfDone);
+            }
+#if MFB_RING_STAGE_LDG
+            load_coords (k + 3);
+#endif
         }
     }
 }
@@ -489,6 +576,11 @@ cudaError_t ring_opt_in (K kernel)
 
 }  // namespace
 
+int ring_write_out_warps (int operatorID, int threads)
+{
+    return threads / 32 - ring_job_warps (operatorID == 0 ? 1 : 9, threads);
+}
+
 size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
 {
     return ring_smem_layout (operatorID, plan).total;
@@ -500,9 +592,11 @@ cudaError_t ring_configure (int operatorID)
     cudaError_t e;
     if (operatorID == 0) {
         if ((e = ring_opt_in (ring_assembly_kernel<1, 384, 2>)) != cudaSuccess) return e;
+        if ((e = ring_opt_in (ring_assembly_kernel<1, 1024, 1>)) != cudaSuccess) return e;
         return ring_opt_in (ring_assembly_kernel<1, 768, 1>);
     }
     if ((e = ring_opt_in (ring_assembly_kernel<9, 384, 2>)) != cudaSuccess) return e;
+    if ((e = ring_opt_in (ring_assembly_kernel<9, 1024, 1>)) != cudaSuccess) return e;
     return ring_opt_in (ring_assembly_kernel<9, 768, 1>);
 }
 
@@ -512,13 +606,17 @@ cudaError_t ring_ctas_per_sm (int operatorID, int threads, size_t smemBytes, int
         return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 768, 1>, 768, smemBytes)
                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 768, 1>, 768, smemBytes);
     }
+    if (threads == 1024) {
+        return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 1024, 1>, 1024, smemBytes)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 1024, 1>, 1024, smemBytes);
+    }
     return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 384, 2>, 384, smemBytes)
                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 384, 2>, 384, smemBytes);
 }
 
 cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,
                          int threads, size_t smemBytes, const double *coord, double *values, double *prec,
-                         int fusePrec, cudaStream_t stream)
+                         int fusePrec, cudaStream_t stream, unsigned *intfDone)
 {
     if (nbTiles <= 0) return cudaSuccess;
     RingArgs args;
@@ -526,8 +624,13 @@ cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTi
     args.coord = coord; args.values = values; args.prec = prec;
     args.fusePrec = fusePrec;
     args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
+    args.intfDone = intfDone;
     const int grid = std::max (1, std::min (ctas, nbTiles));
-    if (threads == 768) {
+    if (threads == 1024) {
+        if (operatorID == 0) ring_assembly_kernel<1, 1024, 1><<<grid, 1024, smemBytes, stream>>> (args);
+        else                 ring_assembly_kernel<9, 1024, 1><<<grid, 1024, smemBytes, stream>>> (args);
+    }
+    else if (threads == 768) {
         if (operatorID == 0) ring_assembly_kernel<1, 768, 1><<<grid, 768, smemBytes, stream>>> (args);
         else                 ring_assembly_kernel<9, 768, 1><<<grid, 768, smemBytes, stream>>> (args);
     }

@@ -182,6 +182,10 @@ void get_average_cycles (const Timer &asmT, const Timer &initT, const Timer &hal
             }
             remove (mine.c_str ());
             remove ((rendezvous + "/nccl_id" + run_token ()).c_str ());      // every rank has initialised its communicator long ago
+            for (int r = 0; r < nbBlocks; r++) {                             // ... and mapped its neighbours' windows
+                remove ((rendezvous + "/p2p_card" + run_token () + "_" + to_string (r)).c_str ());
+                remove ((rendezvous + "/p2p_ok" + run_token () + "_" + to_string (r)).c_str ());
+            }
         }
     }
     if (rank == 0) {
@@ -400,6 +404,37 @@ int main (int argCount, char **argValue)
             f.read ((char*)id, sizeof id);
         }
         check (mfb_ctx_comm_init (ctx, id), "NCCL communicator");
+        // Peer-to-peer windows for the fused RING iteration (mfb_ctx_p2p_*; the GASPI segments of main.cc under
+        // -DGASPI): cards and the outcome travel through the rendezvous directory; every rank switches or none does.
+        if (path == MFB_PATH_RING && fused && env_str ("MFB_HALO", "p2p") != "nccl") {
+            auto put = [&] (const string &name, const void *data, size_t bytes) {
+                { ofstream f (name + ".tmp", ios::binary); f.write ((const char*)data, (streamsize)bytes); }
+                rename ((name + ".tmp").c_str (), name.c_str ());
+            };
+            const string cardBase = rendezvous + "/p2p_card" + run_token () + "_", okBase = rendezvous + "/p2p_ok" + run_token () + "_";
+            vector<unsigned char> cards ((size_t)nbBlocks * MFB_P2P_CARD_BYTES, 0);
+            char ok = mfb_ctx_p2p_card (ctx, cards.data () + (size_t)rank * MFB_P2P_CARD_BYTES) == MFB_OK;
+            put (cardBase + to_string (rank), cards.data () + (size_t)rank * MFB_P2P_CARD_BYTES, MFB_P2P_CARD_BYTES);
+            for (int r = 0; r < nbBlocks; r++) {
+                if (r == rank) continue;
+                wait_for_file (cardBase + to_string (r));
+                ifstream f (cardBase + to_string (r), ios::binary);
+                f.read ((char*)cards.data () + (size_t)r * MFB_P2P_CARD_BYTES, MFB_P2P_CARD_BYTES);
+            }
+            if (ok) ok = mfb_ctx_p2p_connect (ctx, cards.data ()) == MFB_OK;
+            put (okBase + to_string (rank), &ok, 1);
+            bool all = ok != 0;
+            for (int r = 0; r < nbBlocks; r++) {
+                if (r == rank) continue;
+                wait_for_file (okBase + to_string (r));
+                ifstream f (okBase + to_string (r), ios::binary);
+                char theirs = 0;
+                f.read (&theirs, 1);
+                all = all && theirs != 0;
+            }
+            if (!all && ok) check (mfb_ctx_p2p_enable (ctx, 0), "peer-to-peer exchange off");
+            if (rank == 0) cout << "Interface sum: " << (all ? "peer-to-peer windows (NVLink stores + epoch flags)" : "NCCL send / recv") << "\n";
+        }
     }
     end_step ();
 

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("MFB_LIBRARY") or os.path.join(PKG_ROOT, "libminifem_b
 PATH_TILED, PATH_ATOMIC, PATH_COLOR, PATH_RING = 0, 1, 2, 3
 PATH_NAMES = {"tiled": PATH_TILED, "atomic": PATH_ATOMIC, "color": PATH_COLOR, "ring": PATH_RING}
 COMM_ID_BYTES = 128
+P2P_CARD_BYTES = 1024
 
 
 class MfbError(RuntimeError):
@@ -89,6 +90,10 @@ lib.mfb_ctx_device_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER
 lib.mfb_ctx_plan_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
 lib.mfb_comm_unique_id.argtypes = [C.c_void_p]
 lib.mfb_ctx_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+lib.mfb_ctx_p2p_card.argtypes = [C.c_void_p, C.c_void_p]
+lib.mfb_ctx_p2p_connect.argtypes = [C.c_void_p, C.c_void_p]
+lib.mfb_ctx_p2p_enable.argtypes = [C.c_void_p, C.c_int]
+lib.mfb_ctx_p2p_active.argtypes = [C.c_void_p]
 lib.mfb_ctx_halo_pack_host.argtypes = [C.c_void_p, C.c_void_p]
 lib.mfb_ctx_halo_add_host.argtypes = [C.c_void_p, C.c_void_p]
 lib.mfb_ctx_prec_inversion_interface.argtypes = [C.c_void_p]
@@ -125,6 +130,7 @@ DECLARED_SYMBOLS = [
     "mfb_host_free", "mfb_device_count",
     "mfb_device_create_nodeToNode", "mfb_device_create_elemToEdge", "mfb_device_coloring_creation",
     "mfb_ctx_norms", "mfb_ctx_iteration_norms_host",
+    "mfb_ctx_p2p_card", "mfb_ctx_p2p_connect", "mfb_ctx_p2p_enable", "mfb_ctx_p2p_active",
 ]
 
 
@@ -453,6 +459,21 @@ class Context:
     def comm_init(self, unique_id: bytes):
         buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(unique_id)
         _check(lib.mfb_ctx_comm_init(self.handle, buf), "mfb_ctx_comm_init")
+
+    # peer-to-peer exchange of the fused RING iteration (include/minifem_b200.h: mfb_ctx_p2p_*)
+    def p2p_card(self) -> bytes:
+        buf = (C.c_ubyte * P2P_CARD_BYTES)()
+        _check(lib.mfb_ctx_p2p_card(self.handle, buf), "mfb_ctx_p2p_card")
+        return bytes(buf)
+
+    def p2p_connect(self, cards):
+        """cards: the p2p_card() of every subdomain, in rank order."""
+        blob = b"".join(cards)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _check(lib.mfb_ctx_p2p_connect(self.handle, buf), "mfb_ctx_p2p_connect")
+
+    def p2p_enable(self, on=True): _check(lib.mfb_ctx_p2p_enable(self.handle, int(bool(on))), "mfb_ctx_p2p_enable")
+    def p2p_active(self): return bool(lib.mfb_ctx_p2p_active(self.handle))
 
 
 def comm_unique_id() -> bytes:

@@ -43,6 +43,46 @@ def comm_init(ctx):
     ctx.comm_init(uid)
 
 
+def all_gather_bytes(payload, length):
+    """Every rank's `length` bytes, in rank order."""
+    if not dist.is_initialized():
+        return [bytes(payload)]
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    parts = [torch.zeros(length, dtype=torch.uint8, device=dev) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    return [bytes(t.cpu().numpy().tobytes()) for t in parts]
+
+
+def p2p_connect(ctx):
+    """Peer-to-peer exchange of the fused RING iteration (mfb_ctx_p2p_*): every rank publishes its card, the cards
+    travel through torch.distributed, every rank maps its neighbours' windows.  All ranks switch together: if any of
+    them cannot connect (no peer access, cudaIpc refused, more than 64 interfaces) everybody stays on NCCL.  Returns
+    (active, reason).  MFB_HALO=nccl keeps the NCCL exchange."""
+    from . import MfbError, P2P_CARD_BYTES
+    if os.environ.get("MFB_HALO", "p2p").lower() == "nccl":
+        return False, "MFB_HALO=nccl"
+    why = ""
+    try:
+        card = ctx.p2p_card()
+    except MfbError as e:
+        card, why = bytes(P2P_CARD_BYTES), str(e)
+    cards = all_gather_bytes(card, P2P_CARD_BYTES)
+    ok = 0.0
+    if not why:
+        try:
+            ctx.p2p_connect(cards)
+            ok = 1.0
+        except MfbError as e:
+            why = str(e)
+    everyone = -max_over_ranks(-ok)                     # min over ranks
+    if everyone < 1.0:
+        if ok:
+            ctx.p2p_enable(False)
+        return False, why or "another rank could not connect"
+    return True, ""
+
+
 def max_over_ranks(value):
     if not dist.is_initialized():
         return float(value)

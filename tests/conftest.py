@@ -9,6 +9,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 
 
+# tests/test_gpu_multirank.py keeps the contexts of up to four subdomains (two streams each) in this process and lets
+# their kernels wait for each other: more hardware queues than the default 8, so that no stream queues behind another
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -34,8 +34,19 @@ for op in ("lap", "ela"):
         ctx = mfb.Context(s, path=path, device=int(os.environ.get("LOCAL_RANK", rank)), nbBlocks=world, rank=rank,
                           tile_rows=32 if path != "ring" else 16, tile_elems=400 if path != "ring" else 300)
         mdist.comm_init(ctx)
-        for mode in ("fused", "staged"):
-            if mode == "fused":
+        modes = ["fused", "staged"]
+        if path == "ring":
+            # the same fused iteration over the peer-to-peer windows (cudaIpc between the rank processes), twice
+            # (both receive-buffer parities), then NCCL again
+            active, why = mdist.p2p_connect(ctx)
+            assert active or os.environ.get("MFB_HALO", "") == "nccl", why
+            if active:
+                modes = ["fused", "fused", "fused", "staged", "nccl"]
+        for mode in modes:
+            if mode == "nccl":
+                ctx.p2p_enable(False)
+                ctx.iteration()
+            elif mode == "fused":
                 ctx.iteration()
             else:
                 ctx.stages()

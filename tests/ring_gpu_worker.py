@@ -63,6 +63,8 @@ def main():
         check(oracle, f"{op} large tiles", mfb.Setup(mesh, op), tile_rows=64, tile_elems=960)
         check(oracle, f"{op} 384 threads (two CTAs per SM)", mfb.Setup(mesh, op), threads=384)
         check(oracle, f"{op} 384 threads, small caps", mfb.Setup(mesh, op), threads=384, tile_rows=22, tile_elems=352)
+        check(oracle, f"{op} 1024 threads (warpgroups with their own register counts)", mfb.Setup(mesh, op), threads=1024)
+        check(oracle, f"{op} 1024 threads, small caps, staged", mfb.Setup(mesh, op), False, threads=1024, tile_rows=22, tile_elems=352)
         check(oracle, f"{op} one CTA", mfb.Setup(mesh, op), ctas=1)
         check(oracle, f"{op} one tile per CTA", mfb.Setup(mesh, op), ctas=-1)
         check(oracle, f"{op} plan order", mfb.Setup(mesh, op), bank_aware=False)

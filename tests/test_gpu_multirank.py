@@ -85,6 +85,62 @@ def test_fused_interface_split_matches_oracle():
     atomic.close()
 
 
+@pytest.mark.parametrize("op,grid,blocks,threads", [("ela", (12, 10, 8), (2, 1, 1), 0), ("lap", (9, 8, 7), (2, 2, 1), 0),
+                                                     ("ela", (8, 8, 8), (2, 2, 1), 384), ("ela", (9, 8, 7), (2, 2, 1), 1024)])
+def test_p2p_exchange_between_contexts_of_one_process(op, grid, blocks, threads):
+    """The peer-to-peer halo (csrc/kernels_halo_p2p.cu) with every subdomain's context in this process, on one GPU:
+    windows are connected through plain device pointers, every iteration is two launches per subdomain (exchange
+    kernel + RING assembly kernel over all tiles) and the kernels of the subdomains find each other through the
+    epoch flags.  Several iterations in a row exercise both receive-buffer parities; results against the oracle's
+    multi-subdomain FEM iteration (faces, edges and corners shared by up to 8 subdomains)."""
+    n = int(np.prod(blocks))
+    dim = 1 if op == "lap" else 9
+    oracle = Oracle()
+    meshes = [mfb.Mesh.generate(*grid, blocks=blocks, rank=r, seed=5) for r in range(n)]
+    setups = [mfb.Setup(m, op) for m in meshes]
+    results = [oracle.fem_iteration(s) for s in setups]
+    precs = [np.ascontiguousarray(res[1]) for res in results]
+    oracle.halo_exchange(precs, [m.intfIndex for m in meshes], [m.intfNodes for m in meshes],
+                         [m.neighborsList for m in meshes], dim)
+    want = [oracle.prec_inversion(precs[r], s.row, s.col, s.checkBounds, s.mesh.nbNodes, s.operatorID) for r, s in enumerate(setups)]
+    ctxs = [mfb.Context(s, path="ring", nbBlocks=n, rank=r, tile_rows=12, tile_elems=240, threads=threads) for r, s in enumerate(setups)]
+    with pytest.raises(mfb.MfbError, match="comm_init or mfb_ctx_p2p_connect"):
+        ctxs[0].iteration()
+    cards = [c.p2p_card() for c in ctxs]
+    for c in ctxs:
+        c.p2p_connect(cards)
+        assert c.p2p_active()
+    for it in range(3):
+        before = [c.launch_count() for c in ctxs]
+        for c in ctxs:
+            c.iteration()                              # asynchronous: the kernels of all subdomains are in flight together
+        for r, c in enumerate(ctxs):
+            c.sync()
+            assert c.launch_count() - before[r] == 2
+            v, p = c.download()
+            assert row_scaled_error(v, results[r][0], setups[r].row, dim) <= RTOL, (it, r)
+            assert block_scaled_error(p, want[r], dim) <= RTOL, (it, r)
+    for c in ctxs:
+        c.close()
+
+
+def test_p2p_card_checks():
+    meshes = [mfb.Mesh.generate(6, 5, 4, blocks=(2, 1, 1), rank=r, seed=5) for r in range(2)]
+    setups = [mfb.Setup(m, "ela") for m in meshes]
+    tiled = mfb.Context(setups[0], path="tiled", nbBlocks=2, rank=0)
+    with pytest.raises(mfb.MfbError, match="RING"):
+        tiled.p2p_card()
+    tiled.close()
+    ring = mfb.Context(setups[0], path="ring", nbBlocks=2, rank=0)
+    with pytest.raises(mfb.MfbError, match="p2p_card first"):
+        ring.p2p_connect([bytes(mfb.P2P_CARD_BYTES)] * 2)
+    card = ring.p2p_card()
+    with pytest.raises(mfb.MfbError, match="published no card"):
+        ring.p2p_connect([card, bytes(mfb.P2P_CARD_BYTES)])
+    assert not ring.p2p_active()
+    ring.close()
+
+
 @pytest.mark.parametrize("nranks", [2])
 def test_nccl_halo_under_torchrun(nranks, tmp_path):
     import torch

@@ -224,7 +224,8 @@ def test_ring_plan_property(ringlib, oracle):
 
 @pytest.fixture(scope="module")
 def kernel_host():
-    lib = C.CDLL(os.path.join(ROOT, "tools", "libmfb_ringkernel_host.so"))
+    # MFB_RINGKERNEL_HOST_LIB: another build of the same test aid (e.g. -DMFB_RING_STAGE_LDG=1, the other staging variant)
+    lib = C.CDLL(os.environ.get("MFB_RINGKERNEL_HOST_LIB") or os.path.join(ROOT, "tools", "libmfb_ringkernel_host.so"))
     lib.mfb_ring_kernel_host_error.restype = C.c_char_p
     lib.mfb_ring_kernel_host.argtypes = [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_int]
     return lib
@@ -271,6 +272,16 @@ def test_ring_kernel_source_768_threads(kernel_host, oracle, op):
     mesh = mfb.Mesh.generate(9, 8, 8, seed=9)
     setup = mfb.Setup(mesh, op)
     values, prec = run_kernel_on_host(kernel_host, setup, rows=54, entries=960, ctas=2, threads=768)
+    check_against_oracle(oracle, setup, values, prec)
+
+
+@pytest.mark.parametrize("op", ["ela", "lap"])
+def test_ring_kernel_source_1024_threads(kernel_host, oracle, op):
+    """The 1024-thread instantiation (warpgroups with their own register counts on the device: 16 job + 16 write-out warps
+    for elasticity, 24 + 8 for the Laplacian; the write-out warps that take a second row group change from tile to tile)."""
+    mesh = mfb.Mesh.generate(9, 8, 8, seed=10)
+    setup = mfb.Setup(mesh, op)
+    values, prec = run_kernel_on_host(kernel_host, setup, rows=64, entries=1100, ctas=2, threads=1024)
     check_against_oracle(oracle, setup, values, prec)
 
 

@@ -44,13 +44,20 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
     args.smem = ring_smem_layout (operatorID, args.plan);
     args.coord = coord; args.values = values; args.prec = prec;
     args.fusePrec = fusePrec; args.firstTile = 0; args.lastTile = hp.nbTiles;
+    static unsigned intfDone;
+    intfDone = 0;
+    args.intfDone = isInterface ? &intfDone : nullptr;
     if (hp.nbTiles == 0) return 0;
     const size_t smem = ring_smem_bytes (operatorID, args.plan);
     auto launch = [&] (int firstTile, int nbTiles, int grid) {
         if (nbTiles <= 0) return;
         args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
         grid = std::max (1, std::min (grid, nbTiles));
-        if (threads == 768) {
+        if (threads == 1024) {
+            if (operatorID == 0) cta_emu::launch (grid, 1024, smem, [&] () { ring_assembly_kernel<1, 1024, 1> (args); });
+            else                 cta_emu::launch (grid, 1024, smem, [&] () { ring_assembly_kernel<9, 1024, 1> (args); });
+        }
+        else if (threads == 768) {
             if (operatorID == 0) cta_emu::launch (grid, 768, smem, [&] () { ring_assembly_kernel<1, 768, 1> (args); });
             else                 cta_emu::launch (grid, 768, smem, [&] () { ring_assembly_kernel<9, 768, 1> (args); });
         }
@@ -68,5 +75,9 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
         launch (nIntf, nInterior, (nInterior + 3) / 4);
     }
     else launch (0, hp.nbTiles, grid);
+    if (isInterface && (int)intfDone != hp.nbInterfaceTiles * ring_write_out_warps (operatorID, threads == 768 || threads == 1024 ? threads : 384)) {
+        g_error = "interface signal: " + std::to_string (intfDone) + " arrivals for " + std::to_string (hp.nbInterfaceTiles) + " interface tiles";
+        return -1;
+    }
     return 0;
 }
