@@ -384,8 +384,8 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     // two slabs per CTA: 30 rows / 510 slots keep two 384-thread CTAs per SM, 64 rows / 1100 slots fit the
     // single 768-thread CTA
     RingPlanLimits lim;
-    lim.maxRows = c->threads >= 768 ? 64 : 30;
-    lim.maxEntries = c->threads >= 768 ? 1100 : 510;
+    lim.maxRows = c->threads >= 640 ? 64 : 30;
+    lim.maxEntries = c->threads >= 640 ? 1100 : 510;
     if (o && o->tileRows > 0) lim.maxRows = o->tileRows;
     if (o && o->tileElems > 0) lim.maxEntries = o->tileElems;          // RING: tileElems caps the slab slots of a tile
     lim.bankAware = !(o && o->bankAware < 0);
@@ -418,7 +418,7 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     c->ringStats = hp;
     if (const char *v = getenv ("MFB_HALO_OVERLAP")) c->haloCoresident = std::string (v) == "coresident";
     if (const char *v = getenv ("MFB_INTERIOR_TILES_PER_CTA")) c->interiorTilesPerCta = std::max (atoi (v), 1);
-    c->haloReserveCtas = c->threads >= 768 ? 4 : 8;            // four SMs either way
+    c->haloReserveCtas = c->threads >= 640 ? 4 : 8;            // four SMs either way
     if (const char *v = getenv ("MFB_HALO_RESERVE_CTAS")) c->haloReserveCtas = std::max (atoi (v), 0);
     if (const char *v = getenv ("MFB_MULTI_GPU_GRAPH")) c->multiGraph = atoi (v) != 0;
     c->tiledSmem = ring_smem_bytes (c->operatorID, c->ringPlan);
@@ -685,7 +685,7 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
         c->ring = true;
         c->path = MFB_PATH_TILED;
         if (!(o && o->threads > 0)) c->threads = 768;
-        if (c->threads != 384 && c->threads != 768 && c->threads != 1024) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 384 (two CTAs per SM), 768 or 1024 (one) threads per CTA");
+        if (!ring_threads_supported (c->threads)) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 384 (two CTAs per SM), 640, 768, 896 or 1024 (one) threads per CTA");
     }
     if (!c->ring && c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {
         return fail (MFB_ERR_ARG, "mfb_ctx_create: threads must be a multiple of 32 in [32, 256], or the pipelined kernel's CTA size");
@@ -1174,7 +1174,7 @@ extern "C" int mfb_ctx_p2p_connect (mfb_ctx *c, const unsigned char *cards)
     MFB_CUDA (upload (&c->dPeerFlag, peerFlag.data (), peerFlag.size (), bytes));
     c->p2pCtas = 4;
     if (const char *v = getenv ("MFB_P2P_CTAS")) c->p2pCtas = std::max (atoi (v), 1);
-    const int ctasPerSM = c->threads >= 768 ? 1 : 2;
+    const int ctasPerSM = c->threads >= 640 ? 1 : 2;
     c->p2pCtas = std::max (1, std::min (c->p2pCtas, c->haloReserveCtas / ctasPerSM));   // never more SMs than the assembly grid leaves free
     if (c->haloReserveCtas < ctasPerSM) return fail (MFB_ERR_STATE, "mfb_ctx_p2p_connect: MFB_HALO_RESERVE_CTAS leaves no SM to the exchange kernel");
     c->p2pReady = true;

@@ -109,6 +109,7 @@ struct DeviceRingPlan {
 };
 size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan);
 cudaError_t ring_configure (int operatorID);
+bool ring_threads_supported (int threads);          // CTA sizes the RING kernel is instantiated for
 // resident CTAs per SM of the RING kernel for this CTA size and dynamic shared memory (occupancy API)
 cudaError_t ring_ctas_per_sm (int operatorID, int threads, size_t smemBytes, int *ctas);
 cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,

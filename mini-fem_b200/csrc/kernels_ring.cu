@@ -52,6 +52,7 @@ struct RingArgs {
     double *prec;
     int fusePrec;
     int firstTile, lastTile;      // [firstTile, lastTile)
+    unsigned pollNs;              // sleep between two polls of a barrier (0: poll back to back)
     unsigned *intfDone;           // peer-to-peer halo (kernels_halo_p2p.cu): every write-out warp adds one after it has
                                   // written its rows of a tile that owns interface nodes (null: no signal)
 };
@@ -66,7 +67,7 @@ __device__ __forceinline__ unsigned ring_record_head_bytes (uint64_t packed) { r
 inline void ring_mbar_init (uint64_t *bar, unsigned count) { cta_emu::mbar_init (bar, count); }
 inline void ring_mbar_expect_tx (uint64_t *bar, unsigned bytes) { cta_emu::mbar_expect_tx (bar, bytes); }
 inline void ring_mbar_arrive (uint64_t *bar) { cta_emu::mbar_arrive (bar); }
-inline void ring_mbar_wait (uint64_t *bar, unsigned parity) { cta_emu::mbar_wait (bar, parity); }
+inline void ring_mbar_wait (uint64_t *bar, unsigned parity, unsigned = 0) { cta_emu::mbar_wait (bar, parity); }
 inline void ring_bulk_load (void *dst, const void *src, unsigned bytes, uint64_t *bar) { cta_emu::bulk_load (dst, src, bytes, bar); }
 inline void ring_bar_sync (int id, int count) { cta_emu::bar_sync (id, count); }
 inline void ring_cp_async_f64 (double *dst, const double *src) { *dst = *src; }
@@ -95,18 +96,23 @@ __device__ __forceinline__ void ring_mbar_arrive (uint64_t *bar)
     asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ring_smem_u32 (bar)) : "memory");
 }
 
-// Bounded wait: a protocol bug must trap instead of hanging the device.
-__device__ __forceinline__ void ring_mbar_wait (uint64_t *bar, unsigned parity)
+// Bounded wait: a protocol bug must trap instead of hanging the device.  try_wait suspends the warp until the next
+// event on the barrier or the hint runs out; at speed the loops take 1.8 % of the issue slots (PC samples,
+// profiles/r2_ring_wait_loops.txt — the instrumented instruction counts of ncu's source page overstate them 10x).
+// pollNs (MFB_RING_POLL_NS, default 0) adds a plain sleep between two polls.
+__device__ __forceinline__ void ring_mbar_wait (uint64_t *bar, unsigned parity, unsigned pollNs = 0)
 {
     unsigned done = 0;
+    #pragma unroll 1
     for (long spin = 0; spin < (1l << 18); spin++) {
         asm volatile (
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"     // suspended (no issue slots) until the phase
-            "selp.u32 %0, 1, 0, p;\n"                                          // completes or the hint (ns) runs out
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"     // suspended (no issue slots) until an event
+            "selp.u32 %0, 1, 0, p;\n"                                          // or the hint (ns) runs out
             "}\n" : "=r"(done) : "r"(ring_smem_u32 (bar)), "r"(parity), "r"(20000u) : "memory");
         if (done) return;
+        if (pollNs) __nanosleep (pollNs);
     }
     __trap ();
 }
@@ -191,6 +197,8 @@ __host__ __device__ constexpr int ring_job_warps (int opDim, int threads)
     return threads / 32 * MFB_RING_JOB_WARPS_OF_24 / 24;
 #else
     return threads == 1024 ? (opDim == 1 ? 24 : 16)
+         : threads == 896  ? (opDim == 1 ? 20 : 16)
+         : threads == 640  ? (opDim == 1 ? 16 : 11)
                            : threads / 32 * (opDim == 1 ? (threads == 768 ? 20 : 16) : (threads == 768 ? 13 : 14)) / 24;
 #endif
 }
@@ -200,9 +208,12 @@ __host__ __device__ constexpr int ring_job_warps (int opDim, int threads)
 #ifndef MFB_RING_OUT_REGS
 #define MFB_RING_OUT_REGS 56
 #endif
-__host__ __device__ constexpr int ring_job_regs (int opDim, int threads) { return threads == 1024 ? (opDim == 1 ? 72 : MFB_RING_JOB_REGS) : 0; }
-__host__ __device__ constexpr int ring_out_regs (int opDim, int threads) { return threads == 1024 ? (opDim == 1 ? 40 : MFB_RING_OUT_REGS) : 0; }
+// registers per thread after the prologue (0: as launched).  1024 threads are launched with 64: 16 x 72 + 16 x 56 (Laplacian
+// 24 x 72 + 8 x 40); 896 threads with 72: 16 x 80 + 12 x 56 (Laplacian 20 x 80 + 8 x 40)
+__host__ __device__ constexpr int ring_job_regs (int opDim, int threads) { return threads == 1024 ? (opDim == 1 ? 72 : MFB_RING_JOB_REGS) : threads == 896 ? 80 : 0; }
+__host__ __device__ constexpr int ring_out_regs (int opDim, int threads) { return threads == 1024 ? (opDim == 1 ? 40 : MFB_RING_OUT_REGS) : threads == 896 ? (opDim == 1 ? 40 : 56) : 0; }
 
+constexpr unsigned kRingPollNs = 0;      // default sleep between two polls of a barrier
 constexpr int kRingHeadBuffers = 5;      // heads of tiles k - 1 .. k + 3 are alive while the write-out warps work on tile k
 
 inline RingSmemLayout ring_smem_layout (int operatorID, const DeviceRingPlan &plan)
@@ -230,7 +241,7 @@ ring_assembly_kernel (const RingArgs args)
     extern __shared__ __align__(128) unsigned char smemRaw[];
 #endif
     constexpr int NWARPS = THREADS / 32, NJOB = ring_job_warps (OPDIM, THREADS), NOUT = NWARPS - NJOB;
-    static_assert (NJOB > 0 && NOUT > 0 && (THREADS != 1024 || (NJOB % 4 == 0 && 32 * (NJOB * ring_job_regs (OPDIM, THREADS) + NOUT * ring_out_regs (OPDIM, THREADS)) <= 65536)),
+    static_assert (NJOB > 0 && NOUT > 0 && (ring_job_regs (OPDIM, THREADS) == 0 || (NJOB % 4 == 0 && NOUT % 4 == 0 && 32 * (NJOB * ring_job_regs (OPDIM, THREADS) + NOUT * ring_out_regs (OPDIM, THREADS)) <= 65536)),
                    "setmaxnreg works on whole warpgroups and within the register file");
     const DeviceRingPlan &P = args.plan;
     const int tid = threadIdx.x;
@@ -256,7 +267,7 @@ ring_assembly_kernel (const RingArgs args)
     if (tid == 0) {
         for (int b = 0; b < kRingHeadBuffers; b++) ring_mbar_init (headFull + b, 1);
         // tailFull: the loader's TMA (one arrival + its bytes) and every write-out thread's share of the coordinates
-        for (int b = 0; b < 2; b++) { ring_mbar_init (tailFull + b, 1 + NOUT * 32); ring_mbar_init (full + b, NJOB); ring_mbar_init (ready + b, NOUT); }
+        for (int b = 0; b < 2; b++) { ring_mbar_init (tailFull + b, 1 + (MFB_RING_STAGE_LDG ? NOUT : NOUT * 32)); ring_mbar_init (full + b, NJOB); ring_mbar_init (ready + b, NOUT); }
     }
     __syncthreads ();          // the only block barrier
 
@@ -278,7 +289,7 @@ ring_assembly_kernel (const RingArgs args)
             const double *sX = planes0 + (k & 1) * (3 * planeStride), *sY = sX + planeStride, *sZ = sY + planeStride;
             double *slab = slab0 + (k & 1) * slabDoubles;
             const unsigned phase = (unsigned)(k >> 1) & 1u;
-            ring_mbar_wait (tailFull + (k & 1), phase);     // tail and coordinates of tile k are in (requested two tiles ago)
+            ring_mbar_wait (tailFull + (k & 1), phase, args.pollNs);     // tail and coordinates of tile k are in (requested two tiles ago)
             bool slabFree = false;                          // ready[k & 1] (slab drained by the write-out of tile k - 2) is only
                                                             // needed when the first block is stored, a whole batch from now
             // the batches of a tile go round the job warps, starting where the previous tile stopped
@@ -337,7 +348,7 @@ ring_assembly_kernel (const RingArgs args)
                         have = true;
                     }
                 }
-                if (!slabFree) { ring_mbar_wait (ready + (k & 1), phase); slabFree = true; }
+                if (!slabFree) { ring_mbar_wait (ready + (k & 1), phase, args.pollNs); slabFree = true; }
                 if (sIJ != 0xFFFF) {
                     if (OPDIM == 1) {
                         slab[sIJ] = acc[0];
@@ -359,7 +370,7 @@ ring_assembly_kernel (const RingArgs args)
                     }
                 }
             }
-            if (!slabFree) ring_mbar_wait (ready + (k & 1), phase);   // also without a batch: full[] then implies that every
+            if (!slabFree) ring_mbar_wait (ready + (k & 1), phase, args.pollNs);   // also without a batch: full[] then implies that every
                                                                       // write-out warp is done with tile k - 2
             __syncwarp ();
             if (lane == 0) ring_mbar_arrive (full + (k & 1));   // this warp's share of tile k is in the slab; it no longer
@@ -420,7 +431,7 @@ ring_assembly_kernel (const RingArgs args)
             // (no barrier among the write-out warps: full[k & 1] implies that every one of them has finished tile
             // k - 2 — the job warps could not have stored tile k otherwise — and the head fetched below replaces that of
             // tile k - 2)
-            if (k >= 0) ring_mbar_wait (full + (k & 1), (unsigned)(k >> 1) & 1u);   // the job warps are done with tile k
+            if (k >= 0) ring_mbar_wait (full + (k & 1), (unsigned)(k >> 1) & 1u, args.pollNs);   // the job warps are done with tile k
             // ---- staging for tile k + 2 (into the buffers of tile k) -------------------------------------
             const int kn = k + 2;
             if (kn < nbMine) {
@@ -437,7 +448,8 @@ ring_assembly_kernel (const RingArgs args)
                     const int n = otid + q * (NOUT * 32);
                     if (n < h.nbNodes) { pl[n] = stage[q][0]; pl[planeStride + n] = stage[q][1]; pl[2 * planeStride + n] = stage[q][2]; }
                 }
-                ring_mbar_arrive (tailFull + (kn & 1));
+                __syncwarp ();
+                if (lane == 0) ring_mbar_arrive (tailFull + (kn & 1));
 #else
                 // coordinates: asynchronous 8-byte copies that signal tailFull[kn & 1] when they have landed (each costs a
                 // shared-memory wavefront on arrival, but no register, no wait)
@@ -489,8 +501,8 @@ ring_assembly_kernel (const RingArgs args)
                     const bool worker = grp < 3 && comp < 9;
                     const int ca = comp / 3, cb = comp - 3 * ca;              // component (ca, cb) of the 3x3 block
                     const int base = worker ? 10 * grp : lane;                // first lane of the row's nine; idle lanes read themselves
-                    // (1024 threads: 21 row groups of a 63-row tile over 16 warps — the warps that take two change from tile to tile)
-                    const int ow3 = (THREADS == 1024 ? (ow + NOUT - (k * 5) % NOUT) % NOUT : ow) * 3;
+                    // (896 / 1024 threads: 21 row groups of a 63-row tile over 12 / 16 warps — the warps that take two change from tile to tile)
+                    const int ow3 = (THREADS >= 896 ? (ow + NOUT - (k * 5) % NOUT) % NOUT : ow) * 3;
                     for (int r0 = ow3; r0 < nbRows; r0 += NOUT * 3) {
                         const int r = r0 + grp;
                         const bool rowOk = worker && r < nbRows;
@@ -587,31 +599,36 @@ size_t ring_smem_bytes (int operatorID, const DeviceRingPlan &plan)
 }
 
 #ifndef MFB_RING_HOST_EMULATION
+// CTA shapes: 384 threads x 2 CTAs per SM; 640 (96 registers), 768 (80) x 1; 896 and 1024 x 1 with per-warpgroup
+// register counts (setmaxnreg).  One visitor for configure / occupancy / launch.
+template <class F>
+cudaError_t ring_dispatch (int operatorID, int threads, F &&f)
+{
+    const bool lap = operatorID == 0;
+    switch (threads) {
+    case 384:  return lap ? f (ring_assembly_kernel<1, 384, 2>, 384)   : f (ring_assembly_kernel<9, 384, 2>, 384);
+    case 640:  return lap ? f (ring_assembly_kernel<1, 640, 1>, 640)   : f (ring_assembly_kernel<9, 640, 1>, 640);
+    case 768:  return lap ? f (ring_assembly_kernel<1, 768, 1>, 768)   : f (ring_assembly_kernel<9, 768, 1>, 768);
+    case 896:  return lap ? f (ring_assembly_kernel<1, 896, 1>, 896)   : f (ring_assembly_kernel<9, 896, 1>, 896);
+    case 1024: return lap ? f (ring_assembly_kernel<1, 1024, 1>, 1024) : f (ring_assembly_kernel<9, 1024, 1>, 1024);
+    }
+    return cudaErrorInvalidValue;
+}
+
+bool ring_threads_supported (int threads) { return threads == 384 || threads == 640 || threads == 768 || threads == 896 || threads == 1024; }
+
 cudaError_t ring_configure (int operatorID)
 {
-    cudaError_t e;
-    if (operatorID == 0) {
-        if ((e = ring_opt_in (ring_assembly_kernel<1, 384, 2>)) != cudaSuccess) return e;
-        if ((e = ring_opt_in (ring_assembly_kernel<1, 1024, 1>)) != cudaSuccess) return e;
-        return ring_opt_in (ring_assembly_kernel<1, 768, 1>);
+    for (int threads : {384, 640, 768, 896, 1024}) {
+        cudaError_t e = ring_dispatch (operatorID, threads, [] (auto kernel, int) { return ring_opt_in (kernel); });
+        if (e != cudaSuccess) return e;
     }
-    if ((e = ring_opt_in (ring_assembly_kernel<9, 384, 2>)) != cudaSuccess) return e;
-    if ((e = ring_opt_in (ring_assembly_kernel<9, 1024, 1>)) != cudaSuccess) return e;
-    return ring_opt_in (ring_assembly_kernel<9, 768, 1>);
+    return cudaSuccess;
 }
 
 cudaError_t ring_ctas_per_sm (int operatorID, int threads, size_t smemBytes, int *ctas)
 {
-    if (threads == 768) {
-        return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 768, 1>, 768, smemBytes)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 768, 1>, 768, smemBytes);
-    }
-    if (threads == 1024) {
-        return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 1024, 1>, 1024, smemBytes)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 1024, 1>, 1024, smemBytes);
-    }
-    return operatorID == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<1, 384, 2>, 384, smemBytes)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, ring_assembly_kernel<9, 384, 2>, 384, smemBytes);
+    return ring_dispatch (operatorID, threads, [&] (auto kernel, int t) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor (ctas, kernel, t, smemBytes); });
 }
 
 cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTile, int nbTiles, int ctas,
@@ -625,20 +642,13 @@ cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTi
     args.fusePrec = fusePrec;
     args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
     args.intfDone = intfDone;
+    static const unsigned pollNs = getenv ("MFB_RING_POLL_NS") ? (unsigned)std::max (atoi (getenv ("MFB_RING_POLL_NS")), 0) : kRingPollNs;
+    args.pollNs = pollNs;
     const int grid = std::max (1, std::min (ctas, nbTiles));
-    if (threads == 1024) {
-        if (operatorID == 0) ring_assembly_kernel<1, 1024, 1><<<grid, 1024, smemBytes, stream>>> (args);
-        else                 ring_assembly_kernel<9, 1024, 1><<<grid, 1024, smemBytes, stream>>> (args);
-    }
-    else if (threads == 768) {
-        if (operatorID == 0) ring_assembly_kernel<1, 768, 1><<<grid, 768, smemBytes, stream>>> (args);
-        else                 ring_assembly_kernel<9, 768, 1><<<grid, 768, smemBytes, stream>>> (args);
-    }
-    else {
-        if (operatorID == 0) ring_assembly_kernel<1, 384, 2><<<grid, 384, smemBytes, stream>>> (args);
-        else                 ring_assembly_kernel<9, 384, 2><<<grid, 384, smemBytes, stream>>> (args);
-    }
-    return cudaGetLastError ();
+    return ring_dispatch (operatorID, threads, [&] (auto kernel, int t) {
+        kernel<<<grid, t, smemBytes, stream>>> (args);
+        return cudaGetLastError ();
+    });
 }
 #endif
 

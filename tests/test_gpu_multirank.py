@@ -124,6 +124,16 @@ def test_p2p_exchange_between_contexts_of_one_process(op, grid, blocks, threads)
         c.close()
 
 
+@pytest.mark.parametrize("blocks,op", [((2, 2, 2), "ela"), ((3, 1, 1), "lap")])
+def test_p2p_all_subdomains_of_a_partition_in_one_process(blocks, op):
+    """2 x 2 x 2: every subdomain has 7 neighbours (faces, edges and the corner node shared by all 8); 3 x 1 x 1: the
+    middle subdomain has two.  Also the failure path: a subdomain that skips an exchange makes its neighbours report
+    a timeout through mfb_ctx_sync instead of hanging (tests/p2p_worker.py)."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "p2p_worker.py")] + [str(b) for b in blocks] + [op]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "P2P_WORKER_OK" in res.stdout, res.stdout[-3000:]
+
+
 def test_p2p_card_checks():
     meshes = [mfb.Mesh.generate(6, 5, 4, blocks=(2, 1, 1), rank=r, seed=5) for r in range(2)]
     setups = [mfb.Setup(m, "ela") for m in meshes]

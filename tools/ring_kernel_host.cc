@@ -47,23 +47,21 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
     static unsigned intfDone;
     intfDone = 0;
     args.intfDone = isInterface ? &intfDone : nullptr;
+    args.pollNs = 0;
     if (hp.nbTiles == 0) return 0;
     const size_t smem = ring_smem_bytes (operatorID, args.plan);
     auto launch = [&] (int firstTile, int nbTiles, int grid) {
         if (nbTiles <= 0) return;
         args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
         grid = std::max (1, std::min (grid, nbTiles));
-        if (threads == 1024) {
-            if (operatorID == 0) cta_emu::launch (grid, 1024, smem, [&] () { ring_assembly_kernel<1, 1024, 1> (args); });
-            else                 cta_emu::launch (grid, 1024, smem, [&] () { ring_assembly_kernel<9, 1024, 1> (args); });
-        }
-        else if (threads == 768) {
-            if (operatorID == 0) cta_emu::launch (grid, 768, smem, [&] () { ring_assembly_kernel<1, 768, 1> (args); });
-            else                 cta_emu::launch (grid, 768, smem, [&] () { ring_assembly_kernel<9, 768, 1> (args); });
-        }
-        else {
-            if (operatorID == 0) cta_emu::launch (grid, 384, smem, [&] () { ring_assembly_kernel<1, 384, 2> (args); });
-            else                 cta_emu::launch (grid, 384, smem, [&] () { ring_assembly_kernel<9, 384, 2> (args); });
+        auto run = [&] (auto kernel, int t) { cta_emu::launch (grid, t, smem, [&] () { kernel (args); }); };
+        const bool lap = operatorID == 0;
+        switch (threads) {
+        case 1024: if (lap) run (ring_assembly_kernel<1, 1024, 1>, 1024); else run (ring_assembly_kernel<9, 1024, 1>, 1024); break;
+        case 896:  if (lap) run (ring_assembly_kernel<1, 896, 1>, 896);   else run (ring_assembly_kernel<9, 896, 1>, 896); break;
+        case 768:  if (lap) run (ring_assembly_kernel<1, 768, 1>, 768);   else run (ring_assembly_kernel<9, 768, 1>, 768); break;
+        case 640:  if (lap) run (ring_assembly_kernel<1, 640, 1>, 640);   else run (ring_assembly_kernel<9, 640, 1>, 640); break;
+        default:   if (lap) run (ring_assembly_kernel<1, 384, 2>, 384);   else run (ring_assembly_kernel<9, 384, 2>, 384); break;
         }
     };
     const int grid = ctas > 0 ? ctas : 3;
@@ -75,7 +73,7 @@ extern "C" int mfb_ring_kernel_host (int operatorID, int nbNodes, int nbElem, co
         launch (nIntf, nInterior, (nInterior + 3) / 4);
     }
     else launch (0, hp.nbTiles, grid);
-    if (isInterface && (int)intfDone != hp.nbInterfaceTiles * ring_write_out_warps (operatorID, threads == 768 || threads == 1024 ? threads : 384)) {
+    if (isInterface && (int)intfDone != hp.nbInterfaceTiles * ring_write_out_warps (operatorID, threads == 640 || threads == 768 || threads == 896 || threads == 1024 ? threads : 384)) {
         g_error = "interface signal: " + std::to_string (intfDone) + " arrivals for " + std::to_string (hp.nbInterfaceTiles) + " interface tiles";
         return -1;
     }
