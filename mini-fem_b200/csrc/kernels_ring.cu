@@ -186,6 +186,12 @@ __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim ==
 #define MFB_RING_STAGE_LDG 0
 #endif
 
+// Elasticity write-out: 1 = the rows leave as runs of consecutive doubles (the diagonal entry is first stored into the
+// slab), 0 = three rows side by side, every lane copying its component while it sums it (round 2's first shape).
+#ifndef MFB_RING_COALESCED_ROWS
+#define MFB_RING_COALESCED_ROWS 1
+#endif
+
 // Warps per role.  job warps out of 24, measured on the EIB mesh (ms per iteration, final pipeline): elasticity, 768 threads: 12: 0.421,
 // 13: 0.414, 15: 0.439, 16: 0.449; 384 threads (x 2 CTAs): 6 of 12: 0.458, 7: 0.430, 8: 0.482.  The Laplacian has an
 // eighth of the write-out work per row and wants more job warps (768 threads, 20 + 4: 0.252).
@@ -474,7 +480,8 @@ ring_assembly_kernel (const RingArgs args)
                 const RingTileHeader &hdr = *reinterpret_cast<const RingTileHeader*> (sHead);
                 const int nbRows = hdr.nbRows;
                 const RingRow *sRows = reinterpret_cast<const RingRow*> (sHead + sizeof (RingTileHeader));
-                const double *slab = slab0 + (k & 1) * slabDoubles;
+                double *slabW = slab0 + (k & 1) * slabDoubles;
+                const double *slab = slabW;
                 if (OPDIM == 1) {
                     // Laplacian: one lane per row walks its entries (rows are short and the whole matrix is an eighth
                     // of the elasticity one).  Row starts 1 (mod 8) slots apart keep the slab reads in different banks.
@@ -508,6 +515,41 @@ ring_assembly_kernel (const RingArgs args)
                         const bool rowOk = worker && r < nbRows;
                         int node = 0, diagOff = 0xFFFF;
                         double diag = 0.0;
+#if MFB_RING_COALESCED_ROWS
+                        if (rowOk) {
+                            // row sum only; the diagonal entry joins the row in the slab, the row leaves below
+                            const RingRow rr = sRows[r];
+                            const int len = rr.len;
+                            node = rr.node; diagOff = rr.diagOff;             // 0xFFFF never equals a position
+                            double *sp = slabW + (size_t)rr.localStart * SLAB + comp;
+                            double a = 0.0;
+                            for (int q = 0; q < len; q++) {
+                                if (q != diagOff) a += sp[q * SLAB];
+                            }
+                            diag = 0.0 - a;
+                            if (diagOff != 0xFFFF) sp[diagOff * SLAB] = diag;
+                        }
+                        __syncwarp ();
+                        // The three rows leave one after the other, every store instruction of the warp writing 32
+                        // consecutive doubles (a row is one contiguous run of len x 72 bytes in nodeToNodeValue).  A pure
+                        // store kernel writes the matrix in 0.30 ms with the old shape (three 72-byte pieces per instruction,
+                        // 27 lanes) and in 0.19 ms with consecutive doubles (tools/microbench/store_probe.cu).
+                        #pragma unroll
+                        for (int g = 0; g < 3; g++) {
+                            if (r0 + g < nbRows) {                             // uniform over the warp
+                                const RingRow rr = sRows[r0 + g];
+                                const double *src = slab + (size_t)rr.localStart * SLAB;
+                                double *out = args.values + (size_t)rr.valueStart * 9;
+                                const int total = rr.len * 9;
+                                int e = lane / 9, c = lane - 9 * e;            // double m of the row = component c of entry e
+                                for (int m = lane; m < total; m += 32) {
+                                    out[m] = src[e * SLAB + c];
+                                    e += 3; c += 5;                            // 32 = 3 x 9 + 5
+                                    if (c >= 9) { c -= 9; e++; }
+                                }
+                            }
+                        }
+#else
                         if (rowOk) {
                             const RingRow rr = sRows[r];
                             const int len = rr.len;
@@ -521,6 +563,7 @@ ring_assembly_kernel (const RingArgs args)
                             diag = 0.0 - a;
                             if (diagOff != 0xFFFF) out[diagOff * 9] = diag;
                         }
+#endif
                         if (args.fusePrec) {
                             // prec_init + prec_inversion (src/preconditioner.cc:25-87, src/Fortran/elasclpr.f:19-53) by the
                             // nine lanes that hold the block: Dirichlet rows / columns to identity, then cofactor / determinant
