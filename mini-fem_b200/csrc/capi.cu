@@ -684,7 +684,10 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     if (c->path == MFB_PATH_RING) {          // a write-once path like TILED: same stages, same fused iteration
         c->ring = true;
         c->path = MFB_PATH_TILED;
-        if (!(o && o->threads > 0)) c->threads = 768;
+        // default CTA: 768 threads (13 job + 11 write-out warps) for elasticity; the Laplacian, whose write-out is an eighth
+        // of the bytes, runs 24 job + 8 write-out warps in a 1024-thread CTA with per-warpgroup register counts
+        // (EIB, ms per iteration: elasticity 768: 0.406, 896: 0.431, 1024: 0.437, 640: 0.426; Laplacian 768: 0.240, 1024: 0.225)
+        if (!(o && o->threads > 0)) c->threads = p->operatorID == 0 ? 1024 : 768;
         if (!ring_threads_supported (c->threads)) return fail (MFB_ERR_ARG, "mfb_ctx_create: the RING kernel runs 384 (two CTAs per SM), 640, 768, 896 or 1024 (one) threads per CTA");
     }
     if (!c->ring && c->threads != tiled_pipeline_threads () && (c->threads % 32 || c->threads < 32 || c->threads > 256)) {

@@ -186,10 +186,17 @@ __host__ __device__ constexpr int ring_slab_stride (int opDim) { return opDim ==
 #define MFB_RING_STAGE_LDG 0
 #endif
 
-// Elasticity write-out: 1 = the rows leave as runs of consecutive doubles (the diagonal entry is first stored into the
-// slab), 0 = three rows side by side, every lane copying its component while it sums it (round 2's first shape).
+// Elasticity write-out: 0 (shipped) = three rows side by side, every lane copying its component while it sums it;
+// 1 = the diagonal entry is first stored into the slab and the rows leave as runs of consecutive doubles.  A pure store
+// kernel writes the matrix in 0.30 ms with the first shape and in 0.22 ms with the second (tools/microbench/
+// store_probe.cu), but the second pass over the slab and the longer instruction stream of the write-out warps cost
+// more than the stores save: 0.534 against 0.406 ms per EIB iteration (profiles/r2_experiments.md).
 #ifndef MFB_RING_COALESCED_ROWS
-#define MFB_RING_COALESCED_ROWS 1
+#define MFB_RING_COALESCED_ROWS 0
+#endif
+// the copy loop of the first shape split at the diagonal entry (no comparison per entry)
+#ifndef MFB_RING_SPLIT_DIAG
+#define MFB_RING_SPLIT_DIAG 0
 #endif
 
 // Warps per role.  job warps out of 24, measured on the EIB mesh (ms per iteration, final pipeline): elasticity, 768 threads: 12: 0.421,
@@ -202,6 +209,9 @@ __host__ __device__ constexpr int ring_job_warps (int opDim, int threads)
 #ifdef MFB_RING_JOB_WARPS_OF_24
     return threads / 32 * MFB_RING_JOB_WARPS_OF_24 / 24;
 #else
+#ifdef MFB_RING_768_REGS      // experiment: 768 threads as 12 job warps at 96 registers + 12 write-out warps at 64
+    if (threads == 768 && opDim == 9) return 12;
+#endif
     return threads == 1024 ? (opDim == 1 ? 24 : 16)
          : threads == 896  ? (opDim == 1 ? 20 : 16)
          : threads == 640  ? (opDim == 1 ? 16 : 11)
@@ -216,8 +226,13 @@ __host__ __device__ constexpr int ring_job_warps (int opDim, int threads)
 #endif
 // registers per thread after the prologue (0: as launched).  1024 threads are launched with 64: 16 x 72 + 16 x 56 (Laplacian
 // 24 x 72 + 8 x 40); 896 threads with 72: 16 x 80 + 12 x 56 (Laplacian 20 x 80 + 8 x 40)
+#ifdef MFB_RING_768_REGS
+__host__ __device__ constexpr int ring_job_regs (int opDim, int threads) { return threads == 768 && opDim == 9 ? 96 : 0; }
+__host__ __device__ constexpr int ring_out_regs (int opDim, int threads) { return threads == 768 && opDim == 9 ? 64 : 0; }
+#else
 __host__ __device__ constexpr int ring_job_regs (int opDim, int threads) { return threads == 1024 ? (opDim == 1 ? 72 : MFB_RING_JOB_REGS) : threads == 896 ? 80 : 0; }
 __host__ __device__ constexpr int ring_out_regs (int opDim, int threads) { return threads == 1024 ? (opDim == 1 ? 40 : MFB_RING_OUT_REGS) : threads == 896 ? (opDim == 1 ? 40 : 56) : 0; }
+#endif
 
 constexpr unsigned kRingPollNs = 0;      // default sleep between two polls of a barrier
 constexpr int kRingHeadBuffers = 5;      // heads of tiles k - 1 .. k + 3 are alive while the write-out warps work on tile k
@@ -557,9 +572,16 @@ ring_assembly_kernel (const RingArgs args)
                             const double *sp = slab + (size_t)rr.localStart * SLAB + comp;
                             double *out = args.values + (size_t)rr.valueStart * 9 + comp, *op = out;
                             double a = 0.0;
+#if MFB_RING_SPLIT_DIAG
+                            const int dq = diagOff < len ? diagOff : len;
+                            for (int q = 0; q < dq; q++, sp += SLAB, op += 9) { const double v = *sp; a += v; *op = v; }
+                            sp += SLAB; op += 9;
+                            for (int q = dq + 1; q < len; q++, sp += SLAB, op += 9) { const double v = *sp; a += v; *op = v; }
+#else
                             for (int q = 0; q < len; q++, sp += SLAB, op += 9) {
                                 if (q != diagOff) { const double v = *sp; a += v; *op = v; }
                             }
+#endif
                             diag = 0.0 - a;
                             if (diagOff != 0xFFFF) out[diagOff * 9] = diag;
                         }
