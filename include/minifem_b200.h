@@ -139,7 +139,7 @@ typedef struct {
     int device;                     /* CUDA device ordinal */
     int tileRows;                   /* TILED: max rows per tile (0 = default) */
     int tileElems;                  /* TILED: max elements per tile; RING: max slab slots per tile = CSR entries + row padding (0 = default) */
-    int threads;                    /* TILED: threads per CTA (0 = default 256); RING: 0 / 768 (one CTA per SM) or 384 (two) */
+    int threads;                    /* TILED: threads per CTA (0 = default 256); RING: 0 = default (elasticity 768, Laplacian 1024), 640 / 768 / 896 / 1024 (one CTA per SM) or 384 (two) */
     int useGraph;                   /* capture mfb_ctx_iteration in a CUDA graph */
     int ctas;                       /* TILED: CTAs walking the tiles (0 = default, -1 = one per tile) */
     int bankAware;                  /* TILED: order inside each contribution list: 0 / 1 = chosen against
