@@ -349,9 +349,11 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
     }
     // ---- ring rotation / direction per job, lane after lane of a half-warp ---------------------
     // step 0 loads node i, step 1 node j, step 2 + q the q-th code byte
-    static thread_local HalfWarpBanks banks;
+    static thread_local HalfWarpBanks banksTls;
+    HalfWarpBanks &banks = banksTls;          // bound once per tile: every access of the thread-local goes through its wrapper
     std::vector<uint8_t> best;
     std::vector<int> costOf;
+    std::vector<int> idOf;
     int maxSteps = 0;
     for (int b = 0; b < nbBatches; b++) {
         int nbSteps = 0;
@@ -381,21 +383,37 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
                 if (!(lim.bankAware && jb.single && len >= 2)) return;
                 // candidates: the chain reversed; a closed ring of v elements (v + 1 bytes, first = last)
                 // may also start at any of its v nodes
-                const int v = len - 1, nbRot = jb.closedSingle ? v : 1;
-                // cost of having ring node m in step q, once for all candidates
-                const int nbPos = jb.closedSingle ? v : len;
-                costOf.resize ((size_t)len * nbPos);
-                for (int q = 0; q < len; q++) for (int m = 0; m < nbPos; m++) costOf[(size_t)q * nbPos + m] = banks.cost (2 + q, w.newId[codes[m]]);
+                const bool jobClosed = jb.closedSingle;
+                const int v = len - 1, nbRot = jobClosed ? v : 1;
+                // cost of having ring node m in step q, once for all candidates; a closed ring's row is stored twice in a
+                // row (stride 2 v) so that a rotation is an offset, not a division per term
+                const int nbPos = jobClosed ? v : len, stride = jobClosed ? 2 * v : len;
+                idOf.resize ((size_t)nbPos);
+                for (int m = 0; m < nbPos; m++) idOf[m] = w.newId[codes[m]];
+                {   // the search below starts with the ring as it stands and stops at a free candidate: look at that one first
+                    long asIs = 0;
+                    for (int q = 0; q < len && asIs == 0; q++) asIs += banks.cost (2 + q, idOf[jobClosed && q == v ? 0 : q]);
+                    if (asIs == 0) return;
+                }
+                costOf.resize ((size_t)len * stride);
+                for (int q = 0; q < len; q++) {
+                    int *rowCost = costOf.data () + (size_t)q * stride;
+                    for (int m = 0; m < nbPos; m++) rowCost[m] = banks.cost (2 + q, idOf[m]);
+                    if (jobClosed) for (int m = 0; m < v; m++) rowCost[v + m] = rowCost[m];
+                }
                 long bestCost = 1l << 60;
                 int bestRot = 0, bestDir = 0;
                 for (int rot = 0; rot < nbRot && bestCost > 0; rot++) {
                     for (int dir = 0; dir < 2 && bestCost > 0; dir++) {
                         long cost = 0;
-                        for (int q = 0; q < len; q++) {
-                            int src;
-                            if (jb.closedSingle) src = dir ? ((rot - q) % v + v) % v : (rot + q) % v;
-                            else src = dir ? len - 1 - q : q;
-                            cost += costOf[(size_t)q * nbPos + src];
+                        if (jobClosed) {
+                            // src = (rot + q) mod v, resp. (rot - q) mod v = index rot - q + v of the doubled row
+                            if (dir == 0) for (int q = 0; q < len; q++) cost += costOf[(size_t)q * stride + rot + q];
+                            else          for (int q = 0; q < len; q++) cost += costOf[(size_t)q * stride + rot - q + v];
+                        }
+                        else {
+                            if (dir == 0) for (int q = 0; q < len; q++) cost += costOf[(size_t)q * stride + q];
+                            else          for (int q = 0; q < len; q++) cost += costOf[(size_t)q * stride + len - 1 - q];
                         }
                         if (cost < bestCost) { bestCost = cost; bestRot = rot; bestDir = dir; }
                     }
@@ -456,7 +474,8 @@ void plan_tile (int nbRows, const int *rowNodes, const int *elemToNode, const in
     // every node to the bank where it meets the fewest others, then rotate again.
     auto renumber_pass = [&] () {
         const int S = std::min (maxSteps + 2, (int)HalfWarpBanks::kMaxSteps);
-        static thread_local std::vector<std::vector<int>> app;          // inner vectors keep their capacity from tile to tile
+        static thread_local std::vector<std::vector<int>> appTls;       // inner vectors keep their capacity from tile to tile
+        std::vector<std::vector<int>> &app = appTls;
         if ((int)app.size () < nbRef) app.resize ((size_t)nbRef);
         for (int n = 0; n < nbRef; n++) app[n].clear ();
         for (int h = 0; h < nbHalf; h++) {
@@ -580,7 +599,7 @@ namespace {
 // bounding box into two parts that hold a whole number of leaves of (nearly) equal size <= leafSize.
 // Leaves come out box-shaped, which is what keeps mesh edges inside one tile (an interior edge is
 // one job that writes both of its blocks); a run of the Morton curve of the same length is ragged.
-void rcb_split (std::vector<int> &idx, int lo, int hi, int leafSize, const double *coord, std::vector<int> &leafStart)
+void rcb_split (std::vector<int> &idx, int lo, int hi, int leafSize, const double *coord, std::vector<int> &leafStart, int depth = 0)
 {
     const int count = hi - lo;
     if (count <= leafSize && leafSize > 0) { leafStart.push_back (lo); leafSize = 0; }   // below a leaf: keep bisecting, for the order only
@@ -604,8 +623,20 @@ void rcb_split (std::vector<int> &idx, int lo, int hi, int leafSize, const doubl
         const double cx = coord[(size_t)x * 3 + axis], cy = coord[(size_t)y * 3 + axis];
         return cx < cy || (cx == cy && x < y);
     });
-    rcb_split (idx, lo, mid, leafSize, coord, leafStart);
-    rcb_split (idx, mid, hi, leafSize, coord, leafStart);
+    if (depth < 6 && count > 20000) {
+        // the two halves are disjoint ranges of idx: bisect them as tasks; the leaves of the right half follow those of
+        // the left half, as in the sequential recursion
+        std::vector<int> right;
+        #pragma omp task shared(idx, leafStart) firstprivate(lo, mid, leafSize, depth)
+        rcb_split (idx, lo, mid, leafSize, coord, leafStart, depth + 1);
+        #pragma omp task shared(idx, right) firstprivate(mid, hi, leafSize, depth)
+        rcb_split (idx, mid, hi, leafSize, coord, right, depth + 1);
+        #pragma omp taskwait
+        leafStart.insert (leafStart.end (), right.begin (), right.end ());
+        return;
+    }
+    rcb_split (idx, lo, mid, leafSize, coord, leafStart, depth + 1);
+    rcb_split (idx, mid, hi, leafSize, coord, leafStart, depth + 1);
 }
 
 // Tiles = the leaves of the bisection, cut further (greedily, in leaf order) wherever a leaf exceeds
@@ -617,12 +648,26 @@ int cut_node_tiles_rcb (int nbNodes, const int *elemToNode, const int *row, cons
     nodeOrder.resize ((size_t)nbNodes);
     for (int n = 0; n < nbNodes; n++) nodeOrder[n] = n;
     std::vector<int> leafStart;
-    if (nbNodes > 0) rcb_split (nodeOrder, 0, nbNodes, lim.maxRows, coord, leafStart);
+    if (nbNodes > 0) {
+        #pragma omp parallel num_threads(plan_team_size ())
+        #pragma omp single
+        rcb_split (nodeOrder, 0, nbNodes, lim.maxRows, coord, leafStart);
+    }
     leafStart.push_back (nbNodes);
     tileStart.clear ();
+    const int nbLeaves = (int)leafStart.size () - 1;
+    std::vector<std::vector<int>> tilesOfLeaf ((size_t)std::max (nbLeaves, 0));
+    std::string firstError;
+    bool anyFailed = false;
+    // the leaves are cut independently of each other (every thread with its own stamps); their tiles are
+    // concatenated in leaf order afterwards
+    #pragma omp parallel num_threads(plan_team_size ())
+    {
     std::vector<int> nodeStamp ((size_t)nbNodes, -1), ownedStamp ((size_t)nbNodes, -1), fresh;
     int stamp = 0;
     bool failed = false;
+    std::string error;
+    std::vector<int> *tileStartOut = nullptr;
     // does [lo, hi) of nodeOrder fit one tile?  (rows, referenced nodes, slab slots, jobs)
     auto fits = [&] (int lo, int hi) {
         stamp++;
@@ -655,7 +700,7 @@ int cut_node_tiles_rcb (int nbNodes, const int *elemToNode, const int *row, cons
     // so both halves stay compact) instead of losing a ragged tail
     auto emit = [&] (auto &&self, int lo, int hi) -> void {
         if (failed || lo >= hi) return;
-        if (fits (lo, hi)) { tileStart.push_back (lo); return; }
+        if (fits (lo, hi)) { tileStartOut->push_back (lo); return; }
         if (hi - lo == 1) {
             const int n = nodeOrder[lo];
             error = "node " + std::to_string (n + 1) + " alone exceeds the tile caps (" + std::to_string (row[n + 1] - row[n]) + " entries)";
@@ -666,8 +711,19 @@ int cut_node_tiles_rcb (int nbNodes, const int *elemToNode, const int *row, cons
         self (self, lo, mid);
         self (self, mid, hi);
     };
-    for (size_t leaf = 0; leaf + 1 < leafStart.size (); leaf++) emit (emit, leafStart[leaf], leafStart[leaf + 1]);
-    if (failed) return -1;
+    #pragma omp for schedule(dynamic, 64)
+    for (int leaf = 0; leaf < nbLeaves; leaf++) {
+        if (failed) continue;
+        tileStartOut = &tilesOfLeaf[(size_t)leaf];
+        emit (emit, leafStart[(size_t)leaf], leafStart[(size_t)leaf + 1]);
+    }
+    if (failed) {
+        #pragma omp critical
+        { if (!anyFailed) { anyFailed = true; firstError = error; } }
+    }
+    }
+    if (anyFailed) { error = firstError; return -1; }
+    for (int leaf = 0; leaf < nbLeaves; leaf++) tileStart.insert (tileStart.end (), tilesOfLeaf[(size_t)leaf].begin (), tilesOfLeaf[(size_t)leaf].end ());
     tileStart.push_back (nbNodes);
     if (nbNodes == 0) tileStart.assign (1, 0);
     return 0;

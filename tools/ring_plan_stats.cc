@@ -71,6 +71,12 @@ int main (int argc, char **argv)
         for (int b = 0; b < 64; b++) if (histR[b]) printf (" %d:%lld", b, histR[b]);
         printf ("\n");
     }
+    {   // hash of the serialized plan: a refactoring of host/ring_plan.cc must leave it unchanged
+        uint64_t h = 1469598103934665603ull;
+        for (uint8_t b : plan.blob) { h ^= b; h *= 1099511628211ull; }
+        for (uint64_t o : plan.tileOffset) { h ^= o; h *= 1099511628211ull; }
+        printf ("  plan hash %016llx\n", (unsigned long long)h);
+    }
     if (verify_ring_plan (plan, m.nbNodes, m.nbElem, m.elemToNode.data (), row.data (), col.data (), nullptr, err)) { printf ("  VERIFY FAILED: %s\n", err.c_str ()); return 1; }
     printf ("  verify ok\n");
     return 0;
