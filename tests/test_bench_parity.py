@@ -50,6 +50,19 @@ for op in ("ela", "lap"):
     # without the exchange the interface blocks would differ: the harness really moves them
     alone = oracle.prec_inversion(np.ascontiguousarray(res[rank][1]), s.row, s.col, s.checkBounds, s.mesh.nbNodes, s.operatorID)
     assert not bench.oracle_parity(Ctx(res[rank][0], alone), s, meshes[rank], world)["ok"]
+# bench.warm_up: a peer-to-peer exchange that times out on ONE rank is switched off on every rank and the warm-up repeated
+class TimeoutCtx:
+    def __init__(self, fails): self.fails, self.p2p, self.iterations = fails, True, 0
+    def iteration(self): self.iterations += 1
+    def sync(self):
+        if self.fails and self.p2p: raise mfb.MfbError("peer-to-peer halo exchange timed out waiting for a neighbour's flag")
+    def p2p_enable(self, on): self.p2p = on
+tc, halo = TimeoutCtx(rank == 1), {"transport": "p2p"}
+bench.warm_up(mfb, mdist, tc, 3, halo)
+assert halo["transport"] == "nccl" and tc.p2p is False and tc.iterations == 6 and "timed out" in halo["why"], (rank, halo)
+tc, halo = TimeoutCtx(False), {"transport": "p2p"}
+bench.warm_up(mfb, mdist, tc, 3, halo)
+assert halo == {"transport": "p2p"} and tc.iterations == 3
 print("PARITY_WORKER_OK", rank, flush=True)
 '''
 

@@ -21,6 +21,32 @@ assert world == 2
 payload = bytes(range(128)) if rank == 0 else bytes(128)
 assert mdist.broadcast_bytes(payload, 128) == bytes(range(128))
 assert mdist.max_over_ranks(10 + rank) == 11 and mdist.sum_over_ranks(1 + rank) == 3
+cards = mdist.all_gather_bytes(bytes([rank + 1]) * 1024, 1024)                   # the peer-to-peer cards, in rank order
+assert cards == [bytes([1]) * 1024, bytes([2]) * 1024]
+
+
+class FakeCtx:                               # mfb_ctx_p2p_*: all ranks switch to the peer-to-peer exchange, or none does
+    def __init__(self, card_ok, connect_ok): self.card_ok, self.connect_ok, self.enabled, self.seen = card_ok, connect_ok, None, None
+    def p2p_card(self):
+        if not self.card_ok: raise mfb.MfbError("no window")
+        return bytes([7]) * mfb.P2P_CARD_BYTES
+    def p2p_connect(self, cards):
+        self.seen = cards
+        if not self.connect_ok: raise mfb.MfbError("no peer access")
+    def p2p_enable(self, on): self.enabled = on
+
+
+ok = FakeCtx(True, True)
+assert mdist.p2p_connect(ok) == (True, "") and len(ok.seen) == 2 and ok.enabled is None
+one_bad = FakeCtx(True, rank != 1)           # rank 1 cannot map its neighbour: rank 0 must switch off again
+active, why = mdist.p2p_connect(one_bad)
+assert not active and (one_bad.enabled is False if rank == 0 else "no peer access" in why), (rank, why, one_bad.enabled)
+no_card = FakeCtx(rank != 0, True)           # rank 0 has no window to publish
+active, why = mdist.p2p_connect(no_card)
+assert not active and ("no window" in why if rank == 0 else True)
+os.environ["MFB_HALO"] = "nccl"
+assert mdist.p2p_connect(FakeCtx(True, True)) == (False, "MFB_HALO=nccl")
+del os.environ["MFB_HALO"]
 oracle = Oracle()
 grid, blocks = (6, 5, 4), (2, 1, 1)
 meshes = [mfb.Mesh.generate(*grid, blocks=blocks, rank=r, seed=13) for r in range(2)]
