@@ -53,6 +53,13 @@ def main():
         sys.exit("ring_gpu_worker: no CUDA device")
     oracle = Oracle()
     rng = np.random.default_rng(21)
+    if os.environ.get("RING_WORKER_SHAPES_ONLY"):                      # development aid: the CTA shapes only
+        mesh = mfb.Mesh.generate(14, 12, 10, seed=9)
+        for op in ("ela", "lap"):
+            for threads in (384, 640, 768, 896, 1024):
+                check(oracle, f"{op} {threads} threads", mfb.Setup(mesh, op), threads=threads)
+        print("RING_GPU_OK")
+        return
     for op in ("ela", "lap"):
         for grid, seed in (((1, 1, 1), 1), ((5, 4, 3), 2), ((16, 9, 12), 3), ((25, 25, 40), 4)):
             mesh = mfb.Mesh.generate(*grid, seed=seed)
@@ -65,6 +72,8 @@ def main():
         check(oracle, f"{op} 384 threads, small caps", mfb.Setup(mesh, op), threads=384, tile_rows=22, tile_elems=352)
         check(oracle, f"{op} 1024 threads (warpgroups with their own register counts)", mfb.Setup(mesh, op), threads=1024)
         check(oracle, f"{op} 1024 threads, small caps, staged", mfb.Setup(mesh, op), False, threads=1024, tile_rows=22, tile_elems=352)
+        check(oracle, f"{op} 896 threads (16 job warps at 80 + 12 write-out warps at 56 registers)", mfb.Setup(mesh, op), threads=896)
+        check(oracle, f"{op} 640 threads", mfb.Setup(mesh, op), threads=640, tile_rows=40, tile_elems=700)
         check(oracle, f"{op} one CTA", mfb.Setup(mesh, op), ctas=1)
         check(oracle, f"{op} one tile per CTA", mfb.Setup(mesh, op), ctas=-1)
         check(oracle, f"{op} plan order", mfb.Setup(mesh, op), bank_aware=False)
