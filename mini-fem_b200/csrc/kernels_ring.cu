@@ -10,21 +10,20 @@
 // of the row's off-diagonal blocks (element matrices have zero row sums) and is formed while the row
 // streams out of the slab.
 //
-// Per tile:
-//   0. plan record by TMA (cp.async.bulk + mbarrier): the HEAD of tile t+1 (header, row table, node
-//      list) is fetched at the start of tile t, the TAIL (batches, jobs, ring codes) and the
-//      coordinates (cp.async) of tile t+1 while tile t is in its write-out;
-//   1. job phase: one lane per edge, 32 jobs per warp batch, ring codes 8 to a 64-bit word;
-//      finished 3x3 blocks go to the tile-wide slab at the slots of their CSR entries (entry stride
-//      80 bytes, so a block leaves as four 128-bit stores and one 64-bit store);
-//   2. write-out: three consecutive rows per warp, ten lanes each (9 components + one idle lane): a lane
-//      walks its row entry by entry, copies its component to global memory (72 contiguous bytes per
-//      group and instruction) and sums it, then stores its component of the diagonal entry; row starts
-//      in the slab are padded so that the three pieces read together fall into disjoint banks;
-//   3. fused mode: the diagonal blocks wait in shared memory until the tile is done; the last two warps
-//      of the CTA (they get the fewest job batches) then mask / invert them into prec, one lane per
-//      row, at the head of the next tile (prec_init + prec_inversion, src/preconditioner.cc:25-87,
-//      src/Fortran/elasclpr.f:19-53) — two warps with full lanes instead of every warp with four.
+// Per tile (job warps and write-out warps work side by side on different tiles, see ring_assembly_kernel):
+//   0. plan record by TMA (cp.async.bulk + mbarrier): the HEAD (header, row table, node list) three tiles ahead, the
+//      TAIL (batches, jobs, ring codes) and the coordinates (8-byte cp.async copies that signal the tail's barrier)
+//      two tiles ahead, as soon as the job warps have released the buffers;
+//   1. job warps: one lane per edge, 32 jobs per warp batch, ring codes 8 to a 64-bit word; finished 3x3 blocks go to
+//      one of two tile-wide slabs at the slots of their CSR entries (entry stride 80 bytes, so a block leaves as four
+//      128-bit stores and one 64-bit store);
+//   2. write-out warps: three consecutive rows per warp, ten lanes each (9 components + one idle lane): a lane walks
+//      its row entry by entry, copies its component to global memory (72 contiguous bytes per group and instruction)
+//      and sums it, then stores its component of the diagonal entry; row starts in the slab are padded so that the
+//      three pieces read together fall into disjoint banks;
+//   3. fused mode: the nine lanes that hold a row's diagonal block mask and invert it through warp shuffles (cofactors
+//      over the determinant; LAPACK's LU for a singular block) and write prec (prec_init + prec_inversion,
+//      src/preconditioner.cc:25-87, src/Fortran/elasclpr.f:19-53); interface rows leave raw, for the halo sum.
 // Every CSR entry is written exactly once by a plain store; the summation order is fixed by the plan.
 #include "kernels.cuh"
 #include "device_math.cuh"
