@@ -102,8 +102,6 @@ __device__ __forceinline__ void ring_mbar_arrive (uint64_t *bar)
 __device__ __forceinline__ void ring_mbar_wait (uint64_t *bar, unsigned parity, unsigned pollNs = 0)
 {
     unsigned done = 0;
-    const unsigned hint = pollNs >> 12 ? pollNs >> 12 : 20000u;      // upper bits of the knob: the suspend-time hint (ns)
-    pollNs &= 0xFFFu;
     #pragma unroll 1
     for (long spin = 0; spin < (1l << 18); spin++) {
         asm volatile (
@@ -111,7 +109,7 @@ __device__ __forceinline__ void ring_mbar_wait (uint64_t *bar, unsigned parity, 
             ".reg .pred p;\n"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"     // suspended (no issue slots) until an event
             "selp.u32 %0, 1, 0, p;\n"                                          // or the hint (ns) runs out
-            "}\n" : "=r"(done) : "r"(ring_smem_u32 (bar)), "r"(parity), "r"(hint) : "memory");
+            "}\n" : "=r"(done) : "r"(ring_smem_u32 (bar)), "r"(parity), "r"(20000u) : "memory");
         if (done) return;
         if (pollNs) __nanosleep (pollNs);
     }
@@ -708,9 +706,7 @@ cudaError_t launch_ring (int operatorID, const DeviceRingPlan &plan, int firstTi
     args.fusePrec = fusePrec;
     args.firstTile = firstTile; args.lastTile = firstTile + nbTiles;
     args.intfDone = intfDone;
-    // MFB_RING_POLL_NS (< 4096): sleep between two polls; MFB_RING_WAIT_HINT_NS: suspend-time hint of try_wait (default 20000)
-    static const unsigned pollNs = (getenv ("MFB_RING_POLL_NS") ? (unsigned)std::min (std::max (atoi (getenv ("MFB_RING_POLL_NS")), 0), 4095) : kRingPollNs)
-                                 | (getenv ("MFB_RING_WAIT_HINT_NS") ? (unsigned)std::min (std::max (atoi (getenv ("MFB_RING_WAIT_HINT_NS")), 1), 1000000) << 12 : 0u);
+    static const unsigned pollNs = getenv ("MFB_RING_POLL_NS") ? (unsigned)std::max (atoi (getenv ("MFB_RING_POLL_NS")), 0) : kRingPollNs;
     args.pollNs = pollNs;
     const int grid = std::max (1, std::min (ctas, nbTiles));
     return ring_dispatch (operatorID, threads, [&] (auto kernel, int t) {
