@@ -306,7 +306,8 @@ struct mfb_ctx {
     int *dIntfIndex = nullptr;
     std::vector<void*> p2pOpened;  // cudaIpcOpenMemHandle mappings to close
     bool p2pReady = false;
-    int p2pCtas = 4;
+    int p2pCtas = 2, p2pReserveCtas = 2;
+    int deviceCtas = 148;          // RING CTAs the device holds at once
 };
 
 namespace {
@@ -430,6 +431,7 @@ int build_device_ring_plan (mfb_ctx *c, const mfb_problem *p, const mfb_options 
     MFB_CUDA (ring_ctas_per_sm (c->operatorID, c->threads, c->tiledSmem, &perSM));
     perSM = std::max (perSM, 1);
     c->tiledCtas = (o && o->ctas > 0) ? o->ctas : (o && o->ctas == -1) ? (1 << 30) : prop.multiProcessorCount * perSM;
+    c->deviceCtas = prop.multiProcessorCount * perSM;
     return MFB_OK;
 }
 
@@ -542,7 +544,7 @@ int do_iteration (mfb_ctx *c)
         // stream) waits for the assembly kernel's interface tiles — the first tiles of every CTA —, stores their
         // blocks into the neighbours' windows over NVLink, waits for theirs and sums + inverts; the assembly kernel
         // takes ALL tiles on the rest of the device (it never waits for the exchange, so the pair cannot deadlock:
-        // its grid leaves haloReserveCtas free and the exchange kernel asks for no more SMs than that).
+        // its grid leaves p2pReserveCtas free and the exchange kernel asks for no more SMs than that).
         HaloP2PArgs a;
         a.state = c->p2pState;
         a.intfTarget = (unsigned)nIntfTiles * (unsigned)ring_write_out_warps (c->operatorID, c->threads);
@@ -561,7 +563,7 @@ int do_iteration (mfb_ctx *c)
         MFB_CUDA (cudaStreamWaitEvent (c->commStream, c->evIntfDone, 0));
         MFB_CUDA (launch_halo_p2p (a, c->operatorDim, c->p2pCtas, c->commStream));
         c->launches++;
-        const int ctas = std::max (c->tiledCtas - c->haloReserveCtas, 1);
+        const int ctas = std::max (std::min (c->tiledCtas, c->deviceCtas - c->p2pReserveCtas), 1);
         MFB_CUDA (launch_ring (c->operatorID, c->ringPlan, 0, c->plan.nbTiles, ctas, c->threads, c->tiledSmem, c->dCoord,
                                c->dValues, c->dPrec, 1, c->stream, &c->p2pState->intfDone));
         if (c->plan.nbTiles > 0) c->launches++;
@@ -1175,11 +1177,16 @@ extern "C" int mfb_ctx_p2p_connect (mfb_ctx *c, const unsigned char *cards)
     int64_t bytes = 0;
     MFB_CUDA (upload (&c->dPeerRecv, peerRecv.data (), peerRecv.size (), bytes));
     MFB_CUDA (upload (&c->dPeerFlag, peerFlag.data (), peerFlag.size (), bytes));
-    c->p2pCtas = 4;
-    if (const char *v = getenv ("MFB_P2P_CTAS")) c->p2pCtas = std::max (atoi (v), 1);
+    // The assembly grid leaves MFB_P2P_RESERVE_SMS SMs (default 2) to the exchange kernel, which runs one CTA on each
+    // (MFB_P2P_CTAS lowers that): never more SMs than are left free, or the pair could wait for each other.  Two instead
+    // of the four SMs the NCCL chain gets: the EIB block then takes 111 instead of 113 rounds of tiles per CTA.
     const int ctasPerSM = c->threads >= 640 ? 1 : 2;
-    c->p2pCtas = std::max (1, std::min (c->p2pCtas, c->haloReserveCtas / ctasPerSM));   // never more SMs than the assembly grid leaves free
-    if (c->haloReserveCtas < ctasPerSM) return fail (MFB_ERR_STATE, "mfb_ctx_p2p_connect: MFB_HALO_RESERVE_CTAS leaves no SM to the exchange kernel");
+    int reserveSMs = 2;
+    if (const char *v = getenv ("MFB_P2P_RESERVE_SMS")) reserveSMs = std::min (std::max (atoi (v), 1), 16);
+    c->p2pReserveCtas = reserveSMs * ctasPerSM;
+    c->p2pCtas = reserveSMs;
+    if (const char *v = getenv ("MFB_P2P_CTAS")) c->p2pCtas = std::min (std::max (atoi (v), 1), reserveSMs);
+    if (c->deviceCtas - c->p2pReserveCtas < 1) return fail (MFB_ERR_STATE, "mfb_ctx_p2p_connect: the device has too few SMs to run the exchange kernel beside the assembly kernel");
     c->p2pReady = true;
     return MFB_OK;
 }
