@@ -285,6 +285,16 @@ def test_ring_kernel_source_1024_threads(kernel_host, oracle, op):
     check_against_oracle(oracle, setup, values, prec)
 
 
+@pytest.mark.parametrize("threads", [640, 896])
+def test_ring_kernel_source_other_cta_shapes(kernel_host, oracle, threads):
+    """640 threads (11 job + 9 write-out warps at the registers of the launch) and 896 threads (16 + 12, per-warpgroup
+    register counts on the device)."""
+    mesh = mfb.Mesh.generate(8, 7, 6, seed=11)
+    setup = mfb.Setup(mesh, "ela")
+    values, prec = run_kernel_on_host(kernel_host, setup, rows=40, entries=700, ctas=2, threads=threads)
+    check_against_oracle(oracle, setup, values, prec)
+
+
 def test_ring_kernel_source_unfused_interface_and_random_tets(kernel_host, oracle):
     mesh = mfb.Mesh.generate(6, 6, 6, blocks=(2, 1, 1), rank=1, seed=2)
     setup = mfb.Setup(mesh, "ela")
