@@ -271,20 +271,25 @@ def time_paths(mfb, mesh, op, paths, device, steps=20, peak=None):
     out = {}
     E, N = mesh.nbElem, mesh.nbNodes
     for path in paths:
-        t0 = time.perf_counter()
-        setup = mfb.Setup(mesh, op, coloring=(path == "color"))
-        ctx = mfb.Context(setup, path=path, device=device, use_graph=(path == "color"))
-        build_s = time.perf_counter() - t0
-        for _ in range(3):
-            ctx.iteration()
-        ctx.sync()
-        ms = ctx.run_timed(steps) / steps
-        alg = algorithmic_bytes(op, E, setup.nbEdges, N)
-        out[path] = {"ms_per_step": ms, "value": E / (ms * 1e-3), "frac": alg / (ms * 1e-3) / 1e9 / peak if peak else None,
-                     "setup_s": round(build_s, 2)}
-        if path == "color":
-            out[path]["colors"] = setup.nbTotalColors
-        ctx.close()
+        try:
+            t0 = time.perf_counter()
+            setup = mfb.Setup(mesh, op, coloring=(path == "color"))
+            ctx = mfb.Context(setup, path=path, device=device, use_graph=(path in ("color", "blockcolor")))
+            build_s = time.perf_counter() - t0
+            for _ in range(3):
+                ctx.iteration()
+            ctx.sync()
+            ms = ctx.run_timed(steps) / steps
+            alg = algorithmic_bytes(op, E, setup.nbEdges, N)
+            out[path] = {"ms_per_step": ms, "value": E / (ms * 1e-3), "frac": alg / (ms * 1e-3) / 1e9 / peak if peak else None,
+                         "setup_s": round(build_s, 2)}
+            if path == "color":
+                out[path]["colors"] = setup.nbTotalColors
+            if path == "blockcolor":                       # locality-blocked colouring: launches = block colours
+                out[path].update({k: int(v) for k, v in ctx.plan_stats().items()})
+            ctx.close()
+        except mfb.MfbError as e:                          # a side measurement must not take the bench line with it
+            out[path] = {"error": str(e)[:200]}
     return out
 
 
@@ -293,7 +298,7 @@ def other_configs(mfb, args, device, peak):
     CPU builds where BASELINE.json names them."""
     from oracle_lib import Reference, ref_available
     out = {}
-    paths = ["ring", "tiled", "atomic", "color"]
+    paths = ["ring", "tiled", "atomic", "color", "blockcolor"]
     cores = os.cpu_count() or 1
     lm6 = mfb.Mesh.generate(25, 25, 40, seed=1)
     for op, key in (("lap", "1_LM6_lap"), ("ela", "2_LM6_ela")):
@@ -573,7 +578,7 @@ def main():
     dog.limit = 900.0
     other, configs = {}, None
     if world == 1 and not args.no_other_paths:
-        other = time_paths(mfb, mesh, args.op, [q for q in ("ring", "tiled", "atomic", "color") if q != args.path], local, 10, peak)
+        other = time_paths(mfb, mesh, args.op, [q for q in ("ring", "tiled", "atomic", "color", "blockcolor") if q != args.path], local, 10, peak)
     if world == 1 and args.configs != "none" and rank == 0:
         try:
             configs = other_configs(mfb, args, local, peak)

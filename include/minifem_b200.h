@@ -43,6 +43,12 @@ extern "C" {
                                  bench.py, and the fastest path: a warp-specialised kernel,
                                  768 threads per CTA, one CTA per SM (mfb_options.threads = 0 or 768; 384 = two CTAs per SM) */
 
+#define MFB_PATH_BLOCKCOLOR 4  /* memset + one launch per BLOCK colour: the elements are cut into spatial blocks, blocks of one
+                                 colour share no node, one CTA walks the local colours of its block (locality-blocked
+                                 colouring, the idea of the reference's D&C variant, src/assembly.cc:123-244).
+                                 Keeps its own element order: mfb_problem.elemToEdge / colorToElem are not used,
+                                 mfb_options.tileElems = elements per block (0 = 1024) */
+
 const char *mfb_last_error (void);
 const char *mfb_version (void);
 
@@ -261,6 +267,15 @@ int mfb_tile_plan_selfcheck (const mfb_problem *problem, int tileRows, int tileE
  * [11] interface tiles. */
 int mfb_ring_plan_selfcheck (const mfb_problem *problem, int tileRows, int tileEntries,
                              int64_t stats[12]);
+
+/* The layout of MFB_PATH_BLOCKCOLOR, built on the host (no GPU needed; the context builds the same internally):
+ * elemOrder[nbElem] = element ids sorted by (block colour, block, local colour, id); blocks
+ * [launchStart[c], launchStart[c+1]) have block colour c and share no node; local colour q of block b is the
+ * positions [localStart[localIndex[b] + q], localStart[localIndex[b] + q + 1]) of elemOrder, its elements share no
+ * node.  Capacities: launchStart 65, localIndex nbElem + 2, localStart 2 * nbElem + 2.  counts = {blocks, block
+ * colours, max local colours of a block, entries of localStart}.  blockElems 0 = 1024. */
+int mfb_block_coloring (const int *elemToNode, int nbElem, int nbNodes, const double *coord, int blockElems,
+                        int *elemOrder, int *launchStart, int *localIndex, int *localStart, int counts[4]);
 
 /* Pinned host memory for the *_host calls. */
 int mfb_host_alloc (void **ptr, int64_t bytes);

@@ -268,6 +268,9 @@ struct mfb_ctx {
     int nbElem = 0, nbNodes = 0, nbEdges = 0, nbBlocks = 1, rank = 0;
     int nbIntf = 0, nbIntfNodes = 0, nbUniqIntf = 0, nbTotalColors = 0;
     std::vector<int> colorToElem, intfIndex, neighbors;
+    std::vector<int> blockLaunchStart;      // MFB_PATH_BLOCKCOLOR: blocks per block colour (host/mesh_topology.h)
+    int *dLocalIndex = nullptr, *dLocalStart = nullptr;
+    int blockStats[3] = {0, 0, 0};          // blocks, block colours, max local colours
 
     cudaStream_t stream = nullptr, commStream = nullptr;
     cudaEvent_t evStart[5] = {}, evStop[5] = {}, evIntfDone = nullptr, evCommDone = nullptr;
@@ -478,6 +481,15 @@ int do_assembly (mfb_ctx *c, int fusePrec)
     int rc = do_zero (c);                                  // :649-651 / :663-666
     if (rc) return rc;
     if (c->path == MFB_PATH_ATOMIC) return do_scatter_interval (c, 0, c->nbElem);   // :653-659
+    if (c->path == MFB_PATH_BLOCKCOLOR) {
+        for (size_t bcol = 0; bcol + 1 < c->blockLaunchStart.size (); bcol++) {
+            const int first = c->blockLaunchStart[bcol], count = c->blockLaunchStart[bcol + 1] - first;
+            MFB_CUDA (launch_scatter_blocks (c->operatorID, c->dCoord, c->dElemToNode, c->dElemToEdge, c->dValues,
+                                             c->dLocalIndex, c->dLocalStart, first, count, c->stream));
+            if (count > 0) c->launches++;
+        }
+        return MFB_OK;
+    }
     for (int color = 0; color < c->nbTotalColors; color++) {                        // :593-611
         rc = do_scatter_interval (c, c->colorToElem[color], c->colorToElem[color + 1] - c->colorToElem[color]);
         if (rc) return rc;
@@ -645,7 +657,7 @@ extern "C" void mfb_ctx_destroy (mfb_ctx *c)
     for (void *p : p2pPtrs) if (p) cudaFree (p);
     void *ptrs[] = {c->dCoord, c->dValues, c->dPrec, c->dSend, c->dRecv, c->dElemToNode, c->dRow, c->dCol,
                     c->dElemToEdge, c->dCheckBounds, c->dDiagIndex, c->dIntfNodes, c->dUniqNodes,
-                    c->dSlotIndex, c->dSlots, c->dNorm};
+                    c->dSlotIndex, c->dSlots, c->dNorm, c->dLocalIndex, c->dLocalStart};
     for (void *p : ptrs) if (p) cudaFree (p);
     for (void *p : c->planAllocs) if (p) cudaFree (p);
     for (int s = 0; s < 5; s++) {
@@ -682,7 +694,7 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     c->device = o ? o->device : 0;
     c->threads = (o && o->threads > 0) ? o->threads : 256;
     c->useGraph = o ? o->useGraph : 0;
-    if (c->path < MFB_PATH_TILED || c->path > MFB_PATH_RING) return fail (MFB_ERR_ARG, "mfb_ctx_create: unknown path");
+    if (c->path < MFB_PATH_TILED || c->path > MFB_PATH_BLOCKCOLOR) return fail (MFB_ERR_ARG, "mfb_ctx_create: unknown path");
     if (c->path == MFB_PATH_RING) {          // a write-once path like TILED: same stages, same fused iteration
         c->ring = true;
         c->path = MFB_PATH_TILED;
@@ -743,9 +755,27 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
     MFB_CUDA (launch_diag_index (c->dRow, c->dCol, c->dDiagIndex, c->nbNodes, c->stream));
 
     if (c->path != MFB_PATH_TILED) {
-        MFB_CUDA (upload (&c->dElemToNode, p->elemToNode, (size_t)p->nbElem * 4, c->meshBytes));
-        MFB_CUDA (upload (&c->dElemToEdge, p->elemToEdge, (size_t)p->nbElem * 16, c->meshBytes));
-        if (!p->elemToEdge && p->nbElem > 0) {            // create_elemToEdge on the device
+        const int *elemToEdgeHost = p->elemToEdge;
+        if (c->path == MFB_PATH_BLOCKCOLOR) {
+            // the library's own element order: by (block colour, block, local colour); elemToEdge is rebuilt for it below
+            BlockColoring bc;
+            int blockElems = 1024;
+            if (o && o->tileElems > 0) blockElems = o->tileElems;
+            const int rcb = build_block_coloring (p->elemToNode, p->nbElem, p->nbNodes, p->coord, blockElems, bc);
+            if (rcb == -1) return fail (MFB_ERR_COLORS, "mfb_ctx_create: a block needs more than 128 local colours");
+            if (rcb == -2) return fail (MFB_ERR_COLORS, "mfb_ctx_create: the blocks need more than 64 colours");
+            std::vector<int> permuted ((size_t)p->nbElem * 4);
+            for (int e = 0; e < p->nbElem; e++) memcpy (&permuted[(size_t)e * 4], p->elemToNode + (size_t)bc.elemOrder[e] * 4, 4 * sizeof (int));
+            MFB_CUDA (upload (&c->dElemToNode, permuted.data (), permuted.size (), c->meshBytes));
+            MFB_CUDA (upload (&c->dLocalIndex, bc.localIndex.data (), bc.localIndex.size (), c->meshBytes));
+            MFB_CUDA (upload (&c->dLocalStart, bc.localStart.data (), bc.localStart.size (), c->meshBytes));
+            c->blockLaunchStart = bc.launchStart;
+            c->blockStats[0] = bc.nbBlocks; c->blockStats[1] = bc.nbBlockColors; c->blockStats[2] = bc.maxLocalColors;
+            elemToEdgeHost = nullptr;
+        }
+        else MFB_CUDA (upload (&c->dElemToNode, p->elemToNode, (size_t)p->nbElem * 4, c->meshBytes));
+        MFB_CUDA (upload (&c->dElemToEdge, elemToEdgeHost, (size_t)p->nbElem * 16, c->meshBytes));
+        if (!elemToEdgeHost && p->nbElem > 0) {            // create_elemToEdge on the device
             int *dMissing = nullptr, missing = 0;
             MFB_CUDA (cudaMalloc ((void**)&dMissing, sizeof (int)));
             MFB_CUDA (cudaMemsetAsync (dMissing, 0, sizeof (int), c->stream));
@@ -831,6 +861,7 @@ extern "C" int mfb_ctx_assembly_interval (mfb_ctx *c, int firstElem, int lastEle
 {
     CTX_ENTER (c);
     if (c->path == MFB_PATH_TILED) return fail (MFB_ERR_STATE, "mfb_ctx_assembly_interval: element intervals exist on the ATOMIC / COLOR paths only");
+    if (c->path == MFB_PATH_BLOCKCOLOR) return fail (MFB_ERR_STATE, "mfb_ctx_assembly_interval: the BLOCKCOLOR path keeps its own element order; use ATOMIC or COLOR");
     if (firstElem < 0 || lastElem >= c->nbElem) return fail (MFB_ERR_ARG, "mfb_ctx_assembly_interval: interval out of range");
     if (c->path == MFB_PATH_COLOR) {
         // The plain += of the COLOR kernel is only conflict-free inside one colour (coloring.cc): an interval that
@@ -1035,6 +1066,10 @@ extern "C" int mfb_ctx_device_bytes (mfb_ctx *c, int64_t *meshBytes, int64_t *pl
 extern "C" int mfb_ctx_plan_stats (mfb_ctx *c, int64_t stats[8])
 {
     if (!c || !stats) return fail (MFB_ERR_ARG, "NULL argument");
+    if (c->path == MFB_PATH_BLOCKCOLOR) {       // [0] blocks [1] block colours (= launches per assembly) [2] max local colours of a block
+        for (int k = 0; k < 8; k++) stats[k] = k < 3 ? c->blockStats[k] : 0;
+        return MFB_OK;
+    }
     if (c->ring) {              // RING: [1] jobs (mesh edges) [2] ring steps [4] max nodes [6] padded lane-steps
         stats[0] = c->ringStats.nbTiles; stats[1] = c->ringStats.nbJobs; stats[2] = c->ringStats.nbRingSteps;
         stats[3] = c->ringStats.maxRows; stats[4] = c->ringStats.maxNodes; stats[5] = (int64_t)c->tiledSmem;
@@ -1268,6 +1303,25 @@ extern "C" int mfb_ctx_run_timed (mfb_ctx *c, int steps, float *ms)
     MFB_CUDA (cudaEventElapsedTime (ms, c->evStart[4], c->evStop[4]));
     c->stageRan[4] = true;
     return p2p_status (c);
+}
+
+// Host builder of the locality-blocked colouring, exposed for the CPU tests (no GPU): elemOrder[nbElem], and the three
+// index arrays with their sizes in counts[4] = {blocks, block colours, max local colours, localStart entries};
+// launchStart holds up to 65 ints, localIndex nbElem + 2, localStart 2 * nbElem + 2 (upper bounds).
+extern "C" int mfb_block_coloring (const int *elemToNode, int nbElem, int nbNodes, const double *coord, int blockElems,
+                                   int *elemOrder, int *launchStart, int *localIndex, int *localStart, int counts[4])
+{
+    if ((nbElem > 0 && (!elemToNode || !coord)) || !elemOrder || !launchStart || !localIndex || !localStart || !counts) return fail (MFB_ERR_ARG, "mfb_block_coloring: NULL argument");
+    for (int64_t q = 0; q < (int64_t)nbElem * 4; q++) if (elemToNode[q] < 1 || elemToNode[q] > nbNodes) return fail (MFB_ERR_ARG, "mfb_block_coloring: node id out of range");
+    BlockColoring bc;
+    const int rc = build_block_coloring (elemToNode, nbElem, nbNodes, coord, blockElems > 0 ? blockElems : 1024, bc);
+    if (rc) return fail (MFB_ERR_COLORS, rc == -1 ? "mfb_block_coloring: a block needs more than 128 local colours" : "mfb_block_coloring: the blocks need more than 64 colours");
+    std::copy (bc.elemOrder.begin (), bc.elemOrder.end (), elemOrder);
+    std::copy (bc.launchStart.begin (), bc.launchStart.end (), launchStart);
+    std::copy (bc.localIndex.begin (), bc.localIndex.end (), localIndex);
+    std::copy (bc.localStart.begin (), bc.localStart.end (), localStart);
+    counts[0] = bc.nbBlocks; counts[1] = bc.nbBlockColors; counts[2] = bc.maxLocalColors; counts[3] = (int)bc.localStart.size ();
+    return MFB_OK;
 }
 
 extern "C" int mfb_tile_plan_selfcheck (const mfb_problem *p, int tileRows, int tileElems, int64_t stats[6])

@@ -14,6 +14,10 @@ namespace mfb {
 cudaError_t launch_scatter (int operatorID, bool atomic, const double *coord, const int *elemToNode,
                             const int *elemToEdge, double *values, int firstElem, int count,
                             cudaStream_t stream);
+// BLOCKCOLOR: the blocks [firstBlock, firstBlock + nbBlocks) of one block colour, one CTA each (host/mesh_topology.h).
+cudaError_t launch_scatter_blocks (int operatorID, const double *coord, const int *elemToNode, const int *elemToEdge,
+                                   double *values, const int *localIndex, const int *localStart, int firstBlock,
+                                   int nbBlocks, cudaStream_t stream);
 cudaError_t launch_elem_to_edge (const int *row, const int *col, const int *elemToNode,
                                  int *elemToEdge, int nbElem, int *missing, cudaStream_t stream);
 cudaError_t launch_diag_index (const int *row, const int *col, int *diagIndex, int nbNodes,

@@ -19,16 +19,11 @@ __device__ __forceinline__ void accumulate (double *addr, double v)
     else        *addr += v;                // conflict-free by colouring
 }
 
+// One element: what assembly_{lap,ela}_seq do for it (src/assembly.cc:332-479, :485-588).
 template <int OPDIM, bool ATOMIC>
-__global__ void __launch_bounds__(128)
-scatter_elements_kernel (const double *__restrict__ coord, const int4 *__restrict__ elemToNode,
-                         const int4 *__restrict__ elemToEdge, double *__restrict__ values,
-                         int firstElem, int nbElemInterval)
+__device__ __forceinline__ void scatter_element (const double *__restrict__ coord, const int4 *__restrict__ elemToNode,
+                                                 const int4 *__restrict__ elemToEdge, double *__restrict__ values, size_t e)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nbElemInterval) return;
-    const size_t e = (size_t)firstElem + t;
-
     const int4 nd = __ldg (elemToNode + e);                 // 1-based ids, one 16 B load
     const int ids[4] = {nd.x - 1, nd.y - 1, nd.z - 1, nd.w - 1};
     double p[12], c[12];
@@ -57,6 +52,38 @@ scatter_elements_kernel (const double *__restrict__ coord, const int4 *__restric
                 for (int q = 0; q < 9; q++) accumulate<ATOMIC> (dst + q, blk[q]);
             }
         }
+    }
+}
+
+template <int OPDIM, bool ATOMIC>
+__global__ void __launch_bounds__(128)
+scatter_elements_kernel (const double *__restrict__ coord, const int4 *__restrict__ elemToNode,
+                         const int4 *__restrict__ elemToEdge, double *__restrict__ values,
+                         int firstElem, int nbElemInterval)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbElemInterval) return;
+    scatter_element<OPDIM, ATOMIC> (coord, elemToNode, elemToEdge, values, (size_t)firstElem + t);
+}
+
+// BLOCKCOLOR path (host/mesh_topology.h: build_block_coloring): one CTA per block of a block colour — the blocks of one
+// launch share no node —, the block's elements local colour by local colour with a block barrier in between: plain
+// read-modify-write without atomics, and a CSR row is updated many times by ONE CTA while it sits in L1 / L2.
+constexpr int kBlockColorThreads = 128;
+template <int OPDIM>
+__global__ void __launch_bounds__(kBlockColorThreads)
+scatter_blocks_kernel (const double *__restrict__ coord, const int4 *__restrict__ elemToNode,
+                       const int4 *__restrict__ elemToEdge, double *values,
+                       const int *__restrict__ localIndex, const int *__restrict__ localStart, int firstBlock)
+{
+    const int b = firstBlock + blockIdx.x;
+    const int first = localIndex[b], nbLocal = localIndex[b + 1] - first - 1;
+    for (int c = 0; c < nbLocal; c++) {
+        const int lo = localStart[first + c], hi = localStart[first + c + 1];
+        for (int e = lo + threadIdx.x; e < hi; e += kBlockColorThreads) {
+            scatter_element<OPDIM, false> (coord, elemToNode, elemToEdge, values, (size_t)e);
+        }
+        __syncthreads ();          // the next local colour adds to entries this one has written
     }
 }
 
@@ -110,6 +137,18 @@ cudaError_t launch_scatter (int operatorID, bool atomic, const double *coord, co
         if (atomic) scatter_elements_kernel<9, true><<<blocks, threads, 0, stream>>> (coord, e2n, e2e, values, firstElem, count);
         else        scatter_elements_kernel<9, false><<<blocks, threads, 0, stream>>> (coord, e2n, e2e, values, firstElem, count);
     }
+    return cudaGetLastError ();
+}
+
+cudaError_t launch_scatter_blocks (int operatorID, const double *coord, const int *elemToNode, const int *elemToEdge,
+                                   double *values, const int *localIndex, const int *localStart, int firstBlock,
+                                   int nbBlocks, cudaStream_t stream)
+{
+    if (nbBlocks <= 0) return cudaSuccess;
+    const int4 *e2n = reinterpret_cast<const int4*> (elemToNode);
+    const int4 *e2e = reinterpret_cast<const int4*> (elemToEdge);
+    if (operatorID == 0) scatter_blocks_kernel<1><<<nbBlocks, kBlockColorThreads, 0, stream>>> (coord, e2n, e2e, values, localIndex, localStart, firstBlock);
+    else                 scatter_blocks_kernel<9><<<nbBlocks, kBlockColorThreads, 0, stream>>> (coord, e2n, e2e, values, localIndex, localStart, firstBlock);
     return cudaGetLastError ();
 }
 

@@ -1,5 +1,6 @@
 #include "mesh_topology.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -140,6 +141,127 @@ double double_norm (const double *tab, int64_t size)
     double acc = 0;
     for (int64_t i = 0; i < size; i++) acc += tab[i] * tab[i];
     return std::sqrt (acc);
+}
+
+namespace {
+
+// recursive bisection of element centroids into leaves of <= leafSize elements (in `idx` order)
+void bisect_elements (std::vector<int> &idx, int lo, int hi, int leafSize, const std::vector<float> &centroid, std::vector<int> &leafStart)
+{
+    const int count = hi - lo;
+    if (count <= leafSize) { leafStart.push_back (lo); return; }
+    float bmin[3], bmax[3];
+    for (int a = 0; a < 3; a++) bmin[a] = bmax[a] = centroid[(size_t)idx[lo] * 3 + a];
+    for (int q = lo + 1; q < hi; q++) {
+        for (int a = 0; a < 3; a++) {
+            const float v = centroid[(size_t)idx[q] * 3 + a];
+            bmin[a] = std::min (bmin[a], v); bmax[a] = std::max (bmax[a], v);
+        }
+    }
+    int axis = 0;
+    for (int a = 1; a < 3; a++) if (bmax[a] - bmin[a] > bmax[axis] - bmin[axis]) axis = a;
+    const int leaves = (count + leafSize - 1) / leafSize;
+    const int mid = lo + (int)((int64_t)count * (leaves / 2) / leaves);
+    std::nth_element (idx.begin () + lo, idx.begin () + mid, idx.begin () + hi, [&] (int x, int y) {
+        const float cx = centroid[(size_t)x * 3 + axis], cy = centroid[(size_t)y * 3 + axis];
+        return cx < cy || (cx == cy && x < y);
+    });
+    bisect_elements (idx, lo, mid, leafSize, centroid, leafStart);
+    bisect_elements (idx, mid, hi, leafSize, centroid, leafStart);
+}
+
+}  // namespace
+
+int build_block_coloring (const int *elemToNode, int nbElem, int nbNodes, const double *coord, int blockElems,
+                          BlockColoring &out)
+{
+    out = BlockColoring ();
+    out.launchStart.assign (1, 0);
+    out.localIndex.assign (1, 0);
+    out.localStart.assign (1, 0);
+    if (nbElem <= 0) return 0;
+    blockElems = std::max (blockElems, 1);
+    // ---- blocks: leaves of the bisection of the centroids ------------------------------------------------------
+    std::vector<float> centroid ((size_t)nbElem * 3);
+    for (int e = 0; e < nbElem; e++) {
+        for (int a = 0; a < 3; a++) {
+            double sum = 0.0;
+            for (int k = 0; k < kDimElem; k++) sum += coord[(size_t)(elemToNode[(size_t)e * kDimElem + k] - 1) * 3 + a];
+            centroid[(size_t)e * 3 + a] = (float)(0.25 * sum);
+        }
+    }
+    std::vector<int> idx ((size_t)nbElem), leafStart;
+    for (int e = 0; e < nbElem; e++) idx[e] = e;
+    bisect_elements (idx, 0, nbElem, blockElems, centroid, leafStart);
+    leafStart.push_back (nbElem);
+    const int nbBlocks = (int)leafStart.size () - 1;
+    // ---- block colours: first colour none of the block's nodes has seen (64-bit masks per node) ------------------
+    std::vector<uint64_t> nodeBlockMask ((size_t)nbNodes, 0);
+    std::vector<int> blockColor ((size_t)nbBlocks, 0);
+    int nbBlockColors = 0;
+    for (int b = 0; b < nbBlocks; b++) {
+        uint64_t forbidden = 0;
+        for (int q = leafStart[b]; q < leafStart[b + 1]; q++) {
+            const int *en = elemToNode + (size_t)idx[q] * kDimElem;
+            for (int k = 0; k < kDimElem; k++) forbidden |= nodeBlockMask[en[k] - 1];
+        }
+        if (~forbidden == 0) return -2;
+        const int color = __builtin_ctzll (~forbidden);
+        blockColor[b] = color;
+        nbBlockColors = std::max (nbBlockColors, color + 1);
+        for (int q = leafStart[b]; q < leafStart[b + 1]; q++) {
+            const int *en = elemToNode + (size_t)idx[q] * kDimElem;
+            for (int k = 0; k < kDimElem; k++) nodeBlockMask[en[k] - 1] |= 1ull << color;
+        }
+    }
+    // ---- blocks in colour order (stable), local colours inside every block ------------------------------------------
+    std::vector<int> blocksByColor ((size_t)nbBlocks), countOfColor ((size_t)nbBlockColors + 1, 0);
+    for (int b = 0; b < nbBlocks; b++) countOfColor[blockColor[b] + 1]++;
+    for (int c = 0; c < nbBlockColors; c++) countOfColor[c + 1] += countOfColor[c];
+    out.launchStart.assign (countOfColor.begin (), countOfColor.end ());
+    {
+        std::vector<int> cursor (countOfColor.begin (), countOfColor.end () - 1);
+        for (int b = 0; b < nbBlocks; b++) blocksByColor[cursor[blockColor[b]]++] = b;
+    }
+    out.elemOrder.reserve ((size_t)nbElem);
+    out.localIndex.clear (); out.localStart.clear ();
+    std::vector<uint64_t> maskLo ((size_t)nbNodes, 0), maskHi ((size_t)nbNodes, 0);
+    std::vector<int> elems, localColor;
+    for (int nb = 0; nb < nbBlocks; nb++) {
+        const int b = blocksByColor[nb];
+        elems.assign (idx.begin () + leafStart[b], idx.begin () + leafStart[b + 1]);
+        std::sort (elems.begin (), elems.end ());                  // greedy in element order, like coloring.cc
+        localColor.assign (elems.size (), 0);
+        int nbLocal = 0;
+        for (size_t q = 0; q < elems.size (); q++) {
+            const int *en = elemToNode + (size_t)elems[q] * kDimElem;
+            uint64_t lo = 0, hi = 0;
+            for (int k = 0; k < kDimElem; k++) { lo |= maskLo[en[k] - 1]; hi |= maskHi[en[k] - 1]; }
+            int color;
+            if (~lo != 0) color = __builtin_ctzll (~lo);
+            else if (~hi != 0) color = 64 + __builtin_ctzll (~hi);
+            else return -1;
+            localColor[q] = color;
+            nbLocal = std::max (nbLocal, color + 1);
+            for (int k = 0; k < kDimElem; k++) {
+                if (color < 64) maskLo[en[k] - 1] |= 1ull << color; else maskHi[en[k] - 1] |= 1ull << (color - 64);
+            }
+        }
+        for (size_t q = 0; q < elems.size (); q++) {               // the masks are per block: clear what this block set
+            const int *en = elemToNode + (size_t)elems[q] * kDimElem;
+            for (int k = 0; k < kDimElem; k++) { maskLo[en[k] - 1] = 0; maskHi[en[k] - 1] = 0; }
+        }
+        out.localIndex.push_back ((int)out.localStart.size ());
+        for (int c = 0; c < nbLocal; c++) {
+            out.localStart.push_back ((int)out.elemOrder.size ());
+            for (size_t q = 0; q < elems.size (); q++) if (localColor[q] == c) out.elemOrder.push_back (elems[q]);
+        }
+        out.localStart.push_back ((int)out.elemOrder.size ());     // end of the block's last colour
+        out.maxLocalColors = std::max (out.maxLocalColors, nbLocal);
+    }
+    out.localIndex.push_back ((int)out.localStart.size ());
+    out.nbBlocks = nbBlocks; out.nbBlockColors = nbBlockColors;
+    return 0;
 }
 
 }  // namespace mfb

@@ -46,6 +46,25 @@ int build_elem_to_edge (const int *row, const int *col, const int *elemToNode,
 int color_elements (const int *elemToNode, int nbElem, int nbNodes, int *colorPart,
                     int *colorToElem, int *colorPerm);
 
+// Locality-blocked colouring (the idea behind the reference's D&C variant,
+// src/assembly.cc:123-244: colour leaves of a spatial decomposition instead of single elements).  The elements
+// are cut into blocks of <= blockElems by recursive bisection of their centroids; BLOCKS are coloured so that two
+// blocks of one colour share no node (one launch per block colour, one CTA per block), and inside a block the
+// elements are coloured greedily in element order (the CTA walks its local colours with a barrier in between).
+// A CSR row is then touched by few CTAs, each of which adds to it many times while it sits in L1 / L2 — where a
+// colour of the element-wise colouring touches every row of the matrix once.
+struct BlockColoring {
+    std::vector<int> elemOrder;    // new position -> old element id: sorted by (block colour, block, local colour, id)
+    std::vector<int> launchStart;  // nbBlockColors + 1: blocks [launchStart[c], launchStart[c+1]) have block colour c
+    std::vector<int> localIndex;   // nbBlocks + 1: block b's local-colour offsets are localStart[localIndex[b] .. localIndex[b+1]]
+    std::vector<int> localStart;   // element positions (new numbering); local colour q of block b =
+                                   // [localStart[localIndex[b] + q], localStart[localIndex[b] + q + 1])
+    int nbBlocks = 0, nbBlockColors = 0, maxLocalColors = 0;
+};
+// Returns 0, -1 if a block needs more than kMaxColor local colours, -2 if the blocks need more than 64 colours.
+int build_block_coloring (const int *elemToNode, int nbElem, int nbNodes, const double *coord, int blockElems,
+                          BlockColoring &out);
+
 // tab[perm[i]] <- tab[i] for rows of `dim` ints.
 void permute_rows (int *tab, const int *perm, int nbItem, int dim);
 

@@ -14,7 +14,8 @@ PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))            # mini-fem_b200/
 LIB_PATH = os.environ.get("MFB_LIBRARY") or os.path.join(PKG_ROOT, "libminifem_b200.so")   # MFB_LIBRARY: an experimental build
 
 PATH_TILED, PATH_ATOMIC, PATH_COLOR, PATH_RING = 0, 1, 2, 3
-PATH_NAMES = {"tiled": PATH_TILED, "atomic": PATH_ATOMIC, "color": PATH_COLOR, "ring": PATH_RING}
+PATH_BLOCKCOLOR = 4
+PATH_NAMES = {"tiled": PATH_TILED, "atomic": PATH_ATOMIC, "color": PATH_COLOR, "ring": PATH_RING, "blockcolor": PATH_BLOCKCOLOR}
 COMM_ID_BYTES = 128
 P2P_CARD_BYTES = 1024
 
@@ -94,6 +95,7 @@ lib.mfb_ctx_p2p_card.argtypes = [C.c_void_p, C.c_void_p]
 lib.mfb_ctx_p2p_connect.argtypes = [C.c_void_p, C.c_void_p]
 lib.mfb_ctx_p2p_enable.argtypes = [C.c_void_p, C.c_int]
 lib.mfb_ctx_p2p_active.argtypes = [C.c_void_p]
+lib.mfb_block_coloring.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_int)]
 lib.mfb_ctx_halo_pack_host.argtypes = [C.c_void_p, C.c_void_p]
 lib.mfb_ctx_halo_add_host.argtypes = [C.c_void_p, C.c_void_p]
 lib.mfb_ctx_prec_inversion_interface.argtypes = [C.c_void_p]
@@ -130,7 +132,7 @@ DECLARED_SYMBOLS = [
     "mfb_host_free", "mfb_device_count",
     "mfb_device_create_nodeToNode", "mfb_device_create_elemToEdge", "mfb_device_coloring_creation",
     "mfb_ctx_norms", "mfb_ctx_iteration_norms_host",
-    "mfb_ctx_p2p_card", "mfb_ctx_p2p_connect", "mfb_ctx_p2p_enable", "mfb_ctx_p2p_active",
+    "mfb_ctx_p2p_card", "mfb_ctx_p2p_connect", "mfb_ctx_p2p_enable", "mfb_ctx_p2p_active", "mfb_block_coloring",
 ]
 
 
@@ -236,6 +238,23 @@ def device_coloring_creation(elemToNode, nbNodes, device=0):
     _check(lib.mfb_device_coloring_creation(_ptr(e2n), nbElem, nbNodes, _ptr(part), _ptr(c2e), _ptr(perm),
                                             C.byref(nb), device), "mfb_device_coloring_creation")
     return part[:nbElem], c2e[:nb.value + 1].copy(), perm[:nbElem], nb.value
+
+
+def block_coloring(elemToNode, nbNodes, coord, block_elems=0):
+    """mfb_block_coloring: (elemOrder, launchStart, localIndex, localStart, dict of counts)."""
+    e2n = _i32(elemToNode)
+    nbElem = e2n.size // 4
+    xyz = np.ascontiguousarray(coord, np.float64)
+    order = np.zeros(max(nbElem, 1), np.int32)
+    launch = np.zeros(65, np.int32)
+    index = np.zeros(nbElem + 2, np.int32)
+    start = np.zeros(2 * nbElem + 2, np.int32)
+    counts = (C.c_int * 4)()
+    _check(lib.mfb_block_coloring(_ptr(e2n), nbElem, nbNodes, _ptr(xyz), block_elems, _ptr(order), _ptr(launch), _ptr(index),
+                                  _ptr(start), counts), "mfb_block_coloring")
+    blocks, colors, max_local, entries = [int(v) for v in counts]
+    return (order[:nbElem], launch[:colors + 1], index[:blocks + 1], start[:entries],
+            dict(blocks=blocks, block_colors=colors, max_local_colors=max_local))
 
 
 def permute_int_2d(tab, perm, dim):
@@ -450,6 +469,8 @@ class Context:
     def plan_stats(self):
         s = (C.c_int64 * 8)()
         _check(lib.mfb_ctx_plan_stats(self.handle, s), "mfb_ctx_plan_stats")
+        if self.path == PATH_BLOCKCOLOR:
+            return dict(blocks=s[0], block_colors=s[1], max_local_colors=s[2])
         if self.path == PATH_RING:
             return dict(tiles=s[0], jobs=s[1], ring_steps=s[2], max_rows=s[3], max_nodes=s[4], smem_bytes=s[5],
                         padded_lane_steps=s[6], max_blob_bytes=s[7])

@@ -38,7 +38,7 @@ for path in a.paths.split(","):
     setup = mfb.Setup(mesh, a.op, coloring=(path == "color"))
     t1 = time.time()
     ctx = mfb.Context(setup, path=path, tile_rows=a.tile_rows, tile_elems=a.tile_elems, threads=a.threads,
-                      use_graph=(path == "color"), ctas=a.ctas, bank_aware=not a.no_bank_aware)
+                      use_graph=(path in ("color", "blockcolor")), ctas=a.ctas, bank_aware=not a.no_bank_aware)
     t2 = time.time()
     for _ in range(3):
         ctx.iteration()
@@ -53,7 +53,7 @@ for path in a.paths.split(","):
         line += f"  plan {ctx.plan_stats()} bytes {ctx.device_bytes()}"
     print(line, flush=True)
     v, p = ctx.download()
-    if path != "color":
+    if path not in ("color",):
         if ref is None:
             ref = (v, p)
         else:
