@@ -758,6 +758,12 @@ static int ctx_create_impl (const mfb_problem *p, const mfb_options *o, mfb_ctx 
         const int *elemToEdgeHost = p->elemToEdge;
         if (c->path == MFB_PATH_BLOCKCOLOR) {
             // the library's own element order: by (block colour, block, local colour); elemToEdge is rebuilt for it below
+            for (int e = 0; e < p->nbElem; e++) {              // the kernel updates the four entries of a row of the element matrix together
+                const int *en = p->elemToNode + (size_t)e * 4;
+                if (en[0] == en[1] || en[0] == en[2] || en[0] == en[3] || en[1] == en[2] || en[1] == en[3] || en[2] == en[3]) {
+                    return fail (MFB_ERR_ARG, "mfb_ctx_create: an element names a node twice (element " + std::to_string (e) + ")");
+                }
+            }
             BlockColoring bc;
             int blockElems = 1024;
             if (o && o->tileElems > 0) blockElems = o->tileElems;
