@@ -288,8 +288,8 @@ def time_paths(mfb, mesh, op, paths, device, steps=20, peak=None):
             if path == "blockcolor":                       # locality-blocked colouring: launches = block colours
                 out[path].update({k: int(v) for k, v in ctx.plan_stats().items()})
             ctx.close()
-        except mfb.MfbError as e:                          # a side measurement must not take the bench line with it
-            out[path] = {"error": str(e)[:200]}
+        except Exception as e:                             # noqa: BLE001 (a side measurement must not take the bench line with it)
+            out[path] = {"error": repr(e)[:200]}
     return out
 
 

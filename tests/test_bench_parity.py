@@ -104,3 +104,29 @@ def test_algorithmic_bytes_match_survey():
     E, N, Z = 6000000, 1030301, 15210901
     assert bench.algorithmic_bytes("ela", E, Z, N) == 16 * E + 76 * Z + 112 * N == 1367422188
     assert bench.algorithmic_bytes("lap", E, Z, N) == 16 * E + 12 * Z + 36 * N
+
+
+def test_time_paths_records_every_path_and_survives_a_failing_one():
+    """bench.time_paths (the `other_paths` / `configs` side measurements) with stand-in contexts: the blocked colouring
+    reports its launch structure, and a path that fails is recorded instead of taking the bench line with it."""
+    class Setup:
+        def __init__(self, mesh, op, coloring=False): self.nbEdges, self.nbTotalColors = 100, 7
+    class Ctx:
+        def __init__(self, setup, path, device=0, use_graph=False):
+            if path == "tiled": raise mfb.MfbError("tile plan needs more than 227 KB")
+            if path == "atomic": raise KeyError("anything else")
+            self.path, self.graph = path, use_graph
+        def iteration(self): pass
+        def sync(self): pass
+        def run_timed(self, steps): return 2.0 * steps
+        def plan_stats(self): return dict(blocks=5, block_colors=3, max_local_colors=9)
+        def close(self): pass
+    class Fake:
+        MfbError = mfb.MfbError
+    Fake.Setup, Fake.Context = Setup, Ctx
+    class Mesh: nbElem, nbNodes = 1000, 300
+    out = bench.time_paths(Fake, Mesh, "ela", ["ring", "tiled", "atomic", "color", "blockcolor"], 0, 5, peak=1000.0)
+    assert out["ring"]["ms_per_step"] == 2.0 and out["ring"]["value"] == 1000 / 2e-3 and "colors" not in out["ring"]
+    assert "227 KB" in out["tiled"]["error"] and "KeyError" in out["atomic"]["error"]
+    assert out["color"]["colors"] == 7
+    assert out["blockcolor"]["block_colors"] == 3 and out["blockcolor"]["blocks"] == 5 and out["blockcolor"]["ms_per_step"] == 2.0
